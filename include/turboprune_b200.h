@@ -1,0 +1,164 @@
+/*
+ * turboprune_b200 — C ABI of the B200-native (sm_100a) TurboPrune hot path.
+ *
+ * Plain C types only: device pointers as void*, sizes as int64_t / size_t, the CUDA
+ * stream as an opaque void* (a cudaStream_t / CUstream; NULL = default stream).  No
+ * torch or C++ types cross this boundary.  All device buffers are owned by the caller
+ * (the Python host keeps them as torch tensors); nothing here allocates or frees device
+ * memory except where a function says so.  Return value: 0 = ok, negative = error code
+ * (see tp_strerror).  No exceptions cross the ABI.  Functions are re-entrant across
+ * streams; the only global state is an init-once device-property / driver-entry cache.
+ *
+ * Each entry point cites the reference call site (relative to the TurboPrune repo) it
+ * replaces.  The reference has no FFI of its own (pure Python); INTEGRATION.md shows the
+ * ctypes binding a maintainer adds on the reference side.
+ */
+#ifndef TURBOPRUNE_B200_H
+#define TURBOPRUNE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- error codes -------------------------------------------------------------------- */
+#define TP_OK                 0
+#define TP_ERR_INVALID       -1   /* bad argument (null pointer, negative size, unsupported shape) */
+#define TP_ERR_WORKSPACE     -2   /* workspace too small: call the matching *_workspace_bytes */
+#define TP_ERR_CUDA          -3   /* a CUDA runtime/driver call failed (see tp_last_cuda_error) */
+#define TP_ERR_K_RANGE       -4   /* k out of [1, N] — torch.kthvalue raises for this (k == 0!) */
+#define TP_ERR_UNSUPPORTED   -5   /* valid request this build does not implement */
+#define TP_ERR_DEVICE        -6   /* not an sm_100 device */
+
+const char* tp_strerror(int code);
+const char* tp_last_cuda_error(void);      /* text of the last CUDA error seen by this thread */
+int         tp_abi_version(void);          /* bumps when a signature changes */
+int         tp_device_sm_count(void);      /* cached multiprocessor count of the current device */
+
+/* ---- score kinds (utils/pruning_utils.py) ------------------------------------------- */
+#define TP_SCORE_MAG      0   /* |m*w|      prune_mag :75, prune_random_* :109-116 (w := randn draw) */
+#define TP_SCORE_SNIP     1   /* |(g*w)*m|  prune_snip :190 */
+#define TP_SCORE_SYNFLOW  2   /* |(m*g)*w|  prune_synflow :267 */
+
+/* ---- pruning: score -> exact global k-th smallest -> mask ----------------------------
+ * Replaces, in one call, utils/pruning_utils.py:73-87 (prune_mag), :186-203 (prune_snip),
+ * :263-283 (prune_synflow): per-layer score, torch.cat, torch.kthvalue(k), torch.where.
+ *
+ *   w, g, m, mask_out : HOST arrays of n_seg DEVICE pointers (fp32; g may be NULL for
+ *                       TP_SCORE_MAG; mask_out[i] may alias nothing else; it may be NULL
+ *                       as a whole to only compute the threshold)
+ *   numel             : HOST array of n_seg element counts
+ *   k                 : 1-indexed rank, k = int((1-density)*N) computed by the caller in
+ *                       float64 exactly as the reference does; k < 1 or k > N -> TP_ERR_K_RANGE
+ *   thr_out           : DEVICE float — the k-th smallest score (bit-exact torch.kthvalue)
+ *   new mask          : mask_out[i][j] = score <= thr ? 0.f : 1.f   (ties pruned)
+ *   info_out          : optional HOST int64[4] = {path (0 bracketed single sweep, 1 exact
+ *                       3-pass radix fallback), candidates, n_lt, nan_threshold}
+ * The call synchronises the stream once (it has to learn whether the fast path held).
+ */
+size_t tp_topk_workspace_bytes(int n_seg, int64_t total_numel);
+int tp_topk_threshold_mask(const void* const* w, const void* const* g, const void* const* m,
+                           void* const* mask_out, const int64_t* numel, int n_seg,
+                           int64_t k, int score_kind, float* thr_out,
+                           void* ws, size_t ws_bytes, int64_t* info_out, void* stream);
+
+/* mask_out = score <= *thr ? 0 : 1 with a caller-supplied DEVICE threshold
+ * (utils/pruning_utils.py:84-87,140-143).  thr semantics follow fp32 compare: a NaN
+ * threshold keeps everything. */
+int tp_apply_threshold(const void* const* w, const void* const* g, const void* const* m,
+                       void* const* mask_out, const int64_t* numel, int n_seg,
+                       int score_kind, const float* thr, void* ws, size_t ws_bytes, void* stream);
+
+/* zeros_out[i] = #(m[i] == 0) for every segment plus zeros_out[n_seg] = total, one launch,
+ * no host sync (utils/custom_models.py:51-62 does 54 .item() syncs).  zeros_out: DEVICE int64[n_seg+1]. */
+int tp_count_zeros(const void* const* m, const int64_t* numel, int n_seg,
+                   int64_t* zeros_out, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- weight staging: fp32 (mask*w) -> bf16 tensor-core operand layouts ------------------
+ * Replaces the per-forward `mask * weight` (utils/mask_layers.py:25,69,109) and the autocast
+ * fp32->bf16 cast of the product: one pass writes
+ *   wf [Cout][R][S][Cin_p]  (fprop  B operand, K-major, K = (r,s,ci))  and optionally
+ *   wd [Cin_p2][R][S][Cout_p] with taps rotated by 180 deg (dgrad B operand, K = (r,s,co)).
+ * w, mask: fp32 OIHW [Cout][Cin][R][S].  Cin_p / Cout_p: channel counts padded (zero filled).
+ */
+int tp_stage_weights(const void* w, const void* mask, int cout, int cin, int r, int s,
+                     void* wf, int cin_p, void* wd, int cout_p, int cin_p2, void* stream);
+
+/* NCHW/NHWC fp32 or bf16 activation -> NHWC bf16 with channels padded to c_pad (zero fill).
+ * src_dtype: 0 = fp32, 1 = bf16.  Strides in elements. */
+int tp_to_nhwc_bf16(const void* src, int src_dtype, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
+                    int n, int c, int h, int w, void* dst, int c_pad, void* stream);
+
+/* Explicit im2col for inputs with 8 (padded) channels — the 3-channel stem conv, whose rows are
+ * too narrow for a 128-byte TMA row.  x: NHWC bf16 [n][h][w][8]; xcol: [n*p*q][kp] bf16 with
+ * column (r*S+s)*8 + c, zero for columns >= r*s*8; kp % 64 == 0.  The stem conv then runs as a
+ * plain GEMM (1x1 tp_conv_desc with cin = kp) through tp_conv_fprop / tp_conv_wgrad. */
+int tp_im2col_c8(const void* x, int n, int h, int w, int r, int s, int stride_h, int stride_w,
+                 int pad_h, int pad_w, int p, int q, void* xcol, int kp, void* stream);
+
+/* ---- masked implicit-GEMM convolution / linear on tcgen05 tensor cores -----------------
+ * Replaces F.conv2d / F.linear / F.conv1d(k=1) on the masked weight
+ * (utils/mask_layers.py:26-34, :70, :110-118) and their autograd backward.
+ * Activations are NHWC bf16 (channels_last), accumulation fp32 in TMEM.
+ *
+ * tp_conv_desc describes one convolution; linear layers are 1x1 convs with H = W = 1.
+ */
+typedef struct tp_conv_desc {
+  int32_t n, h, w, cin;          /* input  [n, h, w, cin]  (cin = padded channel count, %8 == 0) */
+  int32_t cout, r, s;            /* filter [cout, r, s, cin] */
+  int32_t stride_h, stride_w, pad_h, pad_w;
+  int32_t p, q;                  /* output [n, p, q, cout] */
+} tp_conv_desc;
+
+size_t tp_conv_workspace_bytes(const tp_conv_desc* d, int op);   /* op: 0 fprop, 1 dgrad, 2 wgrad */
+
+/* y[n,p,q,cout] (bf16) = conv(x[n,h,w,cin] (bf16), wf (bf16, tp_stage_weights layout)) + bias */
+int tp_conv_fprop(const tp_conv_desc* d, const void* x, const void* wf, const void* bias_f32,
+                  void* y, void* ws, size_t ws_bytes, void* stream);
+/* dx[n,h,w,cin] (bf16) = conv_dgrad(dy[n,p,q,cout] (bf16), wd (bf16, rotated layout)) */
+int tp_conv_dgrad(const tp_conv_desc* d, const void* dy, const void* wd,
+                  void* dx, void* ws, size_t ws_bytes, void* stream);
+/* dw[cout][cin_real][r][s] (fp32, OIHW) = mask * conv_wgrad(x, dy); db[cout] = sum dy (optional) */
+int tp_conv_wgrad(const tp_conv_desc* d, const void* x, const void* dy, const void* mask,
+                  int cin_real, void* dw, void* db, void* ws, size_t ws_bytes, void* stream);
+
+/* ---- optimizer ------------------------------------------------------------------------
+ * torch.optim.SGD(momentum, weight_decay) as configured at
+ * harness_definitions/standard_pruning_harness.py:70-75, one launch for all segments:
+ *   g += wd*w; buf = first ? g : mu*buf + g; w -= lr*buf     (masked weights keep decaying)
+ * lr is read from a DEVICE float (so LR schedules do not re-record CUDA graphs).
+ */
+int tp_sgd_momentum(void* const* w, const void* const* g, void* const* buf, const int64_t* numel,
+                    int n_seg, const float* lr_dev, float momentum, float weight_decay,
+                    int first_step, void* ws, size_t ws_bytes, void* stream);
+size_t tp_segtable_workspace_bytes(int n_seg);
+
+/* ---- gradient exchange over NVLink/NVSwitch peer memory ---------------------------------
+ * Replaces the c10d Reducer's per-bucket  grad/W -> ncclAllReduce(SUM) -> copy back
+ * (harness_definitions/base_harness.py:81) with one kernel: every rank reads its peers'
+ * bucket copies directly over NVLink, sums them in fixed rank order (bit-identical on all
+ * ranks), scales by `scale` (1/W), multiplies by an optional mask and writes `out`.
+ *
+ *   peer_bufs   : HOST array of `world` DEVICE pointers — the symmetric bucket buffer of
+ *                 every rank as mapped into THIS process (peer_bufs[rank] is the local one)
+ *   signal_pads : HOST array of `world` DEVICE pointers to uint32 signal pads (>= 4 KiB
+ *                 each, zero-initialised once); used for the cross-GPU barriers
+ *   mask        : optional fp32 mask in bucket layout (NULL = none)
+ *   algo        : 0 = one-shot pull (every rank reads all W copies), 1 = two-shot
+ *                 (reduce-scatter of shards + all-gather, via the same symmetric buffers)
+ *   timeout_ms  : bounded spin on the barrier; on expiry the kernel sets *status_dev != 0
+ *                 (optional DEVICE int) instead of hanging
+ */
+int tp_p2p_allreduce_mask(void* const* peer_bufs, void* const* signal_pads, int rank, int world,
+                          int64_t numel, const void* mask, float scale, void* out,
+                          int algo, int timeout_ms, int* status_dev, void* stream);
+
+/* ---- development probes (used by tests/ and tools/, not by the training path) ---------- */
+int tp_probe_run(int which, void* out, size_t out_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TURBOPRUNE_B200_H */

@@ -1,0 +1,80 @@
+// Error plumbing, device cache and the segment-table upload shared by all kernels.
+#include "tp_common.cuh"
+#include <string.h>
+#include <vector>
+
+namespace tp {
+
+static thread_local char g_last_err[512] = "";
+
+void set_last_cuda_error(cudaError_t e, const char* where) {
+  snprintf(g_last_err, sizeof(g_last_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  if (cached[dev] == 0) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;
+  }
+  return cached[dev];
+}
+
+int upload_segs(Arena& ar, const void* const* w, const void* const* g, const void* const* m,
+                void* const* mo, void* const* buf, const int64_t* numel, int n_seg,
+                Seg** dev_out, long long* tiles_out, long long* total_out, cudaStream_t st) {
+  if (n_seg <= 0 || !numel) return TP_ERR_INVALID;
+  std::vector<Seg> h(n_seg);
+  long long start = 0, tile = 0;
+  for (int i = 0; i < n_seg; ++i) {
+    if (numel[i] < 0) return TP_ERR_INVALID;
+    h[i].w = w ? (const float*)w[i] : nullptr;
+    h[i].g = g ? (const float*)g[i] : nullptr;
+    h[i].m = m ? (const float*)m[i] : nullptr;
+    h[i].mo = mo ? (float*)mo[i] : nullptr;
+    h[i].buf = buf ? (float*)buf[i] : nullptr;
+    h[i].n = numel[i];
+    h[i].start = start;
+    h[i].tile0 = tile;
+    start += numel[i];
+    tile += (numel[i] + kTileElems - 1) / kTileElems;
+  }
+  Seg* d = (Seg*)ar.take(sizeof(Seg) * n_seg);
+  if (!d) return TP_ERR_WORKSPACE;
+  // pageable source: the runtime stages the bytes before returning, so `h` may die.
+  TP_CUDA_CHECK(cudaMemcpyAsync(d, h.data(), sizeof(Seg) * n_seg, cudaMemcpyHostToDevice, st));
+  *dev_out = d;
+  if (tiles_out) *tiles_out = tile;
+  if (total_out) *total_out = start;
+  return TP_OK;
+}
+
+}  // namespace tp
+
+extern "C" {
+
+const char* tp_strerror(int code) {
+  switch (code) {
+    case TP_OK: return "ok";
+    case TP_ERR_INVALID: return "invalid argument";
+    case TP_ERR_WORKSPACE: return "workspace too small";
+    case TP_ERR_CUDA: return "CUDA error (see tp_last_cuda_error)";
+    case TP_ERR_K_RANGE: return "kthvalue(): selected number k out of range";
+    case TP_ERR_UNSUPPORTED: return "unsupported configuration";
+    case TP_ERR_DEVICE: return "device is not sm_100 (B200)";
+    default: return "unknown error";
+  }
+}
+
+const char* tp_last_cuda_error(void) { return tp::g_last_err; }
+int tp_abi_version(void) { return 1; }
+int tp_device_sm_count(void) { return tp::sm_count(); }
+
+size_t tp_segtable_workspace_bytes(int n_seg) {
+  return tp::align_up(sizeof(tp::Seg) * (size_t)(n_seg > 0 ? n_seg : 1), 256) + 256;
+}
+
+}  // extern "C"

@@ -1,0 +1,723 @@
+// Masked implicit-GEMM convolution / linear for sm_100a: TMA (tiled + im2col) -> 128B-swizzled
+// shared memory -> tcgen05.mma (bf16 x bf16 -> fp32 in TMEM) -> tcgen05.ld epilogue.
+//
+// Replaces F.conv2d / F.linear / F.conv1d(k=1) on the masked weight and their autograd
+// backward (utils/mask_layers.py:26-34, :70, :110-118 of the reference).  The mask never
+// appears here as a separate pass: fprop/dgrad consume bf16 weights that were masked while
+// being staged (tp_stage_weights), wgrad applies the mask in its finalize step.
+//
+// Two persistent, warp-specialised kernels (1 CTA / SM, 192 threads):
+//   warp 0     : TMA producer (one elected lane)
+//   warp 1     : TMEM allocator + tcgen05.mma issuer (one elected lane)
+//   warps 2..5 : epilogue (TMEM -> registers -> global), one TMEM lane quarter each
+//
+//   k_igemm_fwd  : D[pixels, Cout] = A[pixels, K] * W[Cout, K]^T          (fprop, dgrad)
+//                  A tile 128 pixels x 64 channels by TMA im2col (any r,s,stride,pad) or by
+//                  a plain 2-D TMA box (1x1/s1 convs, linear); both K-major, SWIZZLE_128B.
+//   k_igemm_wgrad: D[Cout, (tap,cin)] = dY^T[Cout, pixels] * Xcol[pixels, (tap,cin)]
+//                  contraction over pixels: both operands MN-major, SWIZZLE_128B; split-K
+//                  partials in fp32, summed in fixed order + masked + permuted to OIHW by
+//                  k_wgrad_finalize (deterministic, no atomics).
+#include "tp_common.cuh"
+#include "tp_ptx.cuh"
+#include <cuda.h>
+#include <mutex>
+
+namespace tp {
+using namespace ptx;
+
+constexpr int kBlockM = 128;         // UMMA M
+constexpr int kBlockK = 64;          // 64 bf16 = 128 B = one swizzle row
+constexpr int kThreads = 192;
+constexpr int kMaxTaps = 64;
+
+struct TapEntry { uint16_t off_w, off_h; int32_t kofs; };
+
+struct FwdParams {
+  int M, N;                 // iteration pixels, output channels
+  int P_it, Q_it;           // iteration grid per image (M = n_img * P_it * Q_it)
+  int cchunks, ntaps;       // K loop = ntaps x cchunks blocks of 64 channels
+  int a_mode;               // 0: tiled 2-D A[M, K];  1: im2col 4-D
+  int base_w, base_h, step_w, step_h;   // im2col coordinate of iteration pixel (p,q): base + q*step
+  long long out_img_pix;    // output pixels per image
+  int out_row_pix;          // output pixels per row
+  int osh, oah, osw, oaw;   // output pixel = (p*osh+oah, q*osw+oaw)
+  int ldc;                  // elements between consecutive output pixels
+  __nv_bfloat16* out;
+  const float* bias;
+  TapEntry taps[kMaxTaps];
+};
+
+struct WgParams {
+  int Mc;                   // Cout
+  int Kpix;                 // contraction length = n_img * P_it * Q_it (dY pixels)
+  int P_it, Q_it;
+  int chunks, cchunks;      // N axis = chunks of 64 K-columns; chunk -> (tap = chunk / cchunks, cc = chunk % cchunks)
+  int nb;                   // chunks per N tile (1..4)
+  int b_mode;               // 0: tiled 2-D Xcol[pixels, Kcols];  1: im2col over X
+  int base_w, base_h, step_w, step_h;
+  int m_tiles, n_tiles, splits, kb_per_split, kblocks;
+  float* partial;           // [m_tiles*n_tiles*splits][128][nb*64]
+  TapEntry taps[kMaxTaps];
+};
+
+__device__ __forceinline__ void decompose_pixel(int m, int P, int Q, int& n, int& p, int& q) {
+  q = m % Q; int t = m / Q; p = t % P; n = t / P;
+}
+
+// ============================================================================================
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ FwdParams p) {
+  constexpr int kABytes = kBlockM * kBlockK * 2;           // 16 KB
+  constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  constexpr int kStageBytes = kABytes + kBBytes;
+  constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
+  constexpr int kAccStages = 2;
+  constexpr uint32_t kTmemCols = (kAccStages * BLOCK_N <= 32) ? 32 : (kAccStages * BLOCK_N <= 64) ? 64 :
+                                 (kAccStages * BLOCK_N <= 128) ? 128 : (kAccStages * BLOCK_N <= 256) ? 256 : 512;
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* tempty_bar = tfull_bar + kAccStages;
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + kAccStages);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m_tiles = (p.M + kBlockM - 1) / kBlockM;
+  const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int total_tiles = m_tiles * n_tiles;
+  const int kiters = p.ntaps * p.cchunks;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < kAccStages; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_t = tile / m_tiles, m_t = tile % m_tiles;
+        const int m0 = m_t * kBlockM;
+        int cn = 0, cp = 0, cq = 0;
+        if (p.a_mode == 1) decompose_pixel(m0, p.P_it, p.Q_it, cn, cp, cq);
+        const int cw = p.base_w + cq * p.step_w, ch = p.base_h + cp * p.step_h;
+        for (int it = 0; it < kiters; ++it) {
+          const int tap = it / p.cchunks, cc = it - tap * p.cchunks;
+          mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+          mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+          uint8_t* sA = smem + stage * kStageBytes;
+          uint8_t* sB = sA + kABytes;
+          if (p.a_mode == 1)
+            tma_load_im2col_4d(sA, &tmA, &full_bar[stage], cc * kBlockK, cw, ch, cn, p.taps[tap].off_w, p.taps[tap].off_h);
+          else
+            tma_load_2d(sA, &tmA, &full_bar[stage], p.taps[tap].kofs + cc * kBlockK, m0);
+          tma_load_2d(sB, &tmB, &full_bar[stage], p.taps[tap].kofs + cc * kBlockK, n_t * BLOCK_N);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer ------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
+        for (int it = 0; it < kiters; ++it) {
+          mbar_wait(&full_bar[stage], phase, 3);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
+          const uint32_t b_addr = a_addr + kABytes;
+          const uint64_t adesc = make_smem_desc(a_addr, 16, 1024, kLayoutSW128);
+          const uint64_t bdesc = make_smem_desc(b_addr, 16, 1024, kLayoutSW128);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in 16-B units
+            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0);
+          }
+          umma_commit(&empty_bar[stage]);     // frees this smem stage when the MMAs have read it
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);         // accumulator complete -> epilogue
+        if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue ------------------------------
+    const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_t = tile / m_tiles, m_t = tile % m_tiles;
+      const int row = m_t * kBlockM + quarter * 32 + lane;
+      const bool row_ok = row < p.M;
+      long long opix = 0;
+      if (row_ok) {
+        int n, pp, qq; decompose_pixel(row, p.P_it, p.Q_it, n, pp, qq);
+        opix = (long long)n * p.out_img_pix + (long long)(pp * p.osh + p.oah) * p.out_row_pix + (qq * p.osw + p.oaw);
+      }
+      __nv_bfloat16* orow = p.out + opix * p.ldc;
+      mbar_wait(&tfull_bar[acc], acc_phase, 4);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_base + (uint32_t)c, v);
+        tmem_ld_wait();
+        const int n0 = n_t * BLOCK_N + c;
+        if (row_ok && n0 < p.N) {
+          float f[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (n0 + j < p.N) f[j] += p.bias[n0 + j];
+          }
+          __nv_bfloat16* dst = orow + n0;
+          if (n0 + 32 <= p.N && (((uintptr_t)dst) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]);
+              __nv_bfloat162 h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
+              __nv_bfloat162 h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+              uint4 pk;
+              pk.x = *(uint32_t*)&h0; pk.y = *(uint32_t*)&h1; pk.z = *(uint32_t*)&h2; pk.w = *(uint32_t*)&h3;
+              *(uint4*)(dst + j) = pk;
+            }
+          } else {
+            for (int j = 0; j < 32; ++j) if (n0 + j < p.N) dst[j] = __float2bfloat16_rn(f[j]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+}
+
+// ============================================================================================
+__global__ void __launch_bounds__(kThreads, 1)
+k_igemm_wgrad(const __grid_constant__ CUtensorMap tmA /* dY [Kpix, Cout] */,
+              const __grid_constant__ CUtensorMap tmB /* X im2col or Xcol tiled */,
+              const __grid_constant__ WgParams p) {
+  constexpr int kABytes = kBlockM * kBlockK * 2;          // 2 boxes of [64 pixels x 64 couts] = 16 KB
+  constexpr int kChunkBytes = 64 * kBlockK * 2;           // 8 KB per 64-column chunk
+  constexpr int kMaxNb = 4;
+  constexpr int kStageBytes = kABytes + kMaxNb * kChunkBytes;   // 48 KB
+  constexpr int kStages = 4;
+  constexpr uint32_t kTmemCols = 512;                     // 2 accumulator stages x 256 columns
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int items = p.m_tiles * p.n_tiles * p.splits;
+  const int ncols = p.nb * 64;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    fence_mbar_init();
+  }
+  if (warp == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int split = item % p.splits, tile = item / p.splits;
+        const int n_t = tile / p.m_tiles, m_t = tile % p.m_tiles;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
+        const int chunk0 = n_t * p.nb;
+        const int nvalid = min(p.nb, p.chunks - chunk0);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          const int pix0 = kb * kBlockK;
+          mbar_wait(&empty_bar[stage], phase ^ 1, 11);
+          mbar_arrive_expect_tx(&full_bar[stage], kABytes + nvalid * kChunkBytes);
+          uint8_t* sA = smem + stage * kStageBytes;
+          uint8_t* sB = sA + kABytes;
+          tma_load_2d(sA, &tmA, &full_bar[stage], m_t * kBlockM, pix0);
+          tma_load_2d(sA + kChunkBytes, &tmA, &full_bar[stage], m_t * kBlockM + 64, pix0);
+          if (p.b_mode == 1) {
+            int cn, cp, cq; decompose_pixel(pix0, p.P_it, p.Q_it, cn, cp, cq);
+            const int cw = p.base_w + cq * p.step_w, ch = p.base_h + cp * p.step_h;
+            for (int j = 0; j < nvalid; ++j) {
+              const int chunk = chunk0 + j, tap = chunk / p.cchunks, cc = chunk - tap * p.cchunks;
+              tma_load_im2col_4d(sB + j * kChunkBytes, &tmB, &full_bar[stage], cc * 64, cw, ch, cn,
+                                 p.taps[tap].off_w, p.taps[tap].off_h);
+            }
+          } else {
+            for (int j = 0; j < nvalid; ++j)
+              tma_load_2d(sB + j * kChunkBytes, &tmB, &full_bar[stage], (chunk0 + j) * 64, pix0);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_bf16(kBlockM, ncols, 1, 1);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int split = item % p.splits;
+        const int kb0 = split * p.kb_per_split;
+        const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 12);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * 256);
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(&full_bar[stage], phase, 13);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
+          const uint32_t b_addr = a_addr + kABytes;
+          // MN-major SW128: 64 MN elements per 128-B row, 8 K rows per 1024-B atom (SBO),
+          // next 64-wide MN block at LBO = 64 rows * 128 B
+          const uint64_t adesc = make_smem_desc(a_addr, kChunkBytes, 1024, kLayoutSW128);
+          const uint64_t bdesc = make_smem_desc(b_addr, kChunkBytes, 1024, kLayoutSW128);
+#pragma unroll
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // 16 K rows = 2 swizzle atoms = 2048 B
+            umma_bf16(d_tmem, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), idesc, (kb > kb0 || k > 0));
+          }
+          umma_commit(&empty_bar[stage]);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+      float* prow = p.partial + ((long long)item * kBlockM + quarter * 32 + lane) * ncols;
+      mbar_wait(&tfull_bar[acc], acc_phase, 14);
+      tc_fence_after();
+      const uint32_t t_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
+#pragma unroll 1
+      for (int c = 0; c < ncols; c += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32(t_base + (uint32_t)c, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4)
+          *(uint4*)(prow + c + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+}
+
+// dW[co][ci][tap] (fp32 OIHW) = mask * sum_split partial   — fixed summation order.
+// One CTA per output channel; K index kk = tap*cin_p + ci is the column of the partial tiles.
+__global__ void __launch_bounds__(256) k_wgrad_finalize(const float* __restrict__ partial, const float* __restrict__ mask,
+                                                        float* __restrict__ dw, int cout, int cin_real, int cin_p, int rs,
+                                                        int nb, int m_tiles, int n_tiles, int splits) {
+  extern __shared__ float s_row[];      // [rs * cin_p] when rs > 1
+  const int co = blockIdx.x;
+  const int m_t = co / kBlockM, r = co % kBlockM;
+  const int ktot = rs * cin_p;
+  const int ncols = nb * 64;
+  const long long obase = (long long)co * cin_real * rs;
+  for (int kk = threadIdx.x; kk < ktot; kk += blockDim.x) {
+    const int chunk = kk >> 6, n_t = chunk / nb, col = (chunk - n_t * nb) * 64 + (kk & 63);
+    const long long item0 = ((long long)n_t * m_tiles + m_t) * splits;
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += partial[((item0 + s) * kBlockM + r) * ncols + col];
+    if (rs == 1) {
+      if (kk < cin_real) dw[obase + kk] = mask[obase + kk] * acc;
+    } else {
+      s_row[kk] = acc;
+    }
+  }
+  if (rs > 1) {
+    __syncthreads();
+    const int nout = cin_real * rs;
+    for (int o = threadIdx.x; o < nout; o += blockDim.x) {
+      const int ci = o / rs, tap = o - ci * rs;
+      dw[obase + o] = mask[obase + o] * s_row[tap * cin_p + ci];
+    }
+  }
+}
+
+// db[c] = sum over pixels of dy[pix][c]  (bias gradient), dy bf16 [npix, ldc]
+__global__ void __launch_bounds__(256) k_colsum(const __nv_bfloat16* __restrict__ dy, long long npix, int c, int ldc,
+                                                float* __restrict__ db) {
+  // one CTA per 32 channels; threads (32 x 8): 8 pixel lanes, fixed-order tree -> deterministic
+  __shared__ float s[8][33];
+  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
+  const int ch = blockIdx.x * 32 + cx;
+  float acc = 0.f;
+  if (ch < c) for (long long i = py; i < npix; i += 8) acc += __bfloat162float(dy[i * ldc + ch]);
+  s[py][cx] = acc;
+  __syncthreads();
+  if (py == 0 && ch < c) {
+    float t = 0.f;
+    for (int j = 0; j < 8; ++j) t += s[j][cx];
+    db[ch] = t;
+  }
+}
+
+// ============================================================================================
+// host side
+// ============================================================================================
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+typedef CUresult (*PFN_encodeIm2col)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                     const int*, const int*, cuuint32_t, cuuint32_t, const cuuint32_t*, CUtensorMapInterleave,
+                                     CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled g_encodeTiled = nullptr;
+static PFN_encodeIm2col g_encodeIm2col = nullptr;
+static int g_driver_version = 0;
+
+static int load_driver_fns() {
+  static std::once_flag once;
+  static int rc = TP_OK;
+  std::call_once(once, []() {
+    void* f1 = nullptr; void* f2 = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f1, cudaEnableDefault, &q) != cudaSuccess || !f1 ||
+        cudaGetDriverEntryPoint("cuTensorMapEncodeIm2col", &f2, cudaEnableDefault, &q) != cudaSuccess || !f2) {
+      set_last_cuda_error(cudaErrorUnknown, "cudaGetDriverEntryPoint(cuTensorMapEncode*)");
+      rc = TP_ERR_CUDA;
+      return;
+    }
+    g_encodeTiled = (PFN_encodeTiled)f1;
+    g_encodeIm2col = (PFN_encodeIm2col)f2;
+    cudaDriverGetVersion(&g_driver_version);
+  });
+  return rc;
+}
+
+static int fail_cu(CUresult r, const char* what) {
+  static thread_local char buf[128];
+  snprintf(buf, sizeof(buf), "%s -> CUresult %d", what, (int)r);
+  set_last_cuda_error(cudaErrorInvalidValue, buf);
+  return TP_ERR_CUDA;
+}
+
+// 2-D bf16 tensor [rows][cols] (cols contiguous, row stride ld elements), box = [box_rows][64 cols], SW128.
+static int make_tiled_map(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_rows) {
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld_elems * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = g_encodeTiled(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, es,
+                             CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                             CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail_cu(r, "cuTensorMapEncodeTiled");
+  return TP_OK;
+}
+
+// im2col map over NHWC bf16 [n][h][w][c]: `pixels` consecutive iteration positions x 64 channels.
+// Iteration grid (P_it x Q_it per image) starts at (base_h, base_w) and advances by (step_h, step_w).
+static int make_im2col_map(CUtensorMap* m, const void* ptr, int n, int h, int w, int c,
+                           int base_w, int base_h, int step_w, int step_h, int P_it, int Q_it, uint32_t pixels) {
+  cuuint64_t dims[4] = {(cuuint64_t)c, (cuuint64_t)w, (cuuint64_t)h, (cuuint64_t)n};
+  cuuint64_t strides[3] = {(cuuint64_t)c * 2, (cuuint64_t)w * c * 2, (cuuint64_t)h * w * c * 2};
+  // bounding box: base positions run from `lower` while < extent + upper  =>  count = Q_it
+  int lower[2] = {base_w, base_h};
+  int upper[2] = {(Q_it - 1) * step_w + 1 + base_w - w, (P_it - 1) * step_h + 1 + base_h - h};
+  cuuint32_t es[4] = {1, (cuuint32_t)step_w, (cuuint32_t)step_h, 1};
+  CUresult r = g_encodeIm2col(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, lower, upper,
+                              64, pixels, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail_cu(r, "cuTensorMapEncodeIm2col");
+  // Driver quirk (CUDA <= 13.1 drivers, see CUTLASS copy_traits_sm90_im2col.hpp): for tensors
+  // smaller than 128 KiB bit 21 of the second descriptor word must be cleared.
+  if (g_driver_version <= 13010 && (size_t)n * h * w * c * 2 < 131072)
+    reinterpret_cast<uint64_t*>(m)[1] &= ~(1ull << 21);
+  return TP_OK;
+}
+
+static bool is_plain_gemm(const tp_conv_desc* d) {
+  return d->r == 1 && d->s == 1 && d->stride_h == 1 && d->stride_w == 1 && d->pad_h == 0 && d->pad_w == 0;
+}
+
+static int pick_block_n(long long m_tiles, int n) {
+  // favour wide tiles (fewer re-reads of the activation tile), but keep the last wave full
+  const int sms = sm_count();
+  int best = 64; double best_score = -1;
+  const int cands[3] = {256, 128, 64};
+  const double weight[3] = {1.0, 0.92, 0.75};
+  for (int i = 0; i < 3; ++i) {
+    int bn = cands[i];
+    if (bn > 64 && n <= bn / 2) continue;
+    long long tiles = m_tiles * ((n + bn - 1) / bn);
+    long long waves = (tiles + sms - 1) / sms;
+    double eff = (double)tiles / (double)(waves * sms) * weight[i];
+    if (eff > best_score) { best_score = eff; best = bn; }
+  }
+  return best;
+}
+
+template <int BN>
+static int launch_fwd(const CUtensorMap& a, const CUtensorMap& b, const FwdParams& p, cudaStream_t st) {
+  constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
+  constexpr int smem = kStages * (kBlockM * kBlockK * 2 + BN * kBlockK * 2) + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TP_CUDA_CHECK(cudaFuncSetAttribute(k_igemm_fwd<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_set = true;
+  }
+  const long long tiles = (long long)((p.M + kBlockM - 1) / kBlockM) * ((p.N + BN - 1) / BN);
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
+  k_igemm_fwd<BN><<<grid, kThreads, smem, st>>>(a, b, p);
+  TP_LAUNCH_CHECK();
+  return TP_OK;
+}
+
+static int run_fwd(const CUtensorMap& a, const CUtensorMap& b, const FwdParams& p, cudaStream_t st) {
+  const int bn = pick_block_n((p.M + kBlockM - 1) / kBlockM, p.N);
+  if (bn == 256) return launch_fwd<256>(a, b, p, st);
+  if (bn == 128) return launch_fwd<128>(a, b, p, st);
+  return launch_fwd<64>(a, b, p, st);
+}
+
+}  // namespace tp
+
+using namespace tp;
+
+extern "C" {
+
+size_t tp_conv_workspace_bytes(const tp_conv_desc* d, int op) {
+  if (!d) return 0;
+  if (op != 2) return 256;
+  // wgrad: split-K partial tiles
+  const int cin_p = d->cin;
+  const int ktot = ((d->r * d->s * cin_p) + 63) / 64 * 64;
+  const int chunks = ktot / 64;
+  const int nb = chunks >= 4 ? 4 : chunks;
+  const int m_tiles = (d->cout + kBlockM - 1) / kBlockM;
+  const int n_tiles = (chunks + nb - 1) / nb;
+  const long long kpix = (long long)d->n * d->p * d->q;
+  const int kblocks = (int)((kpix + 63) / 64);
+  const int sms = sm_count();
+  int splits = (2 * sms + m_tiles * n_tiles - 1) / (m_tiles * n_tiles);
+  if (splits > kblocks) splits = kblocks;
+  if (splits < 1) splits = 1;
+  return (size_t)m_tiles * n_tiles * splits * kBlockM * nb * 64 * sizeof(float) + 1024;
+}
+
+int tp_conv_fprop(const tp_conv_desc* d, const void* x, const void* wf, const void* bias_f32,
+                  void* y, void* ws, size_t ws_bytes, void* stream) {
+  (void)ws; (void)ws_bytes;
+  if (!d || !x || !wf || !y) return TP_ERR_INVALID;
+  if (d->cin % 8 != 0 || d->r * d->s > kMaxTaps) return TP_ERR_UNSUPPORTED;
+  if (d->r * d->s > 1 && d->cin % 64 != 0) return TP_ERR_UNSUPPORTED;
+  int rc = load_driver_fns(); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  FwdParams p = {};
+  p.M = d->n * d->p * d->q; p.N = d->cout;
+  p.P_it = d->p; p.Q_it = d->q;
+  p.cchunks = (d->cin + 63) / 64; p.ntaps = d->r * d->s;
+  p.out_img_pix = (long long)d->p * d->q; p.out_row_pix = d->q;
+  p.osh = 1; p.oah = 0; p.osw = 1; p.oaw = 0;
+  p.ldc = d->cout; p.out = (__nv_bfloat16*)y; p.bias = (const float*)bias_f32;
+  for (int r = 0; r < d->r; ++r) for (int s = 0; s < d->s; ++s) {
+    TapEntry& t = p.taps[r * d->s + s];
+    t.off_w = (uint16_t)s; t.off_h = (uint16_t)r; t.kofs = (r * d->s + s) * d->cin;
+  }
+  CUtensorMap ta, tb;
+  if (is_plain_gemm(d)) {
+    p.a_mode = 0;
+    rc = make_tiled_map(&ta, x, (uint64_t)d->cin, (uint64_t)p.M, (uint64_t)d->cin, kBlockM); if (rc) return rc;
+  } else {
+    p.a_mode = 1;
+    p.base_w = -d->pad_w; p.base_h = -d->pad_h; p.step_w = d->stride_w; p.step_h = d->stride_h;
+    rc = make_im2col_map(&ta, x, d->n, d->h, d->w, d->cin, p.base_w, p.base_h, p.step_w, p.step_h, d->p, d->q, kBlockM);
+    if (rc) return rc;
+  }
+  const int bn = pick_block_n((p.M + kBlockM - 1) / kBlockM, p.N);
+  rc = make_tiled_map(&tb, wf, (uint64_t)d->r * d->s * d->cin, (uint64_t)d->cout, (uint64_t)d->r * d->s * d->cin, (uint32_t)bn);
+  if (rc) return rc;
+  return run_fwd(ta, tb, p, st);
+}
+
+int tp_conv_dgrad(const tp_conv_desc* d, const void* dy, const void* wd,
+                  void* dx, void* ws, size_t ws_bytes, void* stream) {
+  (void)ws; (void)ws_bytes;
+  if (!d || !dy || !wd || !dx) return TP_ERR_INVALID;
+  // here the contraction runs over (r', s', cout): channel count of dY must be TMA friendly
+  const int cop = d->cout;                       // caller passes dY with cout % 8 == 0 (padded if needed)
+  if (cop % 8 != 0 || d->r * d->s > kMaxTaps) return TP_ERR_UNSUPPORTED;
+  if (d->r * d->s > 1 && cop % 64 != 0) return TP_ERR_UNSUPPORTED;
+  int rc = load_driver_fns(); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int R = d->r, S = d->s;
+  const long long ktot = (long long)R * S * cop;
+  if (d->stride_h == 1 && d->stride_w == 1) {
+    // dX = conv(dY, rot180(W)^T) with padding (R-1-pad): wd is stored already rotated
+    FwdParams p = {};
+    p.M = d->n * d->h * d->w; p.N = d->cin;
+    p.P_it = d->h; p.Q_it = d->w;
+    p.cchunks = (cop + 63) / 64; p.ntaps = R * S;
+    p.out_img_pix = (long long)d->h * d->w; p.out_row_pix = d->w;
+    p.osh = 1; p.oah = 0; p.osw = 1; p.oaw = 0;
+    p.ldc = d->cin; p.out = (__nv_bfloat16*)dx; p.bias = nullptr;
+    for (int r = 0; r < R; ++r) for (int s = 0; s < S; ++s) {
+      TapEntry& t = p.taps[r * S + s];
+      t.off_w = (uint16_t)s; t.off_h = (uint16_t)r; t.kofs = (r * S + s) * cop;
+    }
+    CUtensorMap ta, tb;
+    if (is_plain_gemm(d)) {
+      p.a_mode = 0;
+      rc = make_tiled_map(&ta, dy, (uint64_t)cop, (uint64_t)p.M, (uint64_t)cop, kBlockM); if (rc) return rc;
+    } else {
+      p.a_mode = 1;
+      p.base_w = -(S - 1 - d->pad_w); p.base_h = -(R - 1 - d->pad_h); p.step_w = 1; p.step_h = 1;
+      rc = make_im2col_map(&ta, dy, d->n, d->p, d->q, cop, p.base_w, p.base_h, 1, 1, d->h, d->w, kBlockM);
+      if (rc) return rc;
+    }
+    const int bn = pick_block_n((p.M + kBlockM - 1) / kBlockM, p.N);
+    rc = make_tiled_map(&tb, wd, (uint64_t)ktot, (uint64_t)d->cin, (uint64_t)ktot, (uint32_t)bn); if (rc) return rc;
+    return run_fwd(ta, tb, p, st);
+  }
+  // strided conv: decompose dX into stride_h x stride_w parity classes; each class is a
+  // stride-1 gather over dY with its own subset of taps, scattered to every stride-th pixel.
+  const int sh = d->stride_h, sw = d->stride_w;
+  TP_CUDA_CHECK(cudaMemsetAsync(dx, 0, (size_t)d->n * d->h * d->w * d->cin * 2, st));
+  for (int a = 0; a < sh; ++a) for (int b = 0; b < sw; ++b) {
+    const int Hc = (d->h - a + sh - 1) / sh, Wc = (d->w - b + sw - 1) / sw;   // pixels of this class
+    if (Hc <= 0 || Wc <= 0) continue;
+    // taps: input row h = sh*h' + a receives dY row p = h' + (a + pad - r)/sh when divisible
+    int dh_min = 1 << 30, dw_min = 1 << 30, nt = 0;
+    for (int r = 0; r < R; ++r) if ((a + d->pad_h - r) % sh == 0) dh_min = min(dh_min, (a + d->pad_h - r) / sh);
+    for (int s = 0; s < S; ++s) if ((b + d->pad_w - s) % sw == 0) dw_min = min(dw_min, (b + d->pad_w - s) / sw);
+    if (dh_min == (1 << 30) || dw_min == (1 << 30)) continue;     // no tap reaches this class: stays zero
+    FwdParams p = {};
+    p.M = d->n * Hc * Wc; p.N = d->cin;
+    p.P_it = Hc; p.Q_it = Wc;
+    p.cchunks = (cop + 63) / 64;
+    p.a_mode = 1;
+    p.base_w = dw_min; p.base_h = dh_min; p.step_w = 1; p.step_h = 1;
+    p.out_img_pix = (long long)d->h * d->w; p.out_row_pix = d->w;
+    p.osh = sh; p.oah = a; p.osw = sw; p.oaw = b;
+    p.ldc = d->cin; p.out = (__nv_bfloat16*)dx; p.bias = nullptr;
+    for (int r = 0; r < R; ++r) {
+      if ((a + d->pad_h - r) % sh != 0) continue;
+      for (int s = 0; s < S; ++s) {
+        if ((b + d->pad_w - s) % sw != 0) continue;
+        TapEntry& t = p.taps[nt++];
+        t.off_h = (uint16_t)((a + d->pad_h - r) / sh - dh_min);
+        t.off_w = (uint16_t)((b + d->pad_w - s) / sw - dw_min);
+        // wd stores tap (r,s) at rotated position (R-1-r, S-1-s)
+        t.kofs = ((R - 1 - r) * S + (S - 1 - s)) * cop;
+      }
+    }
+    p.ntaps = nt;
+    CUtensorMap ta, tb;
+    rc = make_im2col_map(&ta, dy, d->n, d->p, d->q, cop, p.base_w, p.base_h, 1, 1, Hc, Wc, kBlockM); if (rc) return rc;
+    const int bn = pick_block_n((p.M + kBlockM - 1) / kBlockM, p.N);
+    rc = make_tiled_map(&tb, wd, (uint64_t)ktot, (uint64_t)d->cin, (uint64_t)ktot, (uint32_t)bn); if (rc) return rc;
+    rc = run_fwd(ta, tb, p, st); if (rc) return rc;
+  }
+  return TP_OK;
+}
+
+int tp_conv_wgrad(const tp_conv_desc* d, const void* x, const void* dy, const void* mask,
+                  int cin_real, void* dw, void* db, void* ws, size_t ws_bytes, void* stream) {
+  if (!d || !x || !dy || !mask || !dw || !ws) return TP_ERR_INVALID;
+  if (d->cin % 8 != 0 || d->cout % 8 != 0 || d->r * d->s > kMaxTaps || cin_real > d->cin) return TP_ERR_UNSUPPORTED;
+  if (d->r * d->s > 1 && d->cin % 64 != 0) return TP_ERR_UNSUPPORTED;
+  int rc = load_driver_fns(); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rs = d->r * d->s;
+  WgParams p = {};
+  p.Mc = d->cout;
+  p.Kpix = d->n * d->p * d->q;
+  p.P_it = d->p; p.Q_it = d->q;
+  const int ktot = (rs * d->cin + 63) / 64 * 64;
+  p.chunks = ktot / 64;
+  p.cchunks = (d->cin + 63) / 64;
+  p.nb = p.chunks >= 4 ? 4 : p.chunks;
+  p.m_tiles = (d->cout + kBlockM - 1) / kBlockM;
+  p.n_tiles = (p.chunks + p.nb - 1) / p.nb;
+  p.kblocks = (p.Kpix + 63) / 64;
+  const int sms = sm_count();
+  int splits = (2 * sms + p.m_tiles * p.n_tiles - 1) / (p.m_tiles * p.n_tiles);
+  if (splits > p.kblocks) splits = p.kblocks;
+  if (splits < 1) splits = 1;
+  p.kb_per_split = (p.kblocks + splits - 1) / splits;
+  splits = (p.kblocks + p.kb_per_split - 1) / p.kb_per_split;     // no empty splits
+  p.splits = splits;
+  const size_t need = (size_t)p.m_tiles * p.n_tiles * splits * kBlockM * p.nb * 64 * sizeof(float);
+  if (ws_bytes < need) return TP_ERR_WORKSPACE;
+  p.partial = (float*)ws;
+  for (int r = 0; r < d->r; ++r) for (int s = 0; s < d->s; ++s) {
+    TapEntry& t = p.taps[r * d->s + s];
+    t.off_w = (uint16_t)s; t.off_h = (uint16_t)r; t.kofs = (r * d->s + s) * d->cin;
+  }
+  CUtensorMap ta, tb;
+  rc = make_tiled_map(&ta, dy, (uint64_t)d->cout, (uint64_t)p.Kpix, (uint64_t)d->cout, 64); if (rc) return rc;
+  if (is_plain_gemm(d)) {
+    p.b_mode = 0;
+    rc = make_tiled_map(&tb, x, (uint64_t)d->cin, (uint64_t)p.Kpix, (uint64_t)d->cin, 64); if (rc) return rc;
+  } else {
+    p.b_mode = 1;
+    p.base_w = -d->pad_w; p.base_h = -d->pad_h; p.step_w = d->stride_w; p.step_h = d->stride_h;
+    rc = make_im2col_map(&tb, x, d->n, d->h, d->w, d->cin, p.base_w, p.base_h, p.step_w, p.step_h, d->p, d->q, 64);
+    if (rc) return rc;
+  }
+  constexpr int smem = 4 * (kBlockM * kBlockK * 2 + 4 * 64 * kBlockK * 2) + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    TP_CUDA_CHECK(cudaFuncSetAttribute(k_igemm_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TP_CUDA_CHECK(cudaFuncSetAttribute(k_wgrad_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+    attr_set = true;
+  }
+  const int items = p.m_tiles * p.n_tiles * splits;
+  k_igemm_wgrad<<<items < sms ? items : sms, kThreads, smem, st>>>(ta, tb, p);
+  TP_LAUNCH_CHECK();
+  const size_t fin_smem = rs > 1 ? (size_t)rs * d->cin * sizeof(float) : 0;
+  if (fin_smem > 64 * 1024) return TP_ERR_UNSUPPORTED;
+  k_wgrad_finalize<<<d->cout, 256, fin_smem, st>>>(p.partial, (const float*)mask, (float*)dw, d->cout, cin_real, d->cin, rs,
+                                                    p.nb, p.m_tiles, p.n_tiles, splits);
+  TP_LAUNCH_CHECK();
+  if (db) {
+    k_colsum<<<(d->cout + 31) / 32, 256, 0, st>>>((const __nv_bfloat16*)dy, (long long)p.Kpix, d->cout, d->cout, (float*)db);
+    TP_LAUNCH_CHECK();
+  }
+  return TP_OK;
+}
+
+}  // extern "C"

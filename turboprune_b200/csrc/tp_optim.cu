@@ -1,0 +1,220 @@
+// Weight staging (mask*w -> bf16 tensor-core layouts), activation layout conversion and
+// the fused SGD step.  All HBM-bound streaming kernels.
+#include "tp_common.cuh"
+
+namespace tp {
+
+// One CTA per (cout, r*s-chunk): read OIHW fp32 (w, mask), write
+//   wf[co][r][s][ci]                    (K-major B operand of fprop, K = (r,s,ci))
+//   wd[ci][R-1-r][S-1-s][co]            (K-major B operand of dgrad, K = (r',s',co))
+// OIHW -> O(RS)I is a small transpose per output channel: stage the [Cin][RS] slab of one
+// output channel through shared memory so both the read and the wf write are coalesced.
+__global__ void __launch_bounds__(256) k_stage_weights(const float* __restrict__ w, const float* __restrict__ mask,
+                                                       int cout, int cin, int rs,
+                                                       __nv_bfloat16* __restrict__ wf, int cin_p,
+                                                       __nv_bfloat16* __restrict__ wd, int cout_p, int cin_p2) {
+  extern __shared__ float s_slab[];       // [cin_chunk][rs] fp32, cin_chunk <= 1024/rs... sized by host
+  const int co = blockIdx.x;
+  const int chunk = blockDim.y;           // unused (1)
+  (void)chunk;
+  const int t = threadIdx.x;
+  const long long base = (long long)co * cin * rs;
+  // process channels in chunks of CC so the slab fits in smem
+  const int CC = gridDim.y > 0 ? (cin + gridDim.y - 1) / gridDim.y : cin;
+  const int c0 = blockIdx.y * CC;
+  const int c1 = min(cin, c0 + CC);
+  const int nel = (c1 - c0) * rs;
+  for (int i = t; i < nel; i += blockDim.x) {
+    long long gi = base + (long long)c0 * rs + i;
+    s_slab[i] = mask[gi] * w[gi];        // utils/mask_layers.py:25 — fp32 product, then bf16 (autocast)
+  }
+  __syncthreads();
+  // wf: for each tap, channels contiguous
+  for (int i = t; i < nel; i += blockDim.x) {
+    int tap = i / (c1 - c0), c = i % (c1 - c0);
+    float v = s_slab[c * rs + tap];
+    wf[((long long)co * rs + tap) * cin_p + c0 + c] = __float2bfloat16_rn(v);
+  }
+  if (wd) {
+    for (int i = t; i < nel; i += blockDim.x) {
+      int c = i / rs, tap = i % rs;
+      float v = s_slab[i];
+      wd[((long long)(c0 + c) * rs + (rs - 1 - tap)) * cout_p + co] = __float2bfloat16_rn(v);
+    }
+  }
+  // zero the channel padding of wf (cin..cin_p) — done by the y==0 slice
+  if (blockIdx.y == 0 && cin_p > cin) {
+    int padn = (cin_p - cin) * rs;
+    for (int i = t; i < padn; i += blockDim.x) {
+      int tap = i / (cin_p - cin), c = i % (cin_p - cin);
+      wf[((long long)co * rs + tap) * cin_p + cin + c] = __float2bfloat16_rn(0.f);
+    }
+  }
+}
+
+__global__ void k_zero_bf16(__nv_bfloat16* p, long long n) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = __float2bfloat16_rn(0.f);
+}
+
+// src[n][c][h][w] with arbitrary element strides (fp32 or bf16) -> dst NHWC bf16 [n][h][w][c_pad]
+template <typename T>
+__global__ void __launch_bounds__(256) k_to_nhwc(const T* __restrict__ src, long long sn, long long sc, long long sh, long long sw,
+                                                 int n, int c, int h, int w, __nv_bfloat16* __restrict__ dst, int c_pad) {
+  long long total = (long long)n * h * w * c_pad;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += stride) {
+    int ci = (int)(i % c_pad);
+    long long pix = i / c_pad;
+    int wi = (int)(pix % w);
+    long long t2 = pix / w;
+    int hi = (int)(t2 % h);
+    int ni = (int)(t2 / h);
+    float v = 0.f;
+    if (ci < c) v = (float)src[ni * sn + ci * sc + hi * sh + wi * sw];
+    dst[i] = __float2bfloat16_rn(v);
+  }
+}
+
+
+// Explicit im2col for convolutions whose input has too few channels for a 128-B TMA row
+// (the 3-channel stem conv): x NHWC bf16 [n][h][w][8] -> xcol [n*p*q][kp] bf16 with column
+// (r*S + s)*8 + c.  One thread moves one 16-byte (pixel, tap) cell; columns >= r*s*8 are zero.
+__global__ void __launch_bounds__(256) k_im2col_c8(const uint4* __restrict__ x, int n, int h, int w,
+                                                   int R, int S, int stride_h, int stride_w, int pad_h, int pad_w,
+                                                   int P, int Q, uint4* __restrict__ xcol, int kp8) {
+  const long long total = (long long)n * P * Q * kp8;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += step) {
+    const int cell = (int)(i % kp8);
+    const long long pix = i / kp8;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (cell < R * S) {
+      const int r = cell / S, s = cell - r * S;
+      const int q = (int)(pix % Q); const long long t2 = pix / Q;
+      const int pp = (int)(t2 % P); const int ni = (int)(t2 / P);
+      const int hi = pp * stride_h - pad_h + r, wi = q * stride_w - pad_w + s;
+      if (hi >= 0 && hi < h && wi >= 0 && wi < w) v = x[((long long)ni * h + hi) * w + wi];
+    }
+    xcol[i] = v;
+  }
+}
+
+// torch.optim.SGD (momentum, weight_decay, dampening 0, nesterov False) — one launch for all
+// parameters.  20 B/elem: read w,g,buf; write w,buf.
+__global__ void __launch_bounds__(256) k_sgd(const Seg* __restrict__ segs, int n_seg, long long tiles,
+                                             const float* __restrict__ lr_p, float mu, float wd, int first) {
+  const float lr = *lr_p;
+  const int t = threadIdx.x;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int si = find_seg(segs, n_seg, tile);
+    const Seg sg = segs[si];
+    const long long base = (tile - sg.tile0) * kTileElems;
+    const long long rem = sg.n - base;
+    const int n_in = rem < kTileElems ? (int)rem : kTileElems;
+    float* wp = const_cast<float*>(sg.w) + base;
+    const float* gp = sg.g + base;
+    float* bp = sg.buf + base;
+    bool vec = n_in == kTileElems && ((((uintptr_t)wp) | ((uintptr_t)gp) | ((uintptr_t)bp)) & 15) == 0;
+    if (vec) {
+#pragma unroll
+      for (int it = 0; it < kTileElems / (256 * 4); ++it) {
+        int q = it * 256 + t;
+        float4 w = ((const float4*)wp)[q];
+        float4 g = ld_stream((const float4*)gp + q);
+        float4 b = first ? make_float4(0.f, 0.f, 0.f, 0.f) : ((const float4*)bp)[q];
+        float4 d;
+        d.x = fmaf(wd, w.x, g.x); d.y = fmaf(wd, w.y, g.y); d.z = fmaf(wd, w.z, g.z); d.w = fmaf(wd, w.w, g.w);
+        // buf.mul_(mu).add_(d): two separately rounded ops in torch (no FMA contraction)
+        if (!first) { b.x = __fadd_rn(__fmul_rn(mu, b.x), d.x); b.y = __fadd_rn(__fmul_rn(mu, b.y), d.y); b.z = __fadd_rn(__fmul_rn(mu, b.z), d.z); b.w = __fadd_rn(__fmul_rn(mu, b.w), d.w); }
+        else b = d;
+        w.x = fmaf(-lr, b.x, w.x); w.y = fmaf(-lr, b.y, w.y); w.z = fmaf(-lr, b.z, w.z); w.w = fmaf(-lr, b.w, w.w);
+        ((float4*)bp)[q] = b;
+        ((float4*)wp)[q] = w;
+      }
+    } else {
+      for (int i = t; i < n_in; i += 256) {
+        float w = wp[i], g = gp[i];
+        float d = fmaf(wd, w, g);
+        float b = first ? d : __fadd_rn(__fmul_rn(mu, bp[i]), d);
+        bp[i] = b;
+        wp[i] = fmaf(-lr, b, w);
+      }
+    }
+  }
+}
+
+}  // namespace tp
+
+using namespace tp;
+
+extern "C" {
+
+int tp_stage_weights(const void* w, const void* mask, int cout, int cin, int r, int s,
+                     void* wf, int cin_p, void* wd, int cout_p, int cin_p2, void* stream) {
+  if (!w || !mask || !wf || cout <= 0 || cin <= 0 || r <= 0 || s <= 0 || cin_p < cin) return TP_ERR_INVALID;
+  if (wd && (cout_p < cout || cin_p2 < cin)) return TP_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int rs = r * s;
+  // slab of at most 8192 floats (32 KB) per CTA
+  int max_c = 8192 / rs; if (max_c < 1) return TP_ERR_UNSUPPORTED;
+  int ysplit = (cin + max_c - 1) / max_c;
+  int cc = (cin + ysplit - 1) / ysplit;
+  size_t smem = (size_t)cc * rs * sizeof(float);
+  if (wd) {
+    long long nz = (long long)cin_p2 * rs * cout_p;
+    if (cout_p > cout || cin_p2 > cin) {
+      k_zero_bf16<<<(unsigned)min((nz + 255) / 256, (long long)sm_count() * 16), 256, 0, st>>>((__nv_bfloat16*)wd, nz);
+    }
+  }
+  dim3 grid(cout, ysplit);
+  k_stage_weights<<<grid, 256, smem, st>>>((const float*)w, (const float*)mask, cout, cin, rs,
+                                           (__nv_bfloat16*)wf, cin_p, (__nv_bfloat16*)wd, cout_p, cin_p2);
+  TP_LAUNCH_CHECK();
+  return TP_OK;
+}
+
+int tp_to_nhwc_bf16(const void* src, int src_dtype, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
+                    int n, int c, int h, int w, void* dst, int c_pad, void* stream) {
+  if (!src || !dst || n <= 0 || c <= 0 || h <= 0 || w <= 0 || c_pad < c) return TP_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  long long total = (long long)n * h * w * c_pad;
+  unsigned grid = (unsigned)min((total + 255) / 256, (long long)sm_count() * 32);
+  if (src_dtype == 0) k_to_nhwc<float><<<grid, 256, 0, st>>>((const float*)src, sn, sc, sh, sw, n, c, h, w, (__nv_bfloat16*)dst, c_pad);
+  else if (src_dtype == 1) k_to_nhwc<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, sn, sc, sh, sw, n, c, h, w, (__nv_bfloat16*)dst, c_pad);
+  else return TP_ERR_INVALID;
+  TP_LAUNCH_CHECK();
+  return TP_OK;
+}
+
+int tp_im2col_c8(const void* x, int n, int h, int w, int r, int s, int stride_h, int stride_w,
+                 int pad_h, int pad_w, int p, int q, void* xcol, int kp, void* stream) {
+  if (!x || !xcol || n <= 0 || kp % 64 != 0 || kp < r * s * 8) return TP_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)n * p * q * (kp / 8);
+  unsigned grid = (unsigned)min((total + 255) / 256, (long long)sm_count() * 32);
+  k_im2col_c8<<<grid, 256, 0, st>>>((const uint4*)x, n, h, w, r, s, stride_h, stride_w, pad_h, pad_w, p, q, (uint4*)xcol, kp / 8);
+  TP_LAUNCH_CHECK();
+  return TP_OK;
+}
+
+int tp_sgd_momentum(void* const* w, const void* const* g, void* const* buf, const int64_t* numel,
+                    int n_seg, const float* lr_dev, float momentum, float weight_decay,
+                    int first_step, void* ws, size_t ws_bytes, void* stream) {
+  if (!w || !g || !buf || !numel || n_seg <= 0 || !lr_dev || !ws) return TP_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  Arena ar(ws, ws_bytes);
+  Seg* d_segs = nullptr; long long tiles = 0;
+  int rc = upload_segs(ar, (const void* const*)w, g, nullptr, nullptr, buf, numel, n_seg, &d_segs, &tiles, nullptr, st);
+  if (rc) return rc;
+  if (tiles == 0) return TP_OK;
+  long long gmax = (long long)sm_count() * 8;
+  k_sgd<<<(unsigned)(tiles < gmax ? tiles : gmax), 256, 0, st>>>(d_segs, n_seg, tiles, lr_dev, momentum, weight_decay, first_step);
+  TP_LAUNCH_CHECK();
+  return TP_OK;
+}
+
+}  // extern "C"

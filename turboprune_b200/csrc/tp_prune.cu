@@ -1,0 +1,541 @@
+// Pruning score -> exact global k-th smallest -> mask, for sm_100a.
+//
+// Replaces utils/pruning_utils.py:73-87 / :186-203 / :263-283 of the reference
+// (per-layer score temporaries, torch.cat, single-CTA 16-pass torch.kthvalue, per-layer
+// torch.where) with a bracketed single sweep over the weights:
+//
+//   1. k_sample_hist : 2^20 strided samples -> 65536-bin histogram of the top 16 key bits
+//   2. k_bracket     : one CTA turns the sample quantile (+- 5 sigma of its rank error) into
+//                      a key bracket [lo, hi) that contains the true k-th key w.h.p.
+//   3. k_sweep       : ONE pass over (w, m[, g]) at HBM rate: counts keys < lo and == lo,
+//                      writes the final mask for every key outside (lo, hi) and appends the
+//                      few keys inside to a candidate list            (12 B/elem mag, 16 snip)
+//   4. k_resolve     : one CTA selects the exact (k - n_lt - n_eq)-th candidate (8-bit radix,
+//                      data in L2), emits the threshold and patches the candidates' masks.
+//
+// If the bracket misses (adversarial ties, overflow of the candidate list) the host falls
+// back to an exact 3-pass 11/11/10-bit radix select over the full data + one apply pass.
+// Both paths are bit-exact with torch.kthvalue + torch.where(score <= thr, 0, 1).
+//
+// Keys: scores are |.| of fp32 products, so their IEEE bit patterns order like unsigned
+// integers; NaN patterns (> 0x7f800000) sort above +inf exactly like ATen's radix key
+// (SortingRadixSelect.cuh:20-39).
+#include "tp_common.cuh"
+
+namespace tp {
+
+struct SelState {
+  unsigned long long k;
+  unsigned long long n_lt, n_eq, n_cand;
+  unsigned int lo, hi;           // bracket: lo inclusive lower edge, hi exclusive upper edge
+  unsigned int thr_key;
+  int status;                    // 0 ok, 1 bracket missed -> fallback, 2 ok but threshold is NaN
+  unsigned int prefix, prefix_mask;   // exact radix path
+  unsigned long long k_rem;
+};
+
+constexpr int kSampleBits = 20;
+constexpr int kBracketBins = 65536;       // top 16 bits of a non-negative fp32 key: bits [30:15]
+constexpr int kBracketShift = 15;
+constexpr int kSweepThreads = 256;
+constexpr int kSmemCand = 1024;
+
+template <int KIND>
+__device__ __forceinline__ unsigned int score_key(float w, float g, float m) {
+  float s;
+  if (KIND == TP_SCORE_MAG) s = m * w;                 // pruning_utils.py:75
+  else if (KIND == TP_SCORE_SNIP) s = (g * w) * m;     // pruning_utils.py:190
+  else s = (m * g) * w;                                // pruning_utils.py:267
+  return __float_as_uint(fabsf(s));
+}
+
+template <int KIND>
+__device__ __forceinline__ unsigned int seg_key(const Seg& sg, long long i) {
+  float w = sg.w[i], m = sg.m[i];
+  float g = (KIND == TP_SCORE_MAG) ? 0.f : sg.g[i];
+  return score_key<KIND>(w, g, m);
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int KIND>
+__global__ void k_sample_hist(const Seg* __restrict__ segs, int n_seg, long long N, long long S,
+                              unsigned int* __restrict__ hist) {
+  long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (j >= S) return;
+  long long e = (long long)(((unsigned long long)j * (unsigned long long)N) / (unsigned long long)S);
+  int si = find_seg_by_elem(segs, n_seg, e);
+  unsigned int key = seg_key<KIND>(segs[si], e - segs[si].start);
+  atomicAdd(&hist[key >> kBracketShift], 1u);
+}
+
+__global__ void __launch_bounds__(1024) k_bracket(const unsigned int* __restrict__ hist,
+                                                  long long N, long long S, SelState* st) {
+  __shared__ unsigned long long s_part[1024];
+  const int t = threadIdx.x;
+  constexpr int per = kBracketBins / 1024;
+  unsigned long long loc = 0;
+  for (int i = 0; i < per; ++i) loc += hist[t * per + i];
+  s_part[t] = loc;
+  __syncthreads();
+  // inclusive scan (Hillis-Steele, 10 steps)
+  for (int off = 1; off < 1024; off <<= 1) {
+    unsigned long long v = (t >= off) ? s_part[t - off] : 0ull;
+    __syncthreads();
+    s_part[t] += v;
+    __syncthreads();
+  }
+  unsigned long long before = s_part[t] - loc;
+  const unsigned long long k = st->k;
+  // sample rank of the population's k-th element and its 5-sigma error band
+  unsigned long long rs = (unsigned long long)(((unsigned __int128)k * (unsigned long long)S + (unsigned long long)N - 1) /
+                                               (unsigned long long)N);
+  if (rs < 1) rs = 1;
+  if (rs > (unsigned long long)S) rs = (unsigned long long)S;
+  double p = (double)rs / (double)S;
+  double delta = (S == N) ? 0.0 : (5.0 * sqrt((double)S * p * (1.0 - p)) + 8.0);
+  long long r_lo = (long long)rs - (long long)delta;
+  long long r_hi = (long long)rs + (long long)delta;
+  if (t == 0) {
+    if (r_lo < 1) st->lo = 0u;
+    if (r_hi > S) st->hi = 0x80000000u;
+  }
+  // the thread whose bin range contains a rank publishes the bracket edge
+  if (r_lo >= 1 && (unsigned long long)r_lo > before && (unsigned long long)r_lo <= before + loc) {
+    unsigned long long c = before;
+    for (int i = 0; i < per; ++i) {
+      c += hist[t * per + i];
+      if (c >= (unsigned long long)r_lo) { st->lo = (unsigned int)(t * per + i) << kBracketShift; break; }
+    }
+  }
+  if (r_hi <= S && (unsigned long long)r_hi > before && (unsigned long long)r_hi <= before + loc) {
+    unsigned long long c = before;
+    for (int i = 0; i < per; ++i) {
+      c += hist[t * per + i];
+      if (c >= (unsigned long long)r_hi) { st->hi = (unsigned int)(t * per + i + 1) << kBracketShift; break; }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+struct SweepCtx {
+  unsigned int lo, hi;
+  unsigned int n_lt, n_eq;
+  uint2* s_cand; unsigned int* s_ncand;
+  SelState* st; uint2* cand; unsigned int cap;
+};
+
+__device__ __forceinline__ float classify(SweepCtx& c, unsigned int key, long long gidx) {
+  if (key < c.lo) { c.n_lt++; return 0.f; }
+  if (key == c.lo) { c.n_eq++; return 0.f; }
+  if (key >= c.hi) return 1.f;
+  // inside the bracket: rare (~0.1-1 %) -> candidate list
+  unsigned int slot = atomicAdd(c.s_ncand, 1u);
+  if (slot < kSmemCand) {
+    c.s_cand[slot] = make_uint2(key, (unsigned int)gidx);
+  } else {
+    unsigned long long gs = atomicAdd(&c.st->n_cand, 1ull);
+    if (gs < c.cap) c.cand[gs] = make_uint2(key, (unsigned int)gidx);
+  }
+  return 0.f;   // provisional; k_resolve patches it
+}
+
+template <int KIND, bool WRITE>
+__global__ void __launch_bounds__(kSweepThreads) k_sweep(const Seg* __restrict__ segs, int n_seg, long long tiles,
+                                                         SelState* st, uint2* __restrict__ cand, unsigned int cap) {
+  __shared__ uint2 s_cand[kSmemCand];
+  __shared__ unsigned int s_ncand;
+  __shared__ unsigned long long s_base;
+  __shared__ unsigned int s_red[2][kSweepThreads / 32];
+  SweepCtx c;
+  c.lo = st->lo; c.hi = st->hi; c.n_lt = 0; c.n_eq = 0;
+  c.s_cand = s_cand; c.s_ncand = &s_ncand; c.st = st; c.cand = cand; c.cap = cap;
+  const int t = threadIdx.x;
+  constexpr int kVecIters = kTileElems / (kSweepThreads * 4);   // 4
+
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    if (t == 0) s_ncand = 0;
+    __syncthreads();
+    const int si = find_seg(segs, n_seg, tile);
+    const Seg sg = segs[si];
+    const long long base = (tile - sg.tile0) * kTileElems;
+    const long long rem = sg.n - base;
+    const int n_in = rem < kTileElems ? (int)rem : kTileElems;
+    const float* wp = sg.w + base;
+    const float* mp = sg.m + base;
+    const float* gp = (KIND == TP_SCORE_MAG) ? nullptr : sg.g + base;
+    float* op = WRITE ? sg.mo + base : nullptr;
+    const long long g0 = sg.start + base;
+    bool vec = n_in == kTileElems &&
+               ((((uintptr_t)wp) | ((uintptr_t)mp) | ((uintptr_t)gp) | ((uintptr_t)op)) & 15) == 0;
+    if (vec) {
+      float4 wv[kVecIters], mv[kVecIters], gv[kVecIters];
+#pragma unroll
+      for (int it = 0; it < kVecIters; ++it) {
+        int q = it * kSweepThreads + t;
+        wv[it] = ld_stream((const float4*)wp + q);
+        mv[it] = ld_stream((const float4*)mp + q);
+        if (KIND != TP_SCORE_MAG) gv[it] = ld_stream((const float4*)gp + q);
+        else gv[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int it = 0; it < kVecIters; ++it) {
+        int q = it * kSweepThreads + t;
+        long long gi = g0 + (long long)q * 4;
+        float4 o;
+        o.x = classify(c, score_key<KIND>(wv[it].x, gv[it].x, mv[it].x), gi + 0);
+        o.y = classify(c, score_key<KIND>(wv[it].y, gv[it].y, mv[it].y), gi + 1);
+        o.z = classify(c, score_key<KIND>(wv[it].z, gv[it].z, mv[it].z), gi + 2);
+        o.w = classify(c, score_key<KIND>(wv[it].w, gv[it].w, mv[it].w), gi + 3);
+        if (WRITE) st_stream((float4*)op + q, o);
+      }
+    } else {
+      for (int i = t; i < n_in; i += kSweepThreads) {
+        float g = (KIND == TP_SCORE_MAG) ? 0.f : gp[i];
+        float o = classify(c, score_key<KIND>(wp[i], g, mp[i]), g0 + i);
+        if (WRITE) op[i] = o;
+      }
+    }
+    __syncthreads();
+    unsigned int nc = s_ncand < (unsigned)kSmemCand ? s_ncand : (unsigned)kSmemCand;
+    if (nc) {
+      if (t == 0) s_base = atomicAdd(&st->n_cand, (unsigned long long)nc);
+      __syncthreads();
+      unsigned long long b = s_base;
+      for (unsigned int i = t; i < nc; i += kSweepThreads)
+        if (b + i < cap) cand[b + i] = s_cand[i];
+    }
+    __syncthreads();
+  }
+  // block-reduce the two counters, one atomic pair per CTA
+  unsigned int a = c.n_lt, b = c.n_eq;
+  for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
+  if ((t & 31) == 0) { s_red[0][t >> 5] = a; s_red[1][t >> 5] = b; }
+  __syncthreads();
+  if (t == 0) {
+    unsigned long long A = 0, B = 0;
+    for (int i = 0; i < kSweepThreads / 32; ++i) { A += s_red[0][i]; B += s_red[1][i]; }
+    if (A) atomicAdd(&st->n_lt, A);
+    if (B) atomicAdd(&st->n_eq, B);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_resolve(const Seg* __restrict__ segs, int n_seg, SelState* st,
+                                                  uint2* __restrict__ cand, unsigned int cap,
+                                                  float* __restrict__ thr_out, int write_masks) {
+  __shared__ unsigned int s_hist[256];
+  __shared__ unsigned int s_prefix, s_krem;
+  __shared__ int s_status;
+  const int t = threadIdx.x;
+  const unsigned long long k = st->k, A = st->n_lt, B = st->n_eq, C = st->n_cand;
+  if (t == 0) {
+    int status = 0;
+    if (k <= A || C > cap) status = 1;            // k-th lies below the bracket / list overflow
+    else if (k <= A + B) { st->thr_key = st->lo; }
+    else if (k > A + B + C) status = 1;           // k-th lies above the bracket
+    s_status = status;
+    s_prefix = 0;
+    s_krem = (unsigned int)(k - A - B);
+  }
+  __syncthreads();
+  if (s_status == 1) { if (t == 0) st->status = 1; return; }
+  const unsigned int n = (unsigned int)C;
+  if (k > A + B) {
+    // exact select of the s_krem-th smallest candidate key: 4 x 8-bit radix passes (MSB first)
+    for (int shift = 24; shift >= 0; shift -= 8) {
+      if (t < 256) s_hist[t] = 0;
+      __syncthreads();
+      const unsigned int prefix = s_prefix;
+      const unsigned int pmask = (shift == 24) ? 0u : (0xFFFFFFFFu << (shift + 8));
+      for (unsigned int i = t; i < n; i += 1024) {
+        unsigned int key = cand[i].x;
+        if ((key & pmask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
+      }
+      __syncthreads();
+      if (t == 0) {
+        unsigned int cum = 0, kr = s_krem;
+        for (int d = 0; d < 256; ++d) {
+          unsigned int h = s_hist[d];
+          if (cum + h >= kr) { s_prefix = prefix | ((unsigned int)d << shift); s_krem = kr - cum; break; }
+          cum += h;
+        }
+      }
+      __syncthreads();
+    }
+    if (t == 0) st->thr_key = s_prefix;
+  }
+  __syncthreads();
+  const unsigned int thr = st->thr_key;
+  if (t == 0) {
+    *thr_out = __uint_as_float(thr);
+    st->status = (thr > 0x7f800000u) ? 2 : 0;
+  }
+  if (write_masks && thr <= 0x7f800000u) {
+    for (unsigned int i = t; i < n; i += 1024) {
+      uint2 c = cand[i];
+      int si = find_seg_by_elem(segs, n_seg, (long long)c.y);
+      segs[si].mo[(long long)c.y - segs[si].start] = (c.x <= thr) ? 0.f : 1.f;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exact fallback: 11/11/10-bit radix passes over the full data.
+template <int KIND>
+__global__ void __launch_bounds__(kSweepThreads) k_hist_pass(const Seg* __restrict__ segs, int n_seg, long long tiles,
+                                                             const SelState* __restrict__ st, int shift, int nbits,
+                                                             unsigned int* __restrict__ hist) {
+  __shared__ unsigned int s_hist[2048];
+  const int t = threadIdx.x;
+  for (int i = t; i < 2048; i += kSweepThreads) s_hist[i] = 0;
+  __syncthreads();
+  const unsigned int prefix = st->prefix, pmask = st->prefix_mask, dmask = (1u << nbits) - 1u;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int si = find_seg(segs, n_seg, tile);
+    const Seg& sg = segs[si];
+    const long long base = (tile - sg.tile0) * kTileElems;
+    const long long rem = sg.n - base;
+    const int n_in = rem < kTileElems ? (int)rem : kTileElems;
+    for (int i = t; i < n_in; i += kSweepThreads) {
+      unsigned int key = seg_key<KIND>(sg, base + i);
+      if ((key & pmask) == prefix) atomicAdd(&s_hist[(key >> shift) & dmask], 1u);
+    }
+  }
+  __syncthreads();
+  for (int i = t; i < (1 << nbits); i += kSweepThreads)
+    if (s_hist[i]) atomicAdd(&hist[i], s_hist[i]);
+}
+
+__global__ void k_pick_digit(const unsigned int* __restrict__ hist, int shift, int nbits, SelState* st) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  unsigned long long cum = 0, kr = st->k_rem;
+  for (int d = 0; d < (1 << nbits); ++d) {
+    unsigned long long h = hist[d];
+    if (cum + h >= kr) {
+      st->prefix |= ((unsigned int)d << shift);
+      st->prefix_mask |= (((1u << nbits) - 1u) << shift);
+      st->k_rem = kr - cum;
+      break;
+    }
+    cum += h;
+  }
+}
+
+__global__ void k_publish_thr(SelState* st, float* thr_out) {
+  st->thr_key = st->prefix;
+  st->status = (st->prefix > 0x7f800000u) ? 2 : 0;
+  *thr_out = __uint_as_float(st->prefix);
+}
+
+// mask_out = score <= thr ? 0 : 1 in fp32 compare semantics (NaN threshold keeps everything).
+template <int KIND>
+__global__ void __launch_bounds__(kSweepThreads) k_apply(const Seg* __restrict__ segs, int n_seg, long long tiles,
+                                                         const float* __restrict__ thr_p) {
+  const float thr = *thr_p;
+  const int t = threadIdx.x;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int si = find_seg(segs, n_seg, tile);
+    const Seg sg = segs[si];
+    const long long base = (tile - sg.tile0) * kTileElems;
+    const long long rem = sg.n - base;
+    const int n_in = rem < kTileElems ? (int)rem : kTileElems;
+    const float* wp = sg.w + base;
+    const float* mp = sg.m + base;
+    const float* gp = (KIND == TP_SCORE_MAG) ? nullptr : sg.g + base;
+    float* op = sg.mo + base;
+    bool vec = n_in == kTileElems &&
+               ((((uintptr_t)wp) | ((uintptr_t)mp) | ((uintptr_t)gp) | ((uintptr_t)op)) & 15) == 0;
+    if (vec) {
+#pragma unroll
+      for (int it = 0; it < kTileElems / (kSweepThreads * 4); ++it) {
+        int q = it * kSweepThreads + t;
+        float4 w = ld_stream((const float4*)wp + q), m = ld_stream((const float4*)mp + q);
+        float4 g = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (KIND != TP_SCORE_MAG) g = ld_stream((const float4*)gp + q);
+        float4 o;
+        o.x = (__uint_as_float(score_key<KIND>(w.x, g.x, m.x)) <= thr) ? 0.f : 1.f;
+        o.y = (__uint_as_float(score_key<KIND>(w.y, g.y, m.y)) <= thr) ? 0.f : 1.f;
+        o.z = (__uint_as_float(score_key<KIND>(w.z, g.z, m.z)) <= thr) ? 0.f : 1.f;
+        o.w = (__uint_as_float(score_key<KIND>(w.w, g.w, m.w)) <= thr) ? 0.f : 1.f;
+        st_stream((float4*)op + q, o);
+      }
+    } else {
+      for (int i = t; i < n_in; i += kSweepThreads) {
+        float g = (KIND == TP_SCORE_MAG) ? 0.f : gp[i];
+        op[i] = (__uint_as_float(score_key<KIND>(wp[i], g, mp[i])) <= thr) ? 0.f : 1.f;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kSweepThreads) k_count_zeros(const Seg* __restrict__ segs, int n_seg, long long tiles,
+                                                               unsigned long long* __restrict__ out) {
+  __shared__ unsigned int s_red[kSweepThreads / 32];
+  const int t = threadIdx.x;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    const int si = find_seg(segs, n_seg, tile);
+    const Seg sg = segs[si];
+    const long long base = (tile - sg.tile0) * kTileElems;
+    const long long rem = sg.n - base;
+    const int n_in = rem < kTileElems ? (int)rem : kTileElems;
+    const float* mp = sg.m + base;
+    unsigned int z = 0;
+    if (n_in == kTileElems && (((uintptr_t)mp) & 15) == 0) {
+#pragma unroll
+      for (int it = 0; it < kTileElems / (kSweepThreads * 4); ++it) {
+        float4 m = ld_stream((const float4*)mp + it * kSweepThreads + t);
+        z += (m.x == 0.f) + (m.y == 0.f) + (m.z == 0.f) + (m.w == 0.f);
+      }
+    } else {
+      for (int i = t; i < n_in; i += kSweepThreads) z += (mp[i] == 0.f);
+    }
+    for (int o = 16; o; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+    if ((t & 31) == 0) s_red[t >> 5] = z;
+    __syncthreads();
+    if (t == 0) {
+      unsigned long long tot = 0;
+      for (int i = 0; i < kSweepThreads / 32; ++i) tot += s_red[i];
+      if (tot) { atomicAdd(&out[si], tot); atomicAdd(&out[n_seg], tot); }
+    }
+    __syncthreads();
+  }
+}
+
+static unsigned int cand_cap(long long N) {
+  long long c = N / 8;
+  if (c < (1 << 16)) c = 1 << 16;
+  if (c > (1 << 23)) c = 1 << 23;
+  return (unsigned int)c;
+}
+
+static int sweep_grid(long long tiles) {
+  long long g = (long long)sm_count() * 8;
+  return (int)(tiles < g ? (tiles > 0 ? tiles : 1) : g);
+}
+
+template <int KIND>
+static int run_topk(const Seg* d_segs, int n_seg, long long tiles, long long N, long long k, bool write,
+                    SelState* d_st, unsigned int* d_hist, uint2* d_cand, unsigned int cap,
+                    float* thr_out, int64_t* info, cudaStream_t st) {
+  SelState h = {};
+  h.k = (unsigned long long)k;
+  h.hi = 0x80000000u;
+  TP_CUDA_CHECK(cudaMemcpyAsync(d_st, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+  TP_CUDA_CHECK(cudaMemsetAsync(d_hist, 0, sizeof(unsigned int) * kBracketBins, st));
+  const long long S = N < (1ll << kSampleBits) ? N : (1ll << kSampleBits);
+  k_sample_hist<KIND><<<(unsigned)((S + 255) / 256), 256, 0, st>>>(d_segs, n_seg, N, S, d_hist);
+  k_bracket<<<1, 1024, 0, st>>>(d_hist, N, S, d_st);
+  const int grid = sweep_grid(tiles);
+  if (write) k_sweep<KIND, true><<<grid, kSweepThreads, 0, st>>>(d_segs, n_seg, tiles, d_st, d_cand, cap);
+  else       k_sweep<KIND, false><<<grid, kSweepThreads, 0, st>>>(d_segs, n_seg, tiles, d_st, d_cand, cap);
+  k_resolve<<<1, 1024, 0, st>>>(d_segs, n_seg, d_st, d_cand, cap, thr_out, write ? 1 : 0);
+  TP_LAUNCH_CHECK();
+  TP_CUDA_CHECK(cudaMemcpyAsync(&h, d_st, sizeof(h), cudaMemcpyDeviceToHost, st));
+  TP_CUDA_CHECK(cudaStreamSynchronize(st));
+  int path = 0;
+  if (h.status == 1) {
+    // exact fallback: 3 radix passes over the full data
+    path = 1;
+    SelState f = {};
+    f.k = (unsigned long long)k; f.k_rem = (unsigned long long)k;
+    TP_CUDA_CHECK(cudaMemcpyAsync(d_st, &f, sizeof(f), cudaMemcpyHostToDevice, st));
+    const int shifts[3] = {21, 10, 0}, bits[3] = {11, 11, 10};
+    for (int p = 0; p < 3; ++p) {
+      TP_CUDA_CHECK(cudaMemsetAsync(d_hist, 0, sizeof(unsigned int) * 2048, st));
+      k_hist_pass<KIND><<<grid, kSweepThreads, 0, st>>>(d_segs, n_seg, tiles, d_st, shifts[p], bits[p], d_hist);
+      k_pick_digit<<<1, 32, 0, st>>>(d_hist, shifts[p], bits[p], d_st);
+    }
+    k_publish_thr<<<1, 1, 0, st>>>(d_st, thr_out);
+    if (write) k_apply<KIND><<<grid, kSweepThreads, 0, st>>>(d_segs, n_seg, tiles, thr_out);
+    TP_LAUNCH_CHECK();
+    TP_CUDA_CHECK(cudaMemcpyAsync(&h, d_st, sizeof(h), cudaMemcpyDeviceToHost, st));
+    TP_CUDA_CHECK(cudaStreamSynchronize(st));
+  } else if (h.status == 2 && write) {
+    // NaN threshold: `score <= nan` is false everywhere -> every mask entry becomes 1
+    k_apply<KIND><<<grid, kSweepThreads, 0, st>>>(d_segs, n_seg, tiles, thr_out);
+    TP_LAUNCH_CHECK();
+  }
+  if (info) { info[0] = path; info[1] = (int64_t)h.n_cand; info[2] = (int64_t)h.n_lt; info[3] = (h.status == 2); }
+  return TP_OK;
+}
+
+}  // namespace tp
+
+using namespace tp;
+
+extern "C" {
+
+size_t tp_topk_workspace_bytes(int n_seg, int64_t total_numel) {
+  size_t b = 0;
+  b += align_up(sizeof(Seg) * (size_t)(n_seg > 0 ? n_seg : 1), 256);
+  b += align_up(sizeof(SelState), 256);
+  b += align_up(sizeof(unsigned int) * kBracketBins, 256);
+  b += align_up(sizeof(uint2) * (size_t)cand_cap(total_numel), 256);
+  return b + 1024;
+}
+
+int tp_topk_threshold_mask(const void* const* w, const void* const* g, const void* const* m,
+                           void* const* mask_out, const int64_t* numel, int n_seg,
+                           int64_t k, int score_kind, float* thr_out,
+                           void* ws, size_t ws_bytes, int64_t* info_out, void* stream) {
+  if (!w || !m || !numel || n_seg <= 0 || !thr_out || !ws) return TP_ERR_INVALID;
+  if (score_kind != TP_SCORE_MAG && !g) return TP_ERR_INVALID;
+  if (score_kind < 0 || score_kind > 2) return TP_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  long long N = 0;
+  for (int i = 0; i < n_seg; ++i) { if (numel[i] < 0) return TP_ERR_INVALID; N += numel[i]; }
+  if (k < 1 || k > N) return TP_ERR_K_RANGE;          // torch.kthvalue raises (pruning_utils.py:79)
+  if (N >= (1ll << 32)) return TP_ERR_UNSUPPORTED;    // candidate records carry 32-bit indices
+  Arena ar(ws, ws_bytes);
+  Seg* d_segs = nullptr; long long tiles = 0, total = 0;
+  int rc = upload_segs(ar, w, g, m, mask_out, nullptr, numel, n_seg, &d_segs, &tiles, &total, st);
+  if (rc) return rc;
+  SelState* d_st = (SelState*)ar.take(sizeof(SelState));
+  unsigned int* d_hist = (unsigned int*)ar.take(sizeof(unsigned int) * kBracketBins);
+  const unsigned int cap = cand_cap(N);
+  uint2* d_cand = (uint2*)ar.take(sizeof(uint2) * (size_t)cap);
+  if (!d_st || !d_hist || !d_cand) return TP_ERR_WORKSPACE;
+  const bool write = mask_out != nullptr;
+  switch (score_kind) {
+    case TP_SCORE_MAG: return run_topk<TP_SCORE_MAG>(d_segs, n_seg, tiles, N, k, write, d_st, d_hist, d_cand, cap, thr_out, info_out, st);
+    case TP_SCORE_SNIP: return run_topk<TP_SCORE_SNIP>(d_segs, n_seg, tiles, N, k, write, d_st, d_hist, d_cand, cap, thr_out, info_out, st);
+    default: return run_topk<TP_SCORE_SYNFLOW>(d_segs, n_seg, tiles, N, k, write, d_st, d_hist, d_cand, cap, thr_out, info_out, st);
+  }
+}
+
+int tp_apply_threshold(const void* const* w, const void* const* g, const void* const* m,
+                       void* const* mask_out, const int64_t* numel, int n_seg,
+                       int score_kind, const float* thr, void* ws, size_t ws_bytes, void* stream) {
+  if (!w || !m || !mask_out || !numel || n_seg <= 0 || !thr || !ws) return TP_ERR_INVALID;
+  if (score_kind != TP_SCORE_MAG && !g) return TP_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  Arena ar(ws, ws_bytes);
+  Seg* d_segs = nullptr; long long tiles = 0;
+  int rc = upload_segs(ar, w, g, m, mask_out, nullptr, numel, n_seg, &d_segs, &tiles, nullptr, st);
+  if (rc) return rc;
+  if (tiles == 0) return TP_OK;
+  const int grid = sweep_grid(tiles);
+  if (score_kind == TP_SCORE_MAG) k_apply<TP_SCORE_MAG><<<grid, kSweepThreads, 0, st>>>(d_segs, n_seg, tiles, thr);
+  else if (score_kind == TP_SCORE_SNIP) k_apply<TP_SCORE_SNIP><<<grid, kSweepThreads, 0, st>>>(d_segs, n_seg, tiles, thr);
+  else if (score_kind == TP_SCORE_SYNFLOW) k_apply<TP_SCORE_SYNFLOW><<<grid, kSweepThreads, 0, st>>>(d_segs, n_seg, tiles, thr);
+  else return TP_ERR_INVALID;
+  TP_LAUNCH_CHECK();
+  return TP_OK;
+}
+
+int tp_count_zeros(const void* const* m, const int64_t* numel, int n_seg,
+                   int64_t* zeros_out, void* ws, size_t ws_bytes, void* stream) {
+  if (!m || !numel || n_seg <= 0 || !zeros_out || !ws) return TP_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  Arena ar(ws, ws_bytes);
+  Seg* d_segs = nullptr; long long tiles = 0;
+  int rc = upload_segs(ar, nullptr, nullptr, m, nullptr, nullptr, numel, n_seg, &d_segs, &tiles, nullptr, st);
+  if (rc) return rc;
+  TP_CUDA_CHECK(cudaMemsetAsync(zeros_out, 0, sizeof(int64_t) * (size_t)(n_seg + 1), st));
+  if (tiles == 0) return TP_OK;
+  k_count_zeros<<<sweep_grid(tiles), kSweepThreads, 0, st>>>(d_segs, n_seg, tiles, (unsigned long long*)zeros_out);
+  TP_LAUNCH_CHECK();
+  return TP_OK;
+}
+
+}  // extern "C"

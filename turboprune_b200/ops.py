@@ -1,0 +1,338 @@
+"""Torch-tensor front end of the C-ABI kernels (device memory / streams are torch's; the
+arithmetic is ours).  Every function here launches hand-written sm_100a kernels through
+``_cabi`` — there is no eager / CPU fallback.
+"""
+import ctypes
+from ctypes import c_void_p
+
+import torch
+
+from . import _cabi
+
+_launches = 0          # number of OUR kernel-launching C-ABI calls (bench.py reports it)
+
+
+def _count(n=1):
+    global _launches
+    _launches += n
+
+
+def launch_count() -> int:
+    return _launches
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("turboprune_b200 kernels need CUDA tensors (B200 / sm_100a); there is no CPU path")
+
+
+_ws_cache = {}
+
+
+def _workspace(nbytes: int, device, tag="default") -> torch.Tensor:
+    """Grow-only per-(device, stream, tag) scratch buffer owned by Python."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream, tag)
+    buf = _ws_cache.get(key)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(int(nbytes), 1 << 16), dtype=torch.uint8, device=device)
+        _ws_cache[key] = buf
+    return buf
+
+
+# ---------------------------------------------------------------------------------------------
+# pruning
+# ---------------------------------------------------------------------------------------------
+def topk_threshold_mask(ws, ms, k, gs=None, kind=_cabi.TP_SCORE_MAG, write_masks=True):
+    """Exact k-th smallest score over all layers + new masks (torch.kthvalue / torch.where parity).
+
+    Returns (new_masks | None, thr (0-dim fp32 cuda tensor), info dict).  Raises RuntimeError for
+    k outside [1, N] like torch.kthvalue does (the reference hits this for k == 0,
+    utils/pruning_utils.py:78-79).
+    """
+    lib = _cabi.load()
+    _require_cuda(*ws, *ms)
+    dev = ws[0].device
+    ws = [w.detach().contiguous() for w in ws]
+    ms = [m.detach().contiguous() for m in ms]
+    gs = None if gs is None else [g.detach().contiguous() for g in gs]
+    for t in ws + ms + (gs or []):
+        if t.dtype != torch.float32:
+            raise TypeError("pruning kernels operate on fp32 weights / masks / grads")
+    numel = [w.numel() for w in ws]
+    total = sum(numel)
+    outs = [torch.empty_like(m) for m in ms] if write_masks else None
+    thr = torch.empty((), dtype=torch.float32, device=dev)
+    nbytes = lib.tp_topk_workspace_bytes(len(ws), total)
+    wsb = _workspace(nbytes, dev, "topk")
+    info = (ctypes.c_int64 * 4)()
+    with torch.cuda.device(dev):
+        rc = lib.tp_topk_threshold_mask(
+            _cabi.ptr_array(ws), _cabi.ptr_array(gs), _cabi.ptr_array(ms), _cabi.ptr_array(outs),
+            _cabi.i64_array(numel), len(ws), int(k), int(kind), c_void_p(thr.data_ptr()),
+            c_void_p(wsb.data_ptr()), wsb.numel(), info, _cabi.stream_ptr(dev))
+    if rc == _cabi.TP_ERR_K_RANGE:
+        raise RuntimeError(f"kthvalue(): selected number k out of range for dimension 0 (k={k}, N={total})")
+    _cabi.check(rc, "tp_topk_threshold_mask")
+    _count(4)
+    return outs, thr, {"path": int(info[0]), "candidates": int(info[1]), "n_lt": int(info[2]), "nan_thr": bool(info[3])}
+
+
+def apply_threshold(ws, ms, thr, gs=None, kind=_cabi.TP_SCORE_MAG):
+    lib = _cabi.load()
+    _require_cuda(*ws, *ms, thr)
+    dev = ws[0].device
+    ws = [w.detach().contiguous() for w in ws]
+    ms = [m.detach().contiguous() for m in ms]
+    gs = None if gs is None else [g.detach().contiguous() for g in gs]
+    outs = [torch.empty_like(m) for m in ms]
+    thr = thr.to(device=dev, dtype=torch.float32).reshape(())
+    wsb = _workspace(lib.tp_segtable_workspace_bytes(len(ws)), dev, "seg")
+    with torch.cuda.device(dev):
+        rc = lib.tp_apply_threshold(_cabi.ptr_array(ws), _cabi.ptr_array(gs), _cabi.ptr_array(ms), _cabi.ptr_array(outs),
+                                    _cabi.i64_array([w.numel() for w in ws]), len(ws), int(kind),
+                                    c_void_p(thr.data_ptr()), c_void_p(wsb.data_ptr()), wsb.numel(), _cabi.stream_ptr(dev))
+    _cabi.check(rc, "tp_apply_threshold")
+    _count()
+    return outs
+
+
+def count_zeros(ms):
+    """int64 cuda tensor [n+1]: zeros per mask and the total in the last slot. One launch, no sync."""
+    lib = _cabi.load()
+    _require_cuda(*ms)
+    dev = ms[0].device
+    ms = [m.detach().contiguous() for m in ms]
+    out = torch.empty(len(ms) + 1, dtype=torch.int64, device=dev)
+    wsb = _workspace(lib.tp_segtable_workspace_bytes(len(ms)), dev, "seg")
+    with torch.cuda.device(dev):
+        rc = lib.tp_count_zeros(_cabi.ptr_array(ms), _cabi.i64_array([m.numel() for m in ms]), len(ms),
+                                c_void_p(out.data_ptr()), c_void_p(wsb.data_ptr()), wsb.numel(), _cabi.stream_ptr(dev))
+    _cabi.check(rc, "tp_count_zeros")
+    _count()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# optimizer
+# ---------------------------------------------------------------------------------------------
+def sgd_momentum_step(params, grads, bufs, lr_dev, momentum, weight_decay, first_step):
+    lib = _cabi.load()
+    dev = params[0].device
+    wsb = _workspace(lib.tp_segtable_workspace_bytes(len(params)), dev, "seg")
+    with torch.cuda.device(dev):
+        rc = lib.tp_sgd_momentum(_cabi.ptr_array(params), _cabi.ptr_array(grads), _cabi.ptr_array(bufs),
+                                 _cabi.i64_array([p.numel() for p in params]), len(params),
+                                 c_void_p(lr_dev.data_ptr()), float(momentum), float(weight_decay), int(bool(first_step)),
+                                 c_void_p(wsb.data_ptr()), wsb.numel(), _cabi.stream_ptr(dev))
+    _cabi.check(rc, "tp_sgd_momentum")
+    _count()
+
+
+# ---------------------------------------------------------------------------------------------
+# masked convolution / linear
+# ---------------------------------------------------------------------------------------------
+def _round_up(x, m):
+    return (x + m - 1) // m * m
+
+
+def make_desc(n, h, w, cin, cout, r, s, stride, padding):
+    sh, sw = stride
+    ph, pw = padding
+    p = (h + 2 * ph - r) // sh + 1
+    q = (w + 2 * pw - s) // sw + 1
+    return _cabi.ConvDesc(n, h, w, cin, cout, r, s, sh, sw, ph, pw, p, q)
+
+
+def stage_weights(weight4d, mask4d, cin_p, need_dgrad, cout_p=None):
+    """(mask*w) -> bf16 operand layouts wf [Cout, R*S*cin_p] and (optionally) wd [cin, R*S*cout_p]."""
+    lib = _cabi.load()
+    cout, cin, r, s = weight4d.shape
+    dev = weight4d.device
+    wf = torch.empty(cout, r * s * cin_p, dtype=torch.bfloat16, device=dev)
+    wd = None
+    cout_p = cout if cout_p is None else cout_p
+    if need_dgrad:
+        wd = torch.empty(cin, r * s * cout_p, dtype=torch.bfloat16, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.tp_stage_weights(c_void_p(weight4d.data_ptr()), c_void_p(mask4d.data_ptr()), cout, cin, r, s,
+                                  c_void_p(wf.data_ptr()), cin_p, c_void_p(wd.data_ptr()) if wd is not None else None,
+                                  cout_p, cin, _cabi.stream_ptr(dev))
+    _cabi.check(rc, "tp_stage_weights")
+    _count()
+    return wf, wd
+
+
+def to_nhwc_bf16(x, c_pad):
+    """[N, C, H, W] (any strides; fp32 or bf16) -> contiguous NHWC bf16 [N, H, W, c_pad]."""
+    lib = _cabi.load()
+    n, c, h, w = x.shape
+    if x.dtype == torch.bfloat16 and c == c_pad and x.permute(0, 2, 3, 1).is_contiguous():
+        return x.permute(0, 2, 3, 1)
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    out = torch.empty(n, h, w, c_pad, dtype=torch.bfloat16, device=x.device)
+    sn, sc, sh, sw = x.stride()
+    with torch.cuda.device(x.device):
+        rc = lib.tp_to_nhwc_bf16(c_void_p(x.data_ptr()), 0 if x.dtype == torch.float32 else 1, sn, sc, sh, sw,
+                                 n, c, h, w, c_void_p(out.data_ptr()), c_pad, _cabi.stream_ptr(x.device))
+    _cabi.check(rc, "tp_to_nhwc_bf16")
+    _count()
+    return out
+
+
+def im2col_c8(x_nhwc8, desc, kp):
+    lib = _cabi.load()
+    n, h, w, _ = x_nhwc8.shape
+    out = torch.empty(n * desc.p * desc.q, kp, dtype=torch.bfloat16, device=x_nhwc8.device)
+    with torch.cuda.device(x_nhwc8.device):
+        rc = lib.tp_im2col_c8(c_void_p(x_nhwc8.data_ptr()), n, h, w, desc.r, desc.s, desc.stride_h, desc.stride_w,
+                              desc.pad_h, desc.pad_w, desc.p, desc.q, c_void_p(out.data_ptr()), kp,
+                              _cabi.stream_ptr(x_nhwc8.device))
+    _cabi.check(rc, "tp_im2col_c8")
+    _count()
+    return out
+
+
+def conv_fprop(desc, x_nhwc, wf, bias=None):
+    lib = _cabi.load()
+    dev = x_nhwc.device
+    y = torch.empty(desc.n, desc.p, desc.q, desc.cout, dtype=torch.bfloat16, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.tp_conv_fprop(ctypes.byref(desc), c_void_p(x_nhwc.data_ptr()), c_void_p(wf.data_ptr()),
+                               c_void_p(bias.data_ptr()) if bias is not None else None, c_void_p(y.data_ptr()),
+                               None, 0, _cabi.stream_ptr(dev))
+    _cabi.check(rc, "tp_conv_fprop")
+    _count()
+    return y
+
+
+def conv_dgrad(desc, dy_nhwc, wd):
+    lib = _cabi.load()
+    dev = dy_nhwc.device
+    dx = torch.empty(desc.n, desc.h, desc.w, desc.cin, dtype=torch.bfloat16, device=dev)
+    with torch.cuda.device(dev):
+        rc = lib.tp_conv_dgrad(ctypes.byref(desc), c_void_p(dy_nhwc.data_ptr()), c_void_p(wd.data_ptr()),
+                               c_void_p(dx.data_ptr()), None, 0, _cabi.stream_ptr(dev))
+    _cabi.check(rc, "tp_conv_dgrad")
+    _count(1 if desc.stride_h == 1 and desc.stride_w == 1 else desc.stride_h * desc.stride_w)
+    return dx
+
+
+def conv_wgrad(desc, x_nhwc, dy_nhwc, mask4d, cin_real, want_db=False):
+    lib = _cabi.load()
+    dev = x_nhwc.device
+    dw = torch.empty(desc.cout, cin_real, desc.r, desc.s, dtype=torch.float32, device=dev)
+    db = torch.empty(desc.cout, dtype=torch.float32, device=dev) if want_db else None
+    nbytes = lib.tp_conv_workspace_bytes(ctypes.byref(desc), 2)
+    wsb = _workspace(nbytes, dev, "wgrad")
+    with torch.cuda.device(dev):
+        rc = lib.tp_conv_wgrad(ctypes.byref(desc), c_void_p(x_nhwc.data_ptr()), c_void_p(dy_nhwc.data_ptr()),
+                               c_void_p(mask4d.data_ptr()), cin_real, c_void_p(dw.data_ptr()),
+                               c_void_p(db.data_ptr()) if db is not None else None,
+                               c_void_p(wsb.data_ptr()), wsb.numel(), _cabi.stream_ptr(dev))
+    _cabi.check(rc, "tp_conv_wgrad")
+    _count(3 if want_db else 2)
+    return dw, db
+
+
+class MaskedConv2dFn(torch.autograd.Function):
+    """y = conv2d(x, mask*w, b) with bf16 tensor-core operands and fp32 accumulation.
+
+    Replaces ``F.conv2d(x, mask * weight, ...)`` under bf16 autocast (reference
+    utils/mask_layers.py:23-34 executed inside base_harness.py:121-125) and its autograd
+    backward: dX = dgrad(dY, mask*w), dW = mask * wgrad(x, dY) in fp32, db = sum dY.
+    Activations stay NHWC bf16 (logical NCHW tensors with channels_last strides).
+    """
+
+    @staticmethod
+    def forward(ctx, x, weight, mask, bias, stride, padding):
+        _require_cuda(x, weight, mask)
+        cout, cin, r, s = weight.shape
+        n, _, h, w = x.shape
+        need_dx = ctx.needs_input_grad[0]
+        w32 = weight.detach().contiguous()
+        m32 = mask.detach().contiguous()
+        small_c = (cin % 8 != 0) or (r * s > 1 and cin % 64 != 0)
+        desc = make_desc(n, h, w, cin, cout, r, s, stride, padding)
+        cout_p = _round_up(cout, 8)
+        if small_c:
+            if cin > 8:
+                raise NotImplementedError(f"masked conv with Cin={cin} (not a multiple of 64) and a {r}x{s} filter")
+            if need_dx:
+                raise NotImplementedError("input gradient of a small-channel stem convolution")
+            # stem conv: pad channels to 8, explicit im2col, then a plain GEMM
+            x8 = to_nhwc_bf16(x, 8)
+            kp = r * s * 8
+            xg = im2col_c8(x8, desc, kp)
+            gdesc = _cabi.ConvDesc(n * desc.p * desc.q, 1, 1, kp, cout, 1, 1, 1, 1, 0, 0, 1, 1)
+            wf, wd = stage_weights(w32, m32, 8, False)
+            y = conv_fprop(gdesc, xg, wf, bias).view(n, desc.p, desc.q, cout)
+            ctx.mode = "stem"
+            ctx.gdesc = gdesc
+            ctx.save_for_backward(xg, m32)
+        else:
+            xn = to_nhwc_bf16(x, cin)
+            wf, wd = stage_weights(w32, m32, cin, need_dx, cout_p)
+            y = conv_fprop(desc, xn, wf, bias)
+            ctx.mode = "conv"
+            ctx.save_for_backward(xn, m32, wd)
+        ctx.desc = desc
+        ctx.has_bias = bias is not None
+        ctx.cout_p = cout_p
+        ctx.x_dtype = x.dtype
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        desc = ctx.desc
+        cout = desc.cout
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        need_db = ctx.has_bias and ctx.needs_input_grad[3]
+        dyn = to_nhwc_bf16(dy, ctx.cout_p)
+        dx = dw = db = None
+        if ctx.mode == "stem":
+            xg, m32 = ctx.saved_tensors
+            if need_dw:
+                r, s = desc.r, desc.s
+                cin = m32.shape[1]
+                ones = torch.ones(cout, xg.shape[1], dtype=torch.float32, device=xg.device)
+                gd = ctx.gdesc
+                dwm, db = conv_wgrad(gd, xg, dyn.view(-1, cout), ones.view(cout, -1, 1, 1), xg.shape[1], need_db)
+                # columns are (tap, c8): back to OIHW and apply the mask (9.4 k elements)
+                dw = dwm.view(cout, r * s, 8)[:, :, :cin].permute(0, 2, 1).reshape(cout, cin, r, s) * m32
+        else:
+            xn, m32, wd = ctx.saved_tensors
+            ddesc = desc
+            if ctx.cout_p != cout:
+                ddesc = _cabi.ConvDesc(desc.n, desc.h, desc.w, desc.cin, ctx.cout_p, desc.r, desc.s, desc.stride_h,
+                                       desc.stride_w, desc.pad_h, desc.pad_w, desc.p, desc.q)
+            if need_dx:
+                dx = conv_dgrad(ddesc, dyn, wd).permute(0, 3, 1, 2)
+                if dx.dtype != ctx.x_dtype:
+                    dx = dx.to(ctx.x_dtype)
+            if need_dw:
+                if ctx.cout_p != cout:
+                    m_p = torch.zeros(ctx.cout_p, *m32.shape[1:], dtype=torch.float32, device=m32.device)
+                    m_p[:cout] = m32
+                    dwp, dbp = conv_wgrad(ddesc, xn, dyn, m_p, desc.cin, need_db)
+                    dw = dwp[:cout].contiguous()
+                    db = dbp[:cout].contiguous() if dbp is not None else None
+                else:
+                    dw, db = conv_wgrad(desc, xn, dyn, m32, desc.cin, need_db)
+        if need_db and db is None:
+            db = dy.float().sum(dim=(0, 2, 3))
+        return dx, dw, None, db, None, None
+
+
+def masked_conv2d(x, weight, mask, bias=None, stride=(1, 1), padding=(0, 0)):
+    return MaskedConv2dFn.apply(x, weight, mask, bias, tuple(stride), tuple(padding))
+
+
+def masked_linear(x, weight2d, mask2d, bias=None):
+    """y = x @ (mask*w)^T + b for x [..., in]; runs as a 1x1 convolution over a [rows,1,1,in] image."""
+    shp = x.shape
+    x2 = x.reshape(-1, shp[-1])
+    y = MaskedConv2dFn.apply(x2.view(x2.shape[0], x2.shape[1], 1, 1), weight2d.view(*weight2d.shape, 1, 1),
+                             mask2d.view(*mask2d.shape, 1, 1), bias, (1, 1), (0, 0))
+    return y.reshape(*shp[:-1], weight2d.shape[0])

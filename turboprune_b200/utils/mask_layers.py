@@ -1,0 +1,70 @@
+"""Masked operators — drop-in for the reference's ``utils/mask_layers.py``.
+
+Same class names, constructor arguments, parameter/buffer names (``weight``, ``bias``, fp32
+``mask`` buffer with the weight's shape) and ``set_er_mask`` as the reference
+(utils/mask_layers.py:10-128), so checkpoints, ``custom_models.replace_layers`` and the
+``mask_layer_type`` string lookup keep working.  What changes is ``forward``: instead of
+materialising ``mask * weight`` and calling cuDNN/cuBLAS, it launches the sm_100a
+implicit-GEMM kernels (``turboprune_b200.ops``), which consume weights masked while they are
+staged to bf16 and apply the mask to the weight gradient inside wgrad.
+
+There is deliberately no CPU implementation here: CPU tensors raise.
+"""
+import torch
+import torch.nn as nn
+
+from .. import ops
+
+
+def _pair(v):
+    return (v, v) if isinstance(v, int) else tuple(v)
+
+
+class _MaskMixin:
+    def _init_mask(self):
+        self.register_buffer("mask", torch.ones_like(self.weight))
+
+    def set_er_mask(self, p) -> None:
+        """Bernoulli(p) keep-mask drawn with torch's generator (bit-identical to the reference,
+        utils/mask_layers.py:36-43: the RNG stream is part of the mask-parity contract)."""
+        self.mask = torch.zeros_like(self.weight).bernoulli_(p)
+
+    def _check_plain(self):
+        if getattr(self, "groups", 1) != 1 or any(d != 1 for d in _pair(getattr(self, "dilation", 1))):
+            raise NotImplementedError("grouped / dilated masked convolutions (the reference drops these too)")
+
+
+class ConvMask(_MaskMixin, nn.Conv2d):
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        self._init_mask()
+
+    def forward(self, x):
+        self._check_plain()
+        if isinstance(self.padding, str):
+            raise NotImplementedError("string padding modes")
+        return ops.masked_conv2d(x, self.weight, self.mask, self.bias, _pair(self.stride), _pair(self.padding))
+
+
+class LinearMask(_MaskMixin, nn.Linear):
+    def __init__(self, **kwargs):
+        super().__init__(**kwargs)
+        self._init_mask()
+
+    def forward(self, x):
+        return ops.masked_linear(x, self.weight, self.mask, self.bias)
+
+
+class Conv1dMask(_MaskMixin, nn.Conv1d):
+    """nn.Linear replacement with weight [out, in, 1] (reference: utils/mask_layers.py:82-119)."""
+
+    def __init__(self, in_features: int, out_features: int, bias: bool = False):
+        super().__init__(in_channels=in_features, out_channels=out_features, kernel_size=1, stride=1, bias=bias)
+        self._init_mask()
+
+    def forward(self, x):
+        w = self.weight
+        return ops.masked_linear(x, w.view(w.shape[0], w.shape[1]), self.mask.view(w.shape[0], w.shape[1]), self.bias)
+
+
+MASKED_LAYER_TYPES = (ConvMask, Conv1dMask, LinearMask)
