@@ -22,6 +22,10 @@ void set_last_cuda_error(cudaError_t e, const char* where);
 #define TP_LAUNCH_CHECK() TP_CUDA_CHECK(cudaGetLastError())
 
 int sm_count();                       // cached
+// Make the device that owns `p` current on the calling thread (binds its primary context).
+// Needed because entry points are also called from torch's autograd thread, where no CUDA
+// context may be current yet and the driver API (cuTensorMapEncode*) would fail.
+int bind_device_of(const void* p);
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
 // A bump allocator over the caller's workspace.

@@ -23,6 +23,18 @@ int sm_count() {
   return cached[dev];
 }
 
+int bind_device_of(const void* p) {
+  if (!p) return TP_OK;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return TP_OK; }
+  if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) {
+    int cur = -1;
+    cudaGetDevice(&cur);
+    TP_CUDA_CHECK(cudaSetDevice(a.device));   // CUDA 12+: initialises and binds the primary context
+  }
+  return TP_OK;
+}
+
 int upload_segs(Arena& ar, const void* const* w, const void* const* g, const void* const* m,
                 void* const* mo, void* const* buf, const int64_t* numel, int n_seg,
                 Seg** dev_out, long long* tiles_out, long long* total_out, cudaStream_t st) {

@@ -545,6 +545,7 @@ int tp_conv_fprop(const tp_conv_desc* d, const void* x, const void* wf, const vo
   if (d->cin % 8 != 0 || d->r * d->s > kMaxTaps) return TP_ERR_UNSUPPORTED;
   if (d->r * d->s > 1 && d->cin % 64 != 0) return TP_ERR_UNSUPPORTED;
   int rc = load_driver_fns(); if (rc) return rc;
+  rc = bind_device_of(d ? (const void*)x : nullptr); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   FwdParams p = {};
   p.M = d->n * d->p * d->q; p.N = d->cout;
@@ -582,6 +583,7 @@ int tp_conv_dgrad(const tp_conv_desc* d, const void* dy, const void* wd,
   if (cop % 8 != 0 || d->r * d->s > kMaxTaps) return TP_ERR_UNSUPPORTED;
   if (d->r * d->s > 1 && cop % 64 != 0) return TP_ERR_UNSUPPORTED;
   int rc = load_driver_fns(); if (rc) return rc;
+  rc = bind_device_of(d ? (const void*)dy : nullptr); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int R = d->r, S = d->s;
   const long long ktot = (long long)R * S * cop;
@@ -660,6 +662,7 @@ int tp_conv_wgrad(const tp_conv_desc* d, const void* x, const void* dy, const vo
   if (d->cin % 8 != 0 || d->cout % 8 != 0 || d->r * d->s > kMaxTaps || cin_real > d->cin) return TP_ERR_UNSUPPORTED;
   if (d->r * d->s > 1 && d->cin % 64 != 0) return TP_ERR_UNSUPPORTED;
   int rc = load_driver_fns(); if (rc) return rc;
+  rc = bind_device_of(d ? (const void*)x : nullptr); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int rs = d->r * d->s;
   WgParams p = {};
