@@ -1,0 +1,328 @@
+#!/usr/bin/env python
+"""Headline benchmark: images/sec of the masked data-parallel train step, ResNet-50 @ 80 % unstructured
+(ERK) sparsity, ImageNet-shaped synthetic data, bf16 autocast — BASELINE.json's metric and config.
+
+    python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
+    python bench.py --impl reference ...                      (the reference's CPU path = oracle port, host cores)
+
+One "step" = one pass of the hot path over one batch: H2D (e2e only) -> zero_grad -> autocast forward through
+the sm_100a masked-conv kernels -> CE loss -> backward (dgrad/wgrad kernels, mask fused in wgrad) -> P2P gradient
+mean over NVLink (N>1) -> fused SGD.  Nothing is skipped in the timed region.
+
+Output: ONE JSON line (see the task contract): value = whole-job images/s with inputs resident in HBM,
+e2e = the same through the public API with pinned-host inputs copied every step and the loss read back,
+roofline = the masked implicit-GEMM kernels' achieved TFLOP/s (CUDA events on the launching stream, live in the
+timed region) against the measured sustained bf16 peak, cpu_baseline = the oracle port timed on host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "images_per_sec_resnet50_erk80_train_step"
+GFLOP_PER_IMG = 24.30           # fwd 8.178 + dgrad 7.942 + wgrad 8.178 (masked layers, dense)
+ROOFLINE_IMG_S = 39.8e3         # per-layer max(tensor, HBM) masked-GEMM roofline per GPU
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        d = json.load(open(path))
+        return dict(hbm=d["hbm_gbs"], tf=d["bf16_tflops_sustained"], tf_burst=d["bf16_tflops"], src="measured")
+    return dict(hbm=6650.0, tf=1400.0, tf_burst=1590.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm_sorted = sorted(sm)
+        loaded = sm_sorted[len(sm_sorted) // 3:] or sm_sorted       # drop idle samples at the edges
+        return {"sm_mhz": statistics.median(loaded) if loaded else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def triangular_lr(total_steps, warmup_fraction=0.2):
+    """LR multiplier schedule of the reference (utils/schedulers.py:79-117): interp [0.2, 1, 0]."""
+    import numpy as np
+    return np.interp(np.arange(1 + total_steps), [0, int(warmup_fraction * total_steps), total_steps], [0.2, 1, 0])
+
+
+def cpu_train_step_rate(batch, steps, warmup, threads=None):
+    """The reference's CPU path (oracle port): RN50 ERK-80 train step, bf16 autocast, on host cores."""
+    import torch
+    import oracle.model as om
+    from oracle import prune as OP
+    from oracle.train import train_step
+    if threads:
+        torch.set_num_threads(threads)
+    torch.manual_seed(0)
+    net = om.build("resnet50", "imagenet")
+    torch.manual_seed(1)
+    probs = OP.erk_keep_probabilities([tuple(m.weight.shape) for _, m in om.masked_layers(net)], 0.2)
+    om.set_er_masks(net, probs)
+    opt = torch.optim.SGD(net.parameters(), lr=0.2, momentum=0.9, weight_decay=1e-4)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(batch, 3, 224, 224, generator=g); t = torch.randint(0, 1000, (batch,), generator=g)
+    net.train()
+    for _ in range(warmup):
+        train_step(net, opt, x, t)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        train_step(net, opt, x, t)
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    batch = 16
+    steps = max(1, min(args.steps, 40))
+    rate, s_per_step, threads = cpu_train_step_rate(batch, steps, max(1, min(args.warmup, 2)))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": s_per_step * 1e3,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": "resnet50 imagenet-shape ERK-80% masked train step (reference CPU path, oracle port)",
+                   "global_batch": batch, "sample": f"batch {batch} per step on host cores"},
+        "cpu_baseline": {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
+                         "sample": f"{steps} steps of batch {batch} (torch CPU, bf16 autocast), os.cpu_count()={os.cpu_count()}"},
+        "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--global-batch", type=int, default=512, help="reference semantics: total_batch_size split over ranks")
+    ap.add_argument("--per-gpu-batch", type=int, default=0, help="override: fixed per-GPU batch (weak scaling)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-topk", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from refshim import make_cfg
+    from turboprune_b200 import ops
+    from turboprune_b200.optim import FusedSGD
+    from turboprune_b200.utils import custom_models as cm, pruning_utils as pu
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = max(1, args.warmup)
+    K = max(1, args.steps)
+    B = args.per_gpu_batch or max(1, args.global_batch // world)
+    scaling = "weak" if args.per_gpu_batch else "strong"
+
+    # ---- model: seed-0 ResNet-50, ERK-80 % Bernoulli masks (identical on every rank by construction) ----
+    torch.manual_seed(0)
+    model = cm.TorchVisionModel(make_cfg("resnet50", "imagenet", precision="bfloat16"))
+    torch.manual_seed(1)
+    pu.prune_er_erk(model, 0.2)
+    model = model.to(dev).train()
+    sparsity = model.get_overall_sparsity()
+    opt = FusedSGD(model.parameters(), lr=0.2, momentum=0.9, weight_decay=1e-4)
+    sched_tab = triangular_lr(10 * (W + K) * 3)
+    reducer = None
+    if world > 1:
+        from turboprune_b200.grad_exchange import P2PGradReducer
+        reducer = P2PGradReducer(list(model.parameters()))
+
+    gen = torch.Generator(device=dev).manual_seed(1000 * 0 + rank)
+    pool = [(torch.randn(B, 3, 224, 224, device=dev, generator=gen).contiguous(memory_format=torch.channels_last),
+             torch.randint(0, 1000, (B,), device=dev, generator=gen)) for _ in range(2)]
+    step_idx = [0]
+    loss_acc = torch.zeros((), device=dev)
+
+    def step(x, t):
+        for g in opt.param_groups:
+            g["lr"] = 0.2 * float(sched_tab[min(step_idx[0], len(sched_tab) - 1)])
+        step_idx[0] += 1
+        opt.zero_grad(set_to_none=True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = model(x)
+            loss = torch.nn.functional.cross_entropy(out, t)
+        loss.backward()
+        if reducer is not None:
+            reducer.reduce()
+        opt.step()
+        return loss
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def timed(nsteps, fn):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(nsteps):
+            fn(i)
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    # ---- device-resident run (value) ----
+    for i in range(W):
+        step(*pool[i % 2])
+    timer = ops.KernelTimer()
+    clocks = ClockSampler(local_rank); clocks.start()
+    launches0 = ops.launch_count()
+    ops.set_timer(timer)
+
+    def dev_step(i):
+        loss_acc.add_(step(*pool[i % 2]).detach())
+    ms_total = timed(K, dev_step)
+    ops.set_timer(None)
+    launches = ops.launch_count() - launches0
+    clk = clocks.stop()
+    if reducer is not None:
+        reducer.check_status()
+    img_s = world * B * K / (ms_total / 1e3)
+    tot = timer.totals()
+    gemm_ms = sum(v[0] for v in tot.values())
+    pk = peaks()
+    flops = GFLOP_PER_IMG * 1e9 * B * K
+    achieved_tf = flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
+    roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf"], "unit": "TFLOP/s",
+                "frac": achieved_tf / pk["tf"], "traffic": None, "peak_source": pk["src"] + " sustained bf16",
+                "kernel": "k_igemm_fwd / k_igemm_wgrad (masked implicit GEMM, tcgen05)",
+                "launches_per_step": sum(v[2] for v in tot.values()) / K,
+                "ms_per_step_in_kernel": gemm_ms / K,
+                "by_op_ms_per_step": {k: v[0] / K for k, v in tot.items()},
+                "share_of_step": gemm_ms / ms_total,
+                "flops_per_step": GFLOP_PER_IMG * 1e9 * B,
+                "frac_of_masked_gemm_roofline_img_s": (img_s / world) / ROOFLINE_IMG_S}
+
+    # ---- end-to-end run: pinned host inputs copied every step, loss read back every step ----
+    e2e = None
+    if not args.no_e2e:
+        hpool = [(torch.randn(B, 3, 224, 224).pin_memory(), torch.randint(0, 1000, (B,)).pin_memory()) for _ in range(2)]
+        h2d = hpool[0][0].numel() * 4 + hpool[0][1].numel() * 8
+
+        def e2e_step(i):
+            hx, ht = hpool[i % 2]
+            x = hx.to(dev, non_blocking=True); t = ht.to(dev, non_blocking=True)
+            return float(step(x, t).item())          # the reference returns loss.item() every step (base_harness.py:134)
+        for i in range(2):
+            e2e_step(i)
+        ms_e2e = timed(K, e2e_step)
+        e2e = {"value": world * B * K / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+               "ms_per_step": ms_e2e / K}
+
+    # ---- mask top-k (second half of the metric): prune_mag over the model's 25.5 M masked weights ----
+    topk = None
+    if not args.no_topk and rank == 0:
+        layers = [m for _, m in model._masked()]
+        ws = [m.weight.detach() for m in layers]; ms_ = [torch.ones_like(m.mask) for m in layers]
+        n = sum(w.numel() for w in ws); k = int((1 - 0.2) * n)
+        for _ in range(3):
+            ops.topk_threshold_mask(ws, ms_, k)
+        reps = 10
+        flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+        tms = []
+        for _ in range(reps):
+            flush.zero_()                                  # 256 MiB write: evicts the 126 MB L2
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); _, _, info = ops.topk_threshold_mask(ws, ms_, k); b.record(); torch.cuda.synchronize(dev)
+            tms.append(a.elapsed_time(b))
+        tmed = statistics.median(tms)
+        gbs = 12.0 * n / (tmed / 1e3) / 1e9
+        topk = {"metric": "mask_topk_GBps", "elements": n, "k": k, "algorithmic_bytes": 12 * n, "ms": tmed, "GBps": gbs,
+                "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": None},
+                "path": info["path"], "candidates": info["candidates"], "l2": "flushed between reps"}
+        del flush
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        rate, s_per_step, threads = cpu_train_step_rate(16, 6, 1)
+        cpu = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
+               "sample": f"6 steps of batch 16 of the same workload (oracle port, torch CPU bf16 autocast, {s_per_step:.2f} s/step), "
+                         f"os.cpu_count()={os.cpu_count()}"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": img_s, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
+            "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "resnet50 imagenet-shape [B,3,224,224] ERK-80% unstructured masks, SGD(0.9, wd 1e-4), CE loss",
+                       "global_batch": B * world, "per_gpu_batch": B, "parallelism": f"dp{world}",
+                       "sparsity_percent": sparsity, "l2": "inputs (308 MB/batch at B=512) and activations exceed the 126 MB L2",
+                       "grad_exchange": "none (1 GPU)" if world == 1 else "tp_p2p_allreduce_mask over symmetric memory (NVLink), no NCCL on the data path"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
+            "topk": topk, "loss_mean": float(loss_acc.item()) / K,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -93,7 +93,7 @@ int tp_to_nhwc_bf16(const void* src, int src_dtype, int64_t sn, int64_t sc, int6
 
 /* Explicit im2col for inputs with 8 (padded) channels — the 3-channel stem conv, whose rows are
  * too narrow for a 128-byte TMA row.  x: NHWC bf16 [n][h][w][8]; xcol: [n*p*q][kp] bf16 with
- * column (r*S+s)*8 + c, zero for columns >= r*s*8; kp % 64 == 0.  The stem conv then runs as a
+ * column (r*S+s)*8 + c, zero for columns >= r*s*8; kp % 8 == 0, kp >= r*s*8.  The stem conv then runs as a
  * plain GEMM (1x1 tp_conv_desc with cin = kp) through tp_conv_fprop / tp_conv_wgrad. */
 int tp_im2col_c8(const void* x, int n, int h, int w, int r, int s, int stride_h, int stride_w,
                  int pad_h, int pad_w, int p, int q, void* xcol, int kp, void* stream);

@@ -192,7 +192,7 @@ int tp_to_nhwc_bf16(const void* src, int src_dtype, int64_t sn, int64_t sc, int6
 
 int tp_im2col_c8(const void* x, int n, int h, int w, int r, int s, int stride_h, int stride_w,
                  int pad_h, int pad_w, int p, int q, void* xcol, int kp, void* stream) {
-  if (!x || !xcol || n <= 0 || kp % 64 != 0 || kp < r * s * 8) return TP_ERR_INVALID;
+  if (!x || !xcol || n <= 0 || kp % 8 != 0 || kp < r * s * 8) return TP_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   const long long total = (long long)n * p * q * (kp / 8);
   unsigned grid = (unsigned)min((total + 255) / 256, (long long)sm_count() * 32);

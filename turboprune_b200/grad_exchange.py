@@ -1,0 +1,112 @@
+"""Data-parallel gradient exchange over NVLink peer memory (replaces DDP's Reducer + NCCL).
+
+The reference wraps the model in ``DistributedDataParallel`` with default settings
+(harness_definitions/base_harness.py:81): per-bucket ``grad / W`` -> ``ncclAllReduce(SUM)`` ->
+copy back, plus a broadcast of every buffer (all masks!) from rank 0 on every forward.  Here:
+
+  * gradients are packed into a few large buckets that live in *symmetric memory*
+    (``torch.distributed._symmetric_memory``: every rank's bucket is mapped into every peer's
+    address space over NVLink / NVSwitch);
+  * one ``tp_p2p_allreduce_mask`` kernel per bucket reads the peers' copies directly, sums them
+    in fixed rank order (bit-identical result on every rank), scales by 1/W, applies the mask
+    and leaves the result in the local bucket — ``param.grad`` then simply views the bucket;
+  * nothing else is exchanged: masks are deterministic functions of replica-identical state, so
+    the reference's per-step mask broadcast disappears.  torch.distributed (NCCL) is only used
+    for rendezvous and scalar reductions.
+"""
+import ctypes
+from ctypes import c_void_p
+
+import torch
+import torch.distributed as dist
+
+from . import _cabi, ops
+
+PAD_FLOATS = 1024          # 4 KiB of signal-pad slots at the head of every symmetric bucket
+
+
+class P2PGradReducer:
+    def __init__(self, params, bucket_cap_mb=64.0, algo="auto", group=None, masks=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group or dist.group.WORLD
+        self.world = dist.get_world_size(self.group)
+        self.rank = dist.get_rank(self.group)
+        self.params = [p for p in params if p.requires_grad]
+        self.algo = algo
+        dev = self.params[0].device
+        self.device = dev
+        cap = int(bucket_cap_mb * 1024 * 1024 / 4)
+        # reverse order (gradients become ready back to front), like DDP's bucket assignment
+        self.buckets = []
+        cur, cur_n = [], 0
+        for p in reversed(self.params):
+            n = (p.numel() + 3) // 4 * 4                  # keep every slot 16-byte aligned
+            if cur and cur_n + n > cap:
+                self.buckets.append(cur); cur, cur_n = [], 0
+            cur.append(p); cur_n += n
+        if cur:
+            self.buckets.append(cur)
+        self._bk = []
+        masks = masks or {}
+        for plist in self.buckets:
+            offs, total = [], 0
+            for p in plist:
+                offs.append(total); total += (p.numel() + 3) // 4 * 4
+            buf = symm_mem.empty(PAD_FLOATS + total, dtype=torch.float32, device=dev)
+            buf.zero_()
+            hdl = symm_mem.rendezvous(buf, self.group)
+            ptrs = [int(x) for x in hdl.buffer_ptrs]
+            data_ptrs = (c_void_p * self.world)(*[c_void_p(x + PAD_FLOATS * 4) for x in ptrs])
+            pad_ptrs = (c_void_p * self.world)(*[c_void_p(x) for x in ptrs])
+            data = buf[PAD_FLOATS:]
+            views = [data[o:o + p.numel()].view_as(p) for o, p in zip(offs, plist)]
+            algo = self._algo_for(total)
+            # one-shot: peers read my bucket while I produce the result, so it needs its own
+            # output buffer; two-shot finishes in place (only rank r ever reads shard r).
+            out = torch.empty(total, dtype=torch.float32, device=dev) if algo == 0 else data
+            out_views = [out[o:o + p.numel()].view_as(p) for o, p in zip(offs, plist)]
+            mask = None
+            if any(id(p) in masks for p in plist):
+                mask = torch.ones(total, dtype=torch.float32, device=dev)
+                for o, p in zip(offs, plist):
+                    if id(p) in masks:
+                        mask[o:o + p.numel()] = masks[id(p)].reshape(-1)
+            self._bk.append(dict(buf=buf, hdl=hdl, data=data, views=views, numel=total, params=plist,
+                                 data_ptrs=data_ptrs, pad_ptrs=pad_ptrs, mask=mask, algo=algo, out=out,
+                                 out_views=out_views))
+        self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        torch.cuda.synchronize(dev)
+        dist.barrier(self.group)
+
+    def _algo_for(self, numel):
+        if self.algo == "one_shot":
+            return 0
+        if self.algo == "two_shot":
+            return 1
+        return 0 if numel * 4 <= (1 << 20) else 1
+
+    @torch.no_grad()
+    def reduce(self):
+        """Average gradients across ranks; afterwards every ``param.grad`` views its bucket slot."""
+        lib = _cabi.load()
+        st = _cabi.stream_ptr(self.device)
+        for bk in self._bk:
+            grads = [p.grad for p in bk["params"]]
+            live = [(v, g) for v, g in zip(bk["views"], grads) if g is not None and g.data_ptr() != v.data_ptr()]
+            if live:
+                torch._foreach_copy_([v for v, _ in live], [g for _, g in live])
+            for v, g in zip(bk["views"], grads):
+                if g is None:
+                    v.zero_()
+            rc = lib.tp_p2p_allreduce_mask(bk["data_ptrs"], bk["pad_ptrs"], self.rank, self.world, bk["numel"],
+                                           c_void_p(bk["mask"].data_ptr()) if bk["mask"] is not None else None,
+                                           1.0 / self.world, c_void_p(bk["out"].data_ptr()), bk["algo"],
+                                           20000, c_void_p(self.status.data_ptr()), st)
+            _cabi.check(rc, "tp_p2p_allreduce_mask")
+            ops._count()
+            for p, v in zip(bk["params"], bk["out_views"]):
+                p.grad = v
+
+    def check_status(self):
+        if int(self.status.item()) != 0:
+            raise RuntimeError("tp_p2p_allreduce_mask: peer barrier timed out (a rank did not arrive)")

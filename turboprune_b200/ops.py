@@ -21,6 +21,48 @@ def launch_count() -> int:
     return _launches
 
 
+class KernelTimer:
+    """CUDA-event timing of the masked-GEMM C-ABI calls on the launching stream (bench.py uses it
+    to report the dominant kernel's achieved TFLOP/s live, inside the timed region)."""
+
+    def __init__(self):
+        self.records = []          # (kind, flops, start_event, end_event)
+
+    def totals(self):
+        out = {}
+        for kind, flops, e0, e1 in self.records:
+            ms = e0.elapsed_time(e1)
+            t = out.setdefault(kind, [0.0, 0.0, 0])
+            t[0] += ms; t[1] += flops; t[2] += 1
+        return out
+
+
+_timer = None
+
+
+def set_timer(timer):
+    global _timer
+    _timer = timer
+
+
+class _Timed:
+    def __init__(self, kind, desc, cin_real=None):
+        self.on = _timer is not None
+        if self.on:
+            cin = desc.cin if cin_real is None else cin_real
+            self.flops = 2.0 * desc.n * desc.p * desc.q * desc.cout * cin * desc.r * desc.s
+            self.kind = kind
+
+    def __enter__(self):
+        if self.on:
+            self.e0 = torch.cuda.Event(enable_timing=True); self.e0.record()
+
+    def __exit__(self, *a):
+        if self.on:
+            e1 = torch.cuda.Event(enable_timing=True); e1.record()
+            _timer.records.append((self.kind, self.flops, self.e0, e1))
+
+
 def _require_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:
@@ -198,7 +240,7 @@ def conv_fprop(desc, x_nhwc, wf, bias=None):
     lib = _cabi.load()
     dev = x_nhwc.device
     y = torch.empty(desc.n, desc.p, desc.q, desc.cout, dtype=torch.bfloat16, device=dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _Timed("fprop", desc):
         rc = lib.tp_conv_fprop(ctypes.byref(desc), c_void_p(x_nhwc.data_ptr()), c_void_p(wf.data_ptr()),
                                c_void_p(bias.data_ptr()) if bias is not None else None, c_void_p(y.data_ptr()),
                                None, 0, _cabi.stream_ptr(dev))
@@ -211,7 +253,7 @@ def conv_dgrad(desc, dy_nhwc, wd):
     lib = _cabi.load()
     dev = dy_nhwc.device
     dx = torch.empty(desc.n, desc.h, desc.w, desc.cin, dtype=torch.bfloat16, device=dev)
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _Timed("dgrad", desc):
         rc = lib.tp_conv_dgrad(ctypes.byref(desc), c_void_p(dy_nhwc.data_ptr()), c_void_p(wd.data_ptr()),
                                c_void_p(dx.data_ptr()), None, 0, _cabi.stream_ptr(dev))
     _cabi.check(rc, "tp_conv_dgrad")
@@ -226,7 +268,7 @@ def conv_wgrad(desc, x_nhwc, dy_nhwc, mask4d, cin_real, want_db=False):
     db = torch.empty(desc.cout, dtype=torch.float32, device=dev) if want_db else None
     nbytes = lib.tp_conv_workspace_bytes(ctypes.byref(desc), 2)
     wsb = _workspace(nbytes, dev, "wgrad")
-    with torch.cuda.device(dev):
+    with torch.cuda.device(dev), _Timed("wgrad", desc):
         rc = lib.tp_conv_wgrad(ctypes.byref(desc), c_void_p(x_nhwc.data_ptr()), c_void_p(dy_nhwc.data_ptr()),
                                c_void_p(mask4d.data_ptr()), cin_real, c_void_p(dw.data_ptr()),
                                c_void_p(db.data_ptr()) if db is not None else None,
