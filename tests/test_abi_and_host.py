@@ -1,0 +1,115 @@
+"""CPU: the C-ABI library builds for sm_100a, loads, exports every symbol the header declares; host-side
+mirrors keep the reference's surface; the product refuses to run without CUDA."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    from turboprune_b200 import _cabi
+    header = open(os.path.join(ROOT, "include", "turboprune_b200.h")).read()
+    declared = set(re.findall(r"\b(tp_[a-z0-9_]+)\s*\(", header)) - {"tp_conv_desc"}
+    lib = _cabi.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+        assert name in _cabi.SIGNATURES, f"{name} has no ctypes signature"
+    assert set(_cabi.SIGNATURES) <= declared
+    assert lib.tp_abi_version() >= 1
+    assert b"range" in lib.tp_strerror(-4)
+
+
+def test_sass_contains_blackwell_tensor_and_tma_instructions(built_lib):
+    import shutil, subprocess
+    cu = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.isfile(cu):
+        pytest.skip("cuobjdump not available")
+    sass = subprocess.run([cu, "-sass", built_lib], stdout=subprocess.PIPE, text=True).stdout
+    for mnemonic in ("UTCHMMA", "UTMALDG", "LDTM"):
+        assert mnemonic in sass, mnemonic
+
+
+def test_no_cpu_fallback():
+    from turboprune_b200.utils.mask_layers import ConvMask, Conv1dMask
+    with pytest.raises(RuntimeError):
+        ConvMask(in_channels=8, out_channels=8, kernel_size=3, padding=1)(torch.randn(1, 8, 4, 4))
+    with pytest.raises(RuntimeError):
+        Conv1dMask(8, 4)(torch.randn(2, 8))
+
+
+def test_mask_layer_surface():
+    from turboprune_b200.utils import mask_layers as ml
+    c = ml.ConvMask(in_channels=4, out_channels=6, kernel_size=3, stride=2, padding=1, bias=False)
+    assert c.mask.dtype == torch.float32 and c.mask.shape == c.weight.shape and bool((c.mask == 1).all())
+    assert "mask" in dict(c.named_buffers()) and "mask" in c.state_dict()
+    torch.manual_seed(0); c.set_er_mask(0.3)
+    torch.manual_seed(0); ref = torch.zeros_like(c.weight).bernoulli_(0.3)
+    assert torch.equal(c.mask, ref) and "mask" in dict(c.named_buffers())      # re-assignment keeps the buffer registered
+    f = ml.Conv1dMask(10, 3, bias=True)
+    assert f.weight.shape == (3, 10, 1) and f.mask.shape == (3, 10, 1)
+    l = ml.LinearMask(in_features=10, out_features=3, bias=True)
+    assert l.mask.shape == (3, 10)
+
+
+def test_custom_models_build_like_the_reference():
+    import refshim
+    from turboprune_b200.utils import custom_models as cm, pruning_utils as pu
+    torch.manual_seed(0)
+    m = cm.TorchVisionModel(refshim.make_cfg("resnet18", "cifar10"))
+    names = [n for n, _ in m._masked()]
+    assert len(names) == 21 and names[0] == "conv1" and names[-1] == "fc"
+    assert m.get_overall_sparsity() == 0
+    sd = m.model.state_dict()
+    assert sd["fc.weight"].shape == (10, 512, 1) and sd["conv1.mask"].dtype == torch.float32
+    if refshim.reference_available():
+        ml, rpu, rcm = refshim.load_reference()
+        torch.manual_seed(0); r = rcm.TorchVisionModel(refshim.make_cfg("resnet18", "cifar10"))
+        for (k1, a), (k2, b) in zip(r.state_dict().items(), m.state_dict().items()):
+            assert k1 == k2 and torch.equal(a, b)
+        for fn in ("prune_er_erk", "prune_er_balanced"):
+            torch.manual_seed(5); getattr(pu, fn)(m, 0.2)
+            torch.manual_seed(5); getattr(rpu, fn)(r, 0.2)
+            for a, b in zip(r.state_dict().values(), m.state_dict().values()):
+                assert torch.equal(a, b)
+            assert m.get_overall_sparsity() == r.get_overall_sparsity()       # percent
+    # vgg16 / cifar100 surgery
+    v = cm.TorchVisionModel(refshim.make_cfg("vgg16", "cifar100"))
+    assert len(v._masked()) == 16 and v.model.state_dict()["classifier.6.weight"].shape == (100, 4096, 1)
+
+
+def test_prune_dispatcher_semantics():
+    import refshim
+    from turboprune_b200.utils import pruning_utils as pu
+
+    class Console:
+        def __init__(self): self.lines = []
+        def print(self, *a, **k): self.lines.append(" ".join(str(x) for x in a))
+
+    class H:
+        distributed = False
+        console = Console()
+        train_loader = None
+        class model:
+            @staticmethod
+            def get_overall_sparsity(): return 0.0
+    cfg = refshim.make_cfg(prune_method="does_not_exist")
+    assert pu.prune_the_model(cfg, H, 0.5) is None              # unknown method: message, no exception
+    assert any("Unknown pruning method" in l for l in H.console.lines)
+    assert pu.get_dtype_amp(refshim.make_cfg(precision="bfloat16")) == (torch.bfloat16, True)
+    assert pu.get_dtype_amp(refshim.make_cfg(precision="float32")) == (torch.float32, False)
+
+
+def test_fused_sgd_state_dict_is_torch_compatible():
+    from turboprune_b200.optim import FusedSGD
+    p = torch.nn.Parameter(torch.randn(5))
+    a = FusedSGD([p], lr=0.2, momentum=0.9, weight_decay=1e-4)
+    b = torch.optim.SGD([p], lr=0.2, momentum=0.9, weight_decay=1e-4)
+    ga, gb = a.state_dict()["param_groups"][0], b.state_dict()["param_groups"][0]
+    for key in ("lr", "momentum", "weight_decay", "dampening", "nesterov"):
+        assert ga[key] == gb[key]
+    sched = torch.optim.lr_scheduler.LambdaLR(a, lambda i: 0.5)
+    assert a.param_groups[0]["lr"] == pytest.approx(0.1)

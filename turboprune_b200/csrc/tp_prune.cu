@@ -4,9 +4,11 @@
 // (per-layer score temporaries, torch.cat, single-CTA 16-pass torch.kthvalue, per-layer
 // torch.where) with a bracketed single sweep over the weights:
 //
-//   1. k_sample_hist : 2^20 strided samples -> 65536-bin histogram of the top 16 key bits
-//   2. k_bracket     : one CTA turns the sample quantile (+- 5 sigma of its rank error) into
-//                      a key bracket [lo, hi) that contains the true k-th key w.h.p.
+//   1. k_sample_coarse: 2^20 strided samples -> sample keys + 2048-bin histogram of key bits [30:20]
+//   2. k_sample_fine  : histograms of bits [19:9] inside the coarse bins that hold the sample
+//                       quantile +- 5 sigma of its rank error (shared-memory privatised, no hot atomics);
+//                       the sweep's prologue turns them into a key bracket [lo, hi) that contains
+//                       the true k-th key w.h.p.
 //   3. k_sweep       : ONE pass over (w, m[, g]) at HBM rate: counts keys < lo and == lo,
 //                      writes the final mask for every key outside (lo, hi) and appends the
 //                      few keys inside to a candidate list            (12 B/elem mag, 16 snip)
@@ -31,12 +33,12 @@ struct SelState {
   unsigned int thr_key;
   int status;                    // 0 ok, 1 bracket missed -> fallback, 2 ok but threshold is NaN
   unsigned int prefix, prefix_mask;   // exact radix path
+  unsigned int c_lo, c_hi;            // coarse sample bins of the two bracket ranks
+  unsigned long long before_lo, before_hi;
   unsigned long long k_rem;
 };
 
 constexpr int kSampleBits = 20;
-constexpr int kBracketBins = 65536;       // top 16 bits of a non-negative fp32 key: bits [30:15]
-constexpr int kBracketShift = 15;
 constexpr int kSweepThreads = 256;
 constexpr int kSmemCand = 1024;
 
@@ -57,63 +59,94 @@ __device__ __forceinline__ unsigned int seg_key(const Seg& sg, long long i) {
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int KIND>
-__global__ void k_sample_hist(const Seg* __restrict__ segs, int n_seg, long long N, long long S,
-                              unsigned int* __restrict__ hist) {
-  long long j = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (j >= S) return;
-  long long e = (long long)(((unsigned long long)j * (unsigned long long)N) / (unsigned long long)S);
-  int si = find_seg_by_elem(segs, n_seg, e);
-  unsigned int key = seg_key<KIND>(segs[si], e - segs[si].start);
-  atomicAdd(&hist[key >> kBracketShift], 1u);
+// Block-wide rank search in a histogram of blockDim.x * PER bins: smallest bin whose inclusive
+// cumulative count reaches `rank` (1-indexed).  All threads call; result through shared memory.
+template <int PER>
+__device__ __forceinline__ void block_find_rank(const unsigned int* __restrict__ hist, unsigned long long rank,
+                                                unsigned int* s_bin, unsigned long long* s_before,
+                                                unsigned long long* s_warp /* [32] */) {
+  const int t = threadIdx.x, lane = t & 31, warp = t >> 5, nwarps = blockDim.x >> 5;
+  unsigned int h[PER];
+  unsigned long long loc = 0;
+#pragma unroll
+  for (int i = 0; i < PER; ++i) { h[i] = hist[t * PER + i]; loc += h[i]; }
+  unsigned long long inc = loc;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    unsigned long long v = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += v;
+  }
+  __syncthreads();                       // s_warp may still be read from a previous call
+  if (lane == 31) s_warp[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long v = lane < nwarps ? s_warp[lane] : 0ull, x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned long long u = __shfl_up_sync(0xffffffffu, x, o);
+      if (lane >= o) x += u;
+    }
+    s_warp[lane] = x - v;                // exclusive prefix of the warp totals
+  }
+  __syncthreads();
+  const unsigned long long before = s_warp[warp] + inc - loc;
+  if (rank > before && rank <= before + loc) {
+    unsigned long long c = before;
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+      if (c + h[i] >= rank) { *s_bin = (unsigned int)(t * PER + i); *s_before = c; break; }
+      c += h[i];
+    }
+  }
+  __syncthreads();
 }
 
-__global__ void __launch_bounds__(1024) k_bracket(const unsigned int* __restrict__ hist,
-                                                  long long N, long long S, SelState* st) {
-  __shared__ unsigned long long s_part[1024];
+// Bracket search, level 1: strided sample -> keys (kept for level 2) + 2048-bin histogram of key
+// bits [30:20], privatised in shared memory (no hot global atomics).
+constexpr int kCoarseShift = 20, kFineShift = 9, kDigitBins = 2048;
+
+template <int KIND>
+__global__ void __launch_bounds__(256) k_sample_coarse(const Seg* __restrict__ segs, int n_seg, long long N, long long S,
+                                                       unsigned int* __restrict__ skeys, unsigned int* __restrict__ hist_c) {
+  __shared__ unsigned int s_h[kDigitBins];
   const int t = threadIdx.x;
-  constexpr int per = kBracketBins / 1024;
-  unsigned long long loc = 0;
-  for (int i = 0; i < per; ++i) loc += hist[t * per + i];
-  s_part[t] = loc;
+  for (int i = t; i < kDigitBins; i += 256) s_h[i] = 0;
   __syncthreads();
-  // inclusive scan (Hillis-Steele, 10 steps)
-  for (int off = 1; off < 1024; off <<= 1) {
-    unsigned long long v = (t >= off) ? s_part[t - off] : 0ull;
-    __syncthreads();
-    s_part[t] += v;
-    __syncthreads();
+  for (long long j = blockIdx.x * 256ll + t; j < S; j += (long long)gridDim.x * 256) {
+    long long e = (long long)(((unsigned long long)j * (unsigned long long)N) / (unsigned long long)S);
+    int si = find_seg_by_elem(segs, n_seg, e);
+    unsigned int key = seg_key<KIND>(segs[si], e - segs[si].start);
+    skeys[j] = key;
+    atomicAdd(&s_h[key >> kCoarseShift], 1u);
   }
-  unsigned long long before = s_part[t] - loc;
-  const unsigned long long k = st->k;
-  // sample rank of the population's k-th element and its 5-sigma error band
-  unsigned long long rs = (unsigned long long)(((unsigned __int128)k * (unsigned long long)S + (unsigned long long)N - 1) /
-                                               (unsigned long long)N);
-  if (rs < 1) rs = 1;
-  if (rs > (unsigned long long)S) rs = (unsigned long long)S;
-  double p = (double)rs / (double)S;
-  double delta = (S == N) ? 0.0 : (5.0 * sqrt((double)S * p * (1.0 - p)) + 8.0);
-  long long r_lo = (long long)rs - (long long)delta;
-  long long r_hi = (long long)rs + (long long)delta;
-  if (t == 0) {
-    if (r_lo < 1) st->lo = 0u;
-    if (r_hi > S) st->hi = 0x80000000u;
+  __syncthreads();
+  for (int i = t; i < kDigitBins; i += 256) if (s_h[i]) atomicAdd(&hist_c[i], s_h[i]);
+}
+
+// Level 2: every CTA locates the coarse bins of the two bracket ranks (8 KB of L2 reads), then the
+// sample keys inside those bins are histogrammed on bits [19:9].
+__global__ void __launch_bounds__(256) k_sample_fine(const unsigned int* __restrict__ skeys, long long S,
+                                                     const unsigned int* __restrict__ hist_c,
+                                                     long long r_lo, long long r_hi,
+                                                     unsigned int* __restrict__ hist_f, SelState* st) {
+  __shared__ unsigned int s_h[2][kDigitBins];
+  __shared__ unsigned int s_bin[2];
+  __shared__ unsigned long long s_before[2], s_warp[32];
+  const int t = threadIdx.x;
+  if (t < 2) { s_bin[t] = 0; s_before[t] = 0; }
+  for (int i = t; i < 2 * kDigitBins; i += 256) (&s_h[0][0])[i] = 0;
+  __syncthreads();
+  block_find_rank<kDigitBins / 256>(hist_c, (unsigned long long)(r_lo < 1 ? 1 : r_lo), &s_bin[0], &s_before[0], s_warp);
+  block_find_rank<kDigitBins / 256>(hist_c, (unsigned long long)(r_hi > S ? S : r_hi), &s_bin[1], &s_before[1], s_warp);
+  const unsigned int c_lo = s_bin[0], c_hi = s_bin[1];
+  if (blockIdx.x == 0 && t == 0) { st->c_lo = c_lo; st->c_hi = c_hi; st->before_lo = s_before[0]; st->before_hi = s_before[1]; }
+  for (long long j = blockIdx.x * 256ll + t; j < S; j += (long long)gridDim.x * 256) {
+    const unsigned int key = skeys[j], c = key >> kCoarseShift, f = (key >> kFineShift) & (kDigitBins - 1);
+    if (c == c_lo) atomicAdd(&s_h[0][f], 1u);
+    if (c == c_hi) atomicAdd(&s_h[1][f], 1u);
   }
-  // the thread whose bin range contains a rank publishes the bracket edge
-  if (r_lo >= 1 && (unsigned long long)r_lo > before && (unsigned long long)r_lo <= before + loc) {
-    unsigned long long c = before;
-    for (int i = 0; i < per; ++i) {
-      c += hist[t * per + i];
-      if (c >= (unsigned long long)r_lo) { st->lo = (unsigned int)(t * per + i) << kBracketShift; break; }
-    }
-  }
-  if (r_hi <= S && (unsigned long long)r_hi > before && (unsigned long long)r_hi <= before + loc) {
-    unsigned long long c = before;
-    for (int i = 0; i < per; ++i) {
-      c += hist[t * per + i];
-      if (c >= (unsigned long long)r_hi) { st->hi = (unsigned int)(t * per + i + 1) << kBracketShift; break; }
-    }
-  }
+  __syncthreads();
+  for (int i = t; i < 2 * kDigitBins; i += 256) { unsigned int v = (&s_h[0][0])[i]; if (v) atomicAdd(&hist_f[i], v); }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -141,13 +174,29 @@ __device__ __forceinline__ float classify(SweepCtx& c, unsigned int key, long lo
 
 template <int KIND, bool WRITE>
 __global__ void __launch_bounds__(kSweepThreads) k_sweep(const Seg* __restrict__ segs, int n_seg, long long tiles,
-                                                         SelState* st, uint2* __restrict__ cand, unsigned int cap) {
+                                                         SelState* st, uint2* __restrict__ cand, unsigned int cap,
+                                                         const unsigned int* __restrict__ hist_f,
+                                                         long long r_lo, long long r_hi, long long S) {
   __shared__ uint2 s_cand[kSmemCand];
   __shared__ unsigned int s_ncand;
   __shared__ unsigned long long s_base;
   __shared__ unsigned int s_red[2][kSweepThreads / 32];
+  __shared__ unsigned int s_bin[2];
+  __shared__ unsigned long long s_before[2], s_warp[32];
+  // bracket [lo, hi) from the fine sample histograms — every CTA derives the same two keys
+  if (threadIdx.x < 2) { s_bin[threadIdx.x] = 0; s_before[threadIdx.x] = 0; }
+  __syncthreads();
+  block_find_rank<kDigitBins / kSweepThreads>(hist_f, (unsigned long long)(r_lo < 1 ? 1 : r_lo) - st->before_lo,
+                                              &s_bin[0], &s_before[0], s_warp);
+  block_find_rank<kDigitBins / kSweepThreads>(hist_f + kDigitBins, (unsigned long long)(r_hi > S ? S : r_hi) - st->before_hi,
+                                              &s_bin[1], &s_before[1], s_warp);
+  unsigned int lo = (st->c_lo << kCoarseShift) | (s_bin[0] << kFineShift);
+  unsigned int hi = (((st->c_hi << 11) | s_bin[1]) + 1u) << kFineShift;
+  if (r_lo < 1) lo = 0u;                              // no lower bound
+  if (r_hi > S || hi > 0x80000000u || hi == 0u) hi = 0x80000000u;   // no upper bound (keys are <= 0x7fffffff)
+  if (blockIdx.x == 0 && threadIdx.x == 0) { st->lo = lo; st->hi = hi; }
   SweepCtx c;
-  c.lo = st->lo; c.hi = st->hi; c.n_lt = 0; c.n_eq = 0;
+  c.lo = lo; c.hi = hi; c.n_lt = 0; c.n_eq = 0;
   c.s_cand = s_cand; c.s_ncand = &s_ncand; c.st = st; c.cand = cand; c.cap = cap;
   const int t = threadIdx.x;
   constexpr int kVecIters = kTileElems / (kSweepThreads * 4);   // 4
@@ -223,8 +272,9 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep(const Seg* __restrict__
 __global__ void __launch_bounds__(1024) k_resolve(const Seg* __restrict__ segs, int n_seg, SelState* st,
                                                   uint2* __restrict__ cand, unsigned int cap,
                                                   float* __restrict__ thr_out, int write_masks) {
-  __shared__ unsigned int s_hist[256];
-  __shared__ unsigned int s_prefix, s_krem;
+  __shared__ unsigned int s_hist[kDigitBins];
+  __shared__ unsigned int s_prefix, s_bin;
+  __shared__ unsigned long long s_before, s_krem, s_warp[32];
   __shared__ int s_status;
   const int t = threadIdx.x;
   const unsigned long long k = st->k, A = st->n_lt, B = st->n_eq, C = st->n_cand;
@@ -235,31 +285,42 @@ __global__ void __launch_bounds__(1024) k_resolve(const Seg* __restrict__ segs, 
     else if (k > A + B + C) status = 1;           // k-th lies above the bracket
     s_status = status;
     s_prefix = 0;
-    s_krem = (unsigned int)(k - A - B);
+    s_krem = k - A - B;
   }
   __syncthreads();
   if (s_status == 1) { if (t == 0) st->status = 1; return; }
   const unsigned int n = (unsigned int)C;
+  constexpr int U = 8;                            // independent L2 loads in flight per thread
   if (k > A + B) {
-    // exact select of the s_krem-th smallest candidate key: 4 x 8-bit radix passes (MSB first)
-    for (int shift = 24; shift >= 0; shift -= 8) {
-      if (t < 256) s_hist[t] = 0;
+    // exact select of the s_krem-th smallest candidate key: 11-bit radix passes, MSB first.
+    // Every candidate lies in (lo, hi), so the bits above the highest bit in which lo and hi-1
+    // differ are common to all of them: start below those (a narrow bracket needs 2 passes).
+    const unsigned int span = st->lo ^ (st->hi - 1u);
+    const int top = span ? (31 - __clz(span)) : 0;
+    const int shift0 = (top / 11) * 11;
+    if (t == 0) s_prefix = (shift0 + 11 >= 32) ? 0u : (st->lo & (0xFFFFFFFFu << (shift0 + 11)));
+    __syncthreads();
+    for (int shift = shift0; shift >= 0; shift -= 11) {
+      for (int i = t; i < kDigitBins; i += 1024) s_hist[i] = 0;
+      if (t == 0) { s_bin = 0; s_before = 0; }
       __syncthreads();
       const unsigned int prefix = s_prefix;
-      const unsigned int pmask = (shift == 24) ? 0u : (0xFFFFFFFFu << (shift + 8));
-      for (unsigned int i = t; i < n; i += 1024) {
-        unsigned int key = cand[i].x;
-        if ((key & pmask) == prefix) atomicAdd(&s_hist[(key >> shift) & 255u], 1u);
+      const unsigned int pmask = (shift + 11 >= 32) ? 0u : (0xFFFFFFFFu << (shift + 11));
+      for (unsigned int base = 0; base < n; base += 1024 * U) {
+        unsigned int key[U]; bool ok[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const unsigned int i = base + u * 1024 + t;
+          ok[u] = i < n;
+          key[u] = ok[u] ? cand[i].x : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (ok[u] && (key[u] & pmask) == prefix) atomicAdd(&s_hist[(key[u] >> shift) & (kDigitBins - 1)], 1u);
       }
       __syncthreads();
-      if (t == 0) {
-        unsigned int cum = 0, kr = s_krem;
-        for (int d = 0; d < 256; ++d) {
-          unsigned int h = s_hist[d];
-          if (cum + h >= kr) { s_prefix = prefix | ((unsigned int)d << shift); s_krem = kr - cum; break; }
-          cum += h;
-        }
-      }
+      block_find_rank<kDigitBins / 1024>(s_hist, s_krem, &s_bin, &s_before, s_warp);
+      if (t == 0) { s_prefix = prefix | (s_bin << shift); s_krem -= s_before; }
       __syncthreads();
     }
     if (t == 0) st->thr_key = s_prefix;
@@ -271,10 +332,20 @@ __global__ void __launch_bounds__(1024) k_resolve(const Seg* __restrict__ segs, 
     st->status = (thr > 0x7f800000u) ? 2 : 0;
   }
   if (write_masks && thr <= 0x7f800000u) {
-    for (unsigned int i = t; i < n; i += 1024) {
-      uint2 c = cand[i];
-      int si = find_seg_by_elem(segs, n_seg, (long long)c.y);
-      segs[si].mo[(long long)c.y - segs[si].start] = (c.x <= thr) ? 0.f : 1.f;
+    for (unsigned int base = 0; base < n; base += 1024 * U) {
+      uint2 c[U]; bool ok[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const unsigned int i = base + u * 1024 + t;
+        ok[u] = i < n;
+        c[u] = ok[u] ? cand[i] : make_uint2(0u, 0u);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (!ok[u]) continue;
+        int si = find_seg_by_elem(segs, n_seg, (long long)c[u].y);
+        segs[si].mo[(long long)c[u].y - segs[si].start] = (c[u].x <= thr) ? 0.f : 1.f;
+      }
     }
   }
 }
@@ -415,19 +486,29 @@ static int sweep_grid(long long tiles) {
 
 template <int KIND>
 static int run_topk(const Seg* d_segs, int n_seg, long long tiles, long long N, long long k, bool write,
-                    SelState* d_st, unsigned int* d_hist, uint2* d_cand, unsigned int cap,
+                    SelState* d_st, unsigned int* d_hist, unsigned int* d_skeys, uint2* d_cand, unsigned int cap,
                     float* thr_out, int64_t* info, cudaStream_t st) {
   SelState h = {};
   h.k = (unsigned long long)k;
   h.hi = 0x80000000u;
   TP_CUDA_CHECK(cudaMemcpyAsync(d_st, &h, sizeof(h), cudaMemcpyHostToDevice, st));
-  TP_CUDA_CHECK(cudaMemsetAsync(d_hist, 0, sizeof(unsigned int) * kBracketBins, st));
+  // d_hist layout: [0,2048) coarse sample histogram, [2048, 6144) two fine histograms
+  TP_CUDA_CHECK(cudaMemsetAsync(d_hist, 0, sizeof(unsigned int) * 3 * kDigitBins, st));
   const long long S = N < (1ll << kSampleBits) ? N : (1ll << kSampleBits);
-  k_sample_hist<KIND><<<(unsigned)((S + 255) / 256), 256, 0, st>>>(d_segs, n_seg, N, S, d_hist);
-  k_bracket<<<1, 1024, 0, st>>>(d_hist, N, S, d_st);
+  // sample rank of the population's k-th element and the +-5 sigma band of its sampling error
+  long long rs = (long long)(((unsigned __int128)(unsigned long long)k * (unsigned long long)S + (unsigned long long)N - 1) /
+                             (unsigned long long)N);
+  if (rs < 1) rs = 1;
+  if (rs > S) rs = S;
+  const double pq = (double)rs / (double)S;
+  const long long delta = (S == N) ? 0 : (long long)(5.0 * sqrt((double)S * pq * (1.0 - pq)) + 8.0);
+  const long long r_lo = rs - delta, r_hi = rs + delta;
+  const int sgrid = (int)((S + 255) / 256 < (long long)sm_count() * 4 ? (S + 255) / 256 : (long long)sm_count() * 4);
+  k_sample_coarse<KIND><<<sgrid, 256, 0, st>>>(d_segs, n_seg, N, S, d_skeys, d_hist);
+  k_sample_fine<<<sgrid, 256, 0, st>>>(d_skeys, S, d_hist, r_lo, r_hi, d_hist + kDigitBins, d_st);
   const int grid = sweep_grid(tiles);
-  if (write) k_sweep<KIND, true><<<grid, kSweepThreads, 0, st>>>(d_segs, n_seg, tiles, d_st, d_cand, cap);
-  else       k_sweep<KIND, false><<<grid, kSweepThreads, 0, st>>>(d_segs, n_seg, tiles, d_st, d_cand, cap);
+  if (write) k_sweep<KIND, true><<<grid, kSweepThreads, 0, st>>>(d_segs, n_seg, tiles, d_st, d_cand, cap, d_hist + kDigitBins, r_lo, r_hi, S);
+  else       k_sweep<KIND, false><<<grid, kSweepThreads, 0, st>>>(d_segs, n_seg, tiles, d_st, d_cand, cap, d_hist + kDigitBins, r_lo, r_hi, S);
   k_resolve<<<1, 1024, 0, st>>>(d_segs, n_seg, d_st, d_cand, cap, thr_out, write ? 1 : 0);
   TP_LAUNCH_CHECK();
   TP_CUDA_CHECK(cudaMemcpyAsync(&h, d_st, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -469,7 +550,8 @@ size_t tp_topk_workspace_bytes(int n_seg, int64_t total_numel) {
   size_t b = 0;
   b += align_up(sizeof(Seg) * (size_t)(n_seg > 0 ? n_seg : 1), 256);
   b += align_up(sizeof(SelState), 256);
-  b += align_up(sizeof(unsigned int) * kBracketBins, 256);
+  b += align_up(sizeof(unsigned int) * 3 * kDigitBins, 256);
+  b += align_up(sizeof(unsigned int) * (size_t)(1u << kSampleBits), 256);
   b += align_up(sizeof(uint2) * (size_t)cand_cap(total_numel), 256);
   return b + 1024;
 }
@@ -491,15 +573,16 @@ int tp_topk_threshold_mask(const void* const* w, const void* const* g, const voi
   int rc = upload_segs(ar, w, g, m, mask_out, nullptr, numel, n_seg, &d_segs, &tiles, &total, st);
   if (rc) return rc;
   SelState* d_st = (SelState*)ar.take(sizeof(SelState));
-  unsigned int* d_hist = (unsigned int*)ar.take(sizeof(unsigned int) * kBracketBins);
+  unsigned int* d_hist = (unsigned int*)ar.take(sizeof(unsigned int) * 3 * kDigitBins);
+  unsigned int* d_skeys = (unsigned int*)ar.take(sizeof(unsigned int) * (size_t)(1u << kSampleBits));
   const unsigned int cap = cand_cap(N);
   uint2* d_cand = (uint2*)ar.take(sizeof(uint2) * (size_t)cap);
-  if (!d_st || !d_hist || !d_cand) return TP_ERR_WORKSPACE;
+  if (!d_st || !d_hist || !d_skeys || !d_cand) return TP_ERR_WORKSPACE;
   const bool write = mask_out != nullptr;
   switch (score_kind) {
-    case TP_SCORE_MAG: return run_topk<TP_SCORE_MAG>(d_segs, n_seg, tiles, N, k, write, d_st, d_hist, d_cand, cap, thr_out, info_out, st);
-    case TP_SCORE_SNIP: return run_topk<TP_SCORE_SNIP>(d_segs, n_seg, tiles, N, k, write, d_st, d_hist, d_cand, cap, thr_out, info_out, st);
-    default: return run_topk<TP_SCORE_SYNFLOW>(d_segs, n_seg, tiles, N, k, write, d_st, d_hist, d_cand, cap, thr_out, info_out, st);
+    case TP_SCORE_MAG: return run_topk<TP_SCORE_MAG>(d_segs, n_seg, tiles, N, k, write, d_st, d_hist, d_skeys, d_cand, cap, thr_out, info_out, st);
+    case TP_SCORE_SNIP: return run_topk<TP_SCORE_SNIP>(d_segs, n_seg, tiles, N, k, write, d_st, d_hist, d_skeys, d_cand, cap, thr_out, info_out, st);
+    default: return run_topk<TP_SCORE_SYNFLOW>(d_segs, n_seg, tiles, N, k, write, d_st, d_hist, d_skeys, d_cand, cap, thr_out, info_out, st);
   }
 }
 
