@@ -124,6 +124,27 @@ int tp_conv_dgrad(const tp_conv_desc* d, const void* dy, const void* wd,
 int tp_conv_wgrad(const tp_conv_desc* d, const void* x, const void* dy, const void* mask,
                   int cin_real, void* dw, void* db, void* ws, size_t ws_bytes, void* stream);
 
+/* ---- fused BatchNorm (+ residual add) (+ ReLU) on NHWC bf16 activations ------------------
+ * the unmasked torchvision BatchNorm2d / ReLU / `out += identity` ops between
+ * the masked convolutions (module graph built at utils/custom_models.py:184, run inside
+ * harness_definitions/base_harness.py:124,127).  y, residual, z, dz, dy, dres: bf16 [M][C], C % 8 == 0.
+ *   forward : z = [relu]( (y - mean) * invstd * weight + bias [+ residual] )
+ *             training != 0: batch statistics (biased var), running stats updated with `momentum`
+ *             (unbiased var), *num_batches_tracked += 1, save_mean / save_invstd written (fp32 [C]);
+ *             training == 0: running statistics.
+ *   backward: g = relu ? dz * (z > 0) : dz;  dres = g (optional);  dweight = sum g*xhat; dbias = sum g;
+ *             dy = weight*invstd * (g - mean(g) - xhat * mean(g*xhat))
+ * Reductions use per-CTA partials folded in fixed order (deterministic).
+ */
+size_t tp_bn_workspace_bytes(int64_t m, int c);
+int tp_bn_forward(const void* y, const void* residual, void* z, int64_t m, int c,
+                  const void* weight, const void* bias, void* running_mean, void* running_var,
+                  void* num_batches_tracked, float momentum, float eps, int training, int relu,
+                  void* save_mean, void* save_invstd, void* ws, size_t ws_bytes, void* stream);
+int tp_bn_backward(const void* dz, const void* z, const void* y, int64_t m, int c, const void* weight,
+                   const void* save_mean, const void* save_invstd, int relu, void* dy, void* dres,
+                   void* dweight, void* dbias, void* ws, size_t ws_bytes, void* stream);
+
 /* ---- optimizer ------------------------------------------------------------------------
  * torch.optim.SGD(momentum, weight_decay) as configured at
  * harness_definitions/standard_pruning_harness.py:70-75, one launch for all segments:

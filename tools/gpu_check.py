@@ -10,7 +10,7 @@ import time
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-GROUPS = ["prune", "optim", "gemm", "conv", "dgrad", "wgrad", "layers", "model"]
+GROUPS = ["prune", "optim", "gemm", "conv", "dgrad", "wgrad", "layers", "bn", "model"]
 
 
 def _rel(a, b):
@@ -202,6 +202,40 @@ def g_layers():
     gx, gw, gb = R.masked_linear_grads(x.detach().cpu(), lin.weight.detach().cpu(), lin.mask.cpu(), dy.cpu(), True, True)
     e = dict(f=_rel(y.cpu(), yr), d=_rel(x.grad.cpu(), gx), w=_rel(lin.weight.grad.cpu(), gw), b=_rel(lin.bias.grad.cpu(), gb))
     print("  LinearMask 384->1152 (197 tokens):", e); ok &= all(v < 2e-2 for v in e.values())
+    return ok
+
+
+def g_bn():
+    import torch, torch.nn.functional as F
+    from turboprune_b200.fused_norm import BatchNorm2dB200
+    dev = "cuda"; ok = True
+    for (n, c, h, w, relu, res) in [(4, 64, 9, 7, True, False), (8, 256, 14, 14, True, True), (3, 2048, 7, 7, False, False),
+                                    (64, 64, 56, 56, True, False), (2, 192, 5, 5, False, True)]:
+        g = torch.Generator().manual_seed(c + n)
+        x = (torch.randn(n, c, h, w, generator=g) * 1.7 + 0.3).to(dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        r = torch.randn(n, c, h, w, generator=g).to(dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last) if res else None
+        bn = BatchNorm2dB200(c).to(dev); ref = torch.nn.BatchNorm2d(c).to(dev)
+        with torch.no_grad():
+            bn.weight.copy_(torch.rand(c, generator=g) + 0.5); bn.bias.copy_(torch.randn(c, generator=g) * 0.1)
+        ref.load_state_dict(bn.state_dict())
+        xa = x.clone().requires_grad_(True); xb = x.clone().float().requires_grad_(True)
+        ra = r.clone().requires_grad_(True) if res else None; rb = r.clone().float().requires_grad_(True) if res else None
+        z = bn(xa, residual=ra, relu=relu)
+        zr = ref(xb)
+        if res: zr = zr + rb
+        if relu: zr = torch.relu(zr)
+        dz = torch.randn(z.shape, generator=g).to(dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        z.backward(dz); zr.backward(dz.float())
+        e = dict(f=_rel(z, zr), dx=_rel(xa.grad, xb.grad), dw=_rel(bn.weight.grad, ref.weight.grad), db=_rel(bn.bias.grad, ref.bias.grad),
+                 rm=_rel(bn.running_mean, ref.running_mean), rv=_rel(bn.running_var, ref.running_var))
+        if res: e["dres"] = _rel(ra.grad, rb.grad)
+        good = all(v < 1e-2 for v in e.values()) and int(bn.num_batches_tracked) == 1
+        ok &= good
+        print(f"  bn n{n} c{c} {h}x{w} relu={relu} res={res}: " + " ".join(f"{k}={v:.1e}" for k, v in e.items()) + (" OK" if good else " FAIL"))
+        bn.eval(); ref.eval()
+        with torch.no_grad():
+            ze = bn(x, relu=relu); zre = ref(x.float()); zre = torch.relu(zre) if relu else zre
+        ok &= _rel(ze, zre) < 1e-2
     return ok
 
 

@@ -49,6 +49,11 @@ SIGNATURES = {
     "tp_segtable_workspace_bytes": (c_size_t, [c_int]),
     "tp_p2p_allreduce_mask": (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int64, c_void_p, c_float,
                                       c_void_p, c_int, c_int, c_void_p, c_void_p]),
+    "tp_bn_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "tp_bn_forward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                              c_float, c_float, c_int, c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tp_bn_backward": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                               c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tp_probe_run": (c_int, [c_int, c_void_p, c_size_t, c_void_p]),
 }
 

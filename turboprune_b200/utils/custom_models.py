@@ -135,6 +135,11 @@ class TorchVisionModel(PruneModel):
         if dataset in ("cifar10", "cifar100"):
             self._prepare_for_cifar(dataset)
         self._replace_layers()
+        # B200: BatchNorm / ReLU / residual-add between the masked convs run as fused NHWC kernels
+        # (same modules, parameters and state-dict keys).
+        if getattr(cfg.model_params, "fuse_norm", True):
+            from ..fused_norm import fuse_torchvision_blocks
+            fuse_torchvision_blocks(self.model)
         # Parameters keep their default (OIHW-contiguous) strides; activations become
         # channels_last (NHWC) at the first masked convolution and stay that way.
 
