@@ -31,7 +31,7 @@ static BnGeom bn_geom(long long M, int C) {
   g.tx = tx; g.ty = kBnThreads / tx;
   g.ctiles = (cv + tx - 1) / tx;
   long long rows = (M + g.ty - 1) / g.ty;
-  long long want = (long long)sm_count() * 8 / g.ctiles;
+  long long want = (long long)sm_count() * 4 / g.ctiles;
   if (want < 1) want = 1;
   long long gx = (rows + 3) / 4;            // >= 4 pixel rows per thread
   if (gx > want) gx = want;
@@ -110,6 +110,31 @@ __global__ void __launch_bounds__(kBnThreads) k_bn_stats(const __nv_bfloat16* __
   }
 }
 
+// Fold the per-CTA partials of one channel in a fixed order: 8 part-lanes each sum a strided subset
+// (coalesced across the 32 channel-lanes), then the 8 lane sums are added in lane order.
+constexpr int kFinC = 32, kFinP = 8;
+__device__ __forceinline__ void fold_partials(const float* __restrict__ partial, int nparts, int C, int c,
+                                              float& s1, float& s2, float (*sm)[kFinP][kFinC]) {
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  float a1 = 0.f, a2 = 0.f;
+  if (c < C) {
+    int j = ty;
+    for (; j + 3 * kFinP < nparts; j += 4 * kFinP) {
+      float v1[4], v2[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { v1[u] = partial[(size_t)(j + u * kFinP) * 2 * C + c]; v2[u] = partial[(size_t)(j + u * kFinP) * 2 * C + C + c]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a1 += v1[u]; a2 += v2[u]; }
+    }
+    for (; j < nparts; j += kFinP) { a1 += partial[(size_t)j * 2 * C + c]; a2 += partial[(size_t)j * 2 * C + C + c]; }
+  }
+  sm[0][ty][tx] = a1; sm[1][ty][tx] = a2;
+  __syncthreads();
+  s1 = 0.f; s2 = 0.f;
+#pragma unroll
+  for (int k = 0; k < kFinP; ++k) { s1 += sm[0][k][tx]; s2 += sm[1][k][tx]; }
+}
+
 // one thread per channel: fold the partials in fixed order; emit mean / invstd / scale / shift and
 // update the running statistics (torch semantics: momentum, unbiased running_var).
 __global__ void k_bn_finalize_stats(const float* __restrict__ partial, int nparts, const __nv_bfloat16* __restrict__ y,
@@ -117,11 +142,13 @@ __global__ void k_bn_finalize_stats(const float* __restrict__ partial, int npart
                                     float* running_mean, float* running_var, long long* nbt, float momentum, float eps,
                                     float* __restrict__ save_mean, float* __restrict__ save_invstd,
                                     float* __restrict__ scale, float* __restrict__ shift) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ float sm[2][kFinP][kFinC];
+  const int c = blockIdx.x * kFinC + threadIdx.x;
+  float s1, s2;
+  fold_partials(partial, nparts, C, c, s1, s2, sm);
+  if (threadIdx.y != 0) return;
   if (c == 0 && nbt) *nbt += 1;
   if (c >= C) return;
-  float s1 = 0.f, s2 = 0.f;
-  for (int j = 0; j < nparts; ++j) { s1 += partial[(size_t)j * 2 * C + c]; s2 += partial[(size_t)j * 2 * C + C + c]; }
   const float sh = __bfloat162float(y[c]);
   const float inv_m = 1.f / (float)M;
   const float dm = s1 * inv_m;
@@ -271,10 +298,11 @@ __global__ void __launch_bounds__(kBnThreads) k_bn_bwd_reduce(const __nv_bfloat1
 __global__ void k_bn_finalize_bwd(const float* __restrict__ partial, int nparts, long long M, int C,
                                   const float* __restrict__ weight, const float* __restrict__ mean, const float* __restrict__ invstd,
                                   float* __restrict__ dweight, float* __restrict__ dbias, float* __restrict__ coef) {
-  const int c = blockIdx.x * blockDim.x + threadIdx.x;
-  if (c >= C) return;
-  float s1 = 0.f, s2 = 0.f;
-  for (int j = 0; j < nparts; ++j) { s1 += partial[(size_t)j * 2 * C + c]; s2 += partial[(size_t)j * 2 * C + C + c]; }
+  __shared__ float sm[2][kFinP][kFinC];
+  const int c = blockIdx.x * kFinC + threadIdx.x;
+  float s1, s2;
+  fold_partials(partial, nparts, C, c, s1, s2, sm);
+  if (threadIdx.y != 0 || c >= C) return;
   if (dweight) dweight[c] = s2;
   if (dbias) dbias[c] = s1;
   const float inv_m = 1.f / (float)M;
@@ -365,7 +393,7 @@ int tp_bn_forward(const void* y, const void* residual, void* z, int64_t M, int C
   dim3 block(g.tx, g.ty), grid(g.grid_x, g.ctiles);
   if (training) {
     k_bn_stats<<<grid, block, 0, st>>>((const __nv_bfloat16*)y, M, C, partial);
-    k_bn_finalize_stats<<<(C + 255) / 256, 256, 0, st>>>(partial, g.grid_x, (const __nv_bfloat16*)y, M, C,
+    k_bn_finalize_stats<<<(C + kFinC - 1) / kFinC, dim3(kFinC, kFinP), 0, st>>>(partial, g.grid_x, (const __nv_bfloat16*)y, M, C,
                                                           (const float*)weight, (const float*)bias, (float*)running_mean,
                                                           (float*)running_var, (long long*)num_batches_tracked, momentum, eps,
                                                           (float*)save_mean, (float*)save_invstd, scale, shift);
@@ -398,7 +426,7 @@ int tp_bn_backward(const void* dz, const void* z, const void* y, int64_t M, int 
   const __nv_bfloat16 *d = (const __nv_bfloat16*)dz, *zz = (const __nv_bfloat16*)z, *yy = (const __nv_bfloat16*)y;
   if (relu) k_bn_bwd_reduce<true><<<grid, block, 0, st>>>(d, zz, yy, M, C, (const float*)save_mean, (const float*)save_invstd, partial);
   else k_bn_bwd_reduce<false><<<grid, block, 0, st>>>(d, zz, yy, M, C, (const float*)save_mean, (const float*)save_invstd, partial);
-  k_bn_finalize_bwd<<<(C + 255) / 256, 256, 0, st>>>(partial, g.grid_x, M, C, (const float*)weight, (const float*)save_mean,
+  k_bn_finalize_bwd<<<(C + kFinC - 1) / kFinC, dim3(kFinC, kFinP), 0, st>>>(partial, g.grid_x, M, C, (const float*)weight, (const float*)save_mean,
                                                       (const float*)save_invstd, (float*)dweight, (float*)dbias, coef);
   __nv_bfloat16* o = (__nv_bfloat16*)dy; __nv_bfloat16* r = (__nv_bfloat16*)dres;
   if (relu && r) k_bn_bwd_apply<true, true><<<grid, block, 0, st>>>(d, zz, yy, M, C, coef, o, r);
