@@ -25,6 +25,28 @@ from . import _cabi, ops
 PAD_FLOATS = 1024          # 4 KiB of signal-pad slots at the head of every symmetric bucket
 
 
+def plan_buckets(numels, cap_elems):
+    """Pure host logic: pack parameters (given in REVERSE registration order, i.e. the order gradients become
+    ready) into buckets of at most ``cap_elems`` fp32 slots; every slot is padded to a multiple of 4 elements so it
+    stays 16-byte aligned.  Returns [(indices, offsets, total_elems)].  Must be identical on every rank."""
+    buckets, cur, offs, total = [], [], [], 0
+    for i, n in enumerate(numels):
+        slot = (n + 3) // 4 * 4
+        if cur and total + slot > cap_elems:
+            buckets.append((cur, offs, total)); cur, offs, total = [], [], 0
+        cur.append(i); offs.append(total); total += slot
+    if cur:
+        buckets.append((cur, offs, total))
+    return buckets
+
+
+def shard_bounds(numel, world):
+    """float4-granular shard [s0, s1) of every rank for the two-shot algorithm (mirrors k_p2p_allreduce<1>)."""
+    n4 = numel // 4
+    per = (n4 + world - 1) // world
+    return [(min(n4, per * r) * 4, min(n4, min(n4, per * r) + per) * 4) for r in range(world)]
+
+
 class P2PGradReducer:
     def __init__(self, params, bucket_cap_mb=64.0, algo="auto", group=None, masks=None):
         import torch.distributed._symmetric_memory as symm_mem
@@ -37,15 +59,9 @@ class P2PGradReducer:
         self.device = dev
         cap = int(bucket_cap_mb * 1024 * 1024 / 4)
         # reverse order (gradients become ready back to front), like DDP's bucket assignment
-        self.buckets = []
-        cur, cur_n = [], 0
-        for p in reversed(self.params):
-            n = (p.numel() + 3) // 4 * 4                  # keep every slot 16-byte aligned
-            if cur and cur_n + n > cap:
-                self.buckets.append(cur); cur, cur_n = [], 0
-            cur.append(p); cur_n += n
-        if cur:
-            self.buckets.append(cur)
+        rev = list(reversed(self.params))
+        self.plan = plan_buckets([p.numel() for p in rev], cap)
+        self.buckets = [[rev[i] for i in idx] for idx, _, _ in self.plan]
         self._bk = []
         masks = masks or {}
         for plist in self.buckets:
