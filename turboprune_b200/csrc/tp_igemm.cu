@@ -43,6 +43,7 @@ struct FwdParams {
   int out_row_pix;          // output pixels per row
   int osh, oah, osw, oaw;   // output pixel = (p*osh+oah, q*osw+oaw)
   int ldc;                  // elements between consecutive output pixels
+  int tma_store;            // 1: epilogue stages 32x64 sub-tiles in smem and stores them with TMA (tmC)
   __nv_bfloat16* out;
   const float* bias;
   TapEntry taps[kMaxTaps];
@@ -69,7 +70,7 @@ __device__ __forceinline__ void decompose_pixel(int m, int P, int Q, int& n, int
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1)
 k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ FwdParams p) {
+            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ FwdParams p) {
   constexpr int kABytes = kBlockM * kBlockK * 2;           // 16 KB
   constexpr int kBBytes = BLOCK_N * kBlockK * 2;
   constexpr int kStageBytes = kABytes + kBBytes;
@@ -79,7 +80,9 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
                                  (kAccStages * BLOCK_N <= 128) ? 128 : (kAccStages * BLOCK_N <= 256) ? 256 : 512;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = (uint64_t*)(smem + kStages * kStageBytes);
+  constexpr int kStgBytes = 32 * 128;                      // one epilogue warp's 32 rows x 64 bf16 columns
+  uint8_t* stg_base = smem + kStages * kStageBytes;        // 4 warps x 2 buffers x 4 KB (1024-B aligned)
+  uint64_t* full_bar = (uint64_t*)(stg_base + 8 * kStgBytes);
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tfull_bar = empty_bar + kStages;
   uint64_t* tempty_bar = tfull_bar + kAccStages;
@@ -92,7 +95,7 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int kiters = p.ntaps * p.cchunks;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmA); prefetch_tmap(&tmB);
+    prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmC);
     for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < kAccStages; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
     fence_mbar_init();
@@ -113,18 +116,22 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         int cn = 0, cp = 0, cq = 0;
         if (p.a_mode == 1) decompose_pixel(m0, p.P_it, p.Q_it, cn, cp, cq);
         const int cw = p.base_w + cq * p.step_w, ch = p.base_h + cp * p.step_h;
-        for (int it = 0; it < kiters; ++it) {
-          const int tap = it / p.cchunks, cc = it - tap * p.cchunks;
-          mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-          mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-          uint8_t* sA = smem + stage * kStageBytes;
-          uint8_t* sB = sA + kABytes;
-          if (p.a_mode == 1)
-            tma_load_im2col_4d(sA, &tmA, &full_bar[stage], cc * kBlockK, cw, ch, cn, p.taps[tap].off_w, p.taps[tap].off_h);
-          else
-            tma_load_2d(sA, &tmA, &full_bar[stage], p.taps[tap].kofs + cc * kBlockK, m0);
-          tma_load_2d(sB, &tmB, &full_bar[stage], p.taps[tap].kofs + cc * kBlockK, n_t * BLOCK_N);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        // nested tap / channel-chunk loops: no integer division on the single producer thread
+        // (the first ncu source view showed the producer, not TMA or the tensor pipe, as the limiter)
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const TapEntry te = p.taps[tap];
+          for (int cc = 0; cc < p.cchunks; ++cc) {
+            mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+            mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+            uint8_t* sA = smem + stage * kStageBytes;
+            uint8_t* sB = sA + kABytes;
+            if (p.a_mode == 1)
+              tma_load_im2col_4d(sA, &tmA, &full_bar[stage], cc * kBlockK, cw, ch, cn, te.off_w, te.off_h);
+            else
+              tma_load_2d(sA, &tmA, &full_bar[stage], te.kofs + cc * kBlockK, m0);
+            tma_load_2d(sB, &tmB, &full_bar[stage], te.kofs + cc * kBlockK, n_t * BLOCK_N);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
+          }
         }
       }
     }
@@ -161,6 +168,7 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ------------------------------ epilogue ------------------------------
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
     int acc = 0; uint32_t acc_phase = 0;
+    int stg_sel = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
       const int n_t = tile / m_tiles, m_t = tile % m_tiles;
       const int row = m_t * kBlockM + quarter * 32 + lane;
@@ -174,6 +182,47 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_wait(&tfull_bar[acc], acc_phase, 4);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
+      if (p.tma_store) {
+        // TMEM -> registers -> 128B-swizzled smem sub-tile (32 rows x 64 cols) -> TMA store: every
+        // output line leaves the SM as full 128-byte rows instead of 32 scattered 16-byte pieces.
+        uint8_t* my_stg = stg_base + (warp - 2) * 2 * kStgBytes;
+#pragma unroll 1
+        for (int c = 0; c < BLOCK_N; c += 64) {
+          const int n0 = n_t * BLOCK_N + c;
+          if (n0 >= p.N) break;
+          uint8_t* buf = my_stg + stg_sel * kStgBytes;
+          if (lane == 0) bulk_wait_read<1>();            // the store that last used this buffer has read it
+          __syncwarp();
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_base + (uint32_t)(c + 32 * h), v);
+            tmem_ld_wait();
+            float f[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+            if (p.bias) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) if (n0 + 32 * h + j < p.N) f[j] += p.bias[n0 + 32 * h + j];
+            }
+#pragma unroll
+            for (int j = 0; j < 32; j += 8) {
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]);
+              __nv_bfloat162 h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
+              __nv_bfloat162 h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
+              uint4 pk;
+              pk.x = *(uint32_t*)&h0; pk.y = *(uint32_t*)&h1; pk.z = *(uint32_t*)&h2; pk.w = *(uint32_t*)&h3;
+              const int chunk16 = h * 4 + (j >> 3);                    // 16-byte chunk index within the 128-B row
+              *(uint4*)(buf + lane * 128 + ((chunk16 ^ (lane & 7)) << 4)) = pk;
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) { tma_store_2d(&tmC, buf, n0, m_t * kBlockM + quarter * 32); bulk_commit(); }
+          stg_sel ^= 1;
+        }
+      } else {
 #pragma unroll 1
       for (int c = 0; c < BLOCK_N; c += 32) {
         uint32_t v[32];
@@ -205,11 +254,13 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           }
         }
       }
+      }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
+    if (p.tma_store && lane == 0) bulk_wait_all();     // outstanding tile stores must land before exit
   }
   tc_fence_before();
   __syncthreads();
@@ -261,6 +312,17 @@ k_igemm_wgrad(const __grid_constant__ CUtensorMap tmA /* dY [Kpix, Cout] */,
         const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
         const int chunk0 = n_t * p.nb;
         const int nvalid = min(p.nb, p.chunks - chunk0);
+        // Everything that needs an integer division is hoisted out of the K loop (one producer thread
+        // feeds the whole SM): per-chunk (tap, channel) coordinates once per item, and the pixel
+        // coordinate of a K block advanced incrementally by 64 = sn*P*Q + sp*Q + sq.
+        int c_c[4]; uint16_t c_ow[4], c_oh[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int chunk = min(chunk0 + j, p.chunks - 1), tap = chunk / p.cchunks;
+          c_c[j] = (chunk - tap * p.cchunks) * 64; c_ow[j] = p.taps[tap].off_w; c_oh[j] = p.taps[tap].off_h;
+        }
+        int cn, cp, cq; decompose_pixel(kb0 * kBlockK, p.P_it, p.Q_it, cn, cp, cq);
+        const int sq = kBlockK % p.Q_it, t1 = kBlockK / p.Q_it, sp = t1 % p.P_it, sn = t1 / p.P_it;
         for (int kb = kb0; kb < kb1; ++kb) {
           const int pix0 = kb * kBlockK;
           mbar_wait(&empty_bar[stage], phase ^ 1, 11);
@@ -270,16 +332,18 @@ k_igemm_wgrad(const __grid_constant__ CUtensorMap tmA /* dY [Kpix, Cout] */,
           tma_load_2d(sA, &tmA, &full_bar[stage], m_t * kBlockM, pix0);
           tma_load_2d(sA + kChunkBytes, &tmA, &full_bar[stage], m_t * kBlockM + 64, pix0);
           if (p.b_mode == 1) {
-            int cn, cp, cq; decompose_pixel(pix0, p.P_it, p.Q_it, cn, cp, cq);
             const int cw = p.base_w + cq * p.step_w, ch = p.base_h + cp * p.step_h;
-            for (int j = 0; j < nvalid; ++j) {
-              const int chunk = chunk0 + j, tap = chunk / p.cchunks, cc = chunk - tap * p.cchunks;
-              tma_load_im2col_4d(sB + j * kChunkBytes, &tmB, &full_bar[stage], cc * 64, cw, ch, cn,
-                                 p.taps[tap].off_w, p.taps[tap].off_h);
-            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j < nvalid)
+                tma_load_im2col_4d(sB + j * kChunkBytes, &tmB, &full_bar[stage], c_c[j], cw, ch, cn, c_ow[j], c_oh[j]);
+            cq += sq; if (cq >= p.Q_it) { cq -= p.Q_it; cp += 1; }
+            cp += sp; if (cp >= p.P_it) { cp -= p.P_it; cn += 1; }
+            cn += sn;
           } else {
-            for (int j = 0; j < nvalid; ++j)
-              tma_load_2d(sB + j * kChunkBytes, &tmB, &full_bar[stage], (chunk0 + j) * 64, pix0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (j < nvalid) tma_load_2d(sB + j * kChunkBytes, &tmB, &full_bar[stage], (chunk0 + j) * 64, pix0);
           }
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
@@ -491,9 +555,9 @@ static int pick_block_n(long long m_tiles, int n) {
 }
 
 template <int BN>
-static int launch_fwd(const CUtensorMap& a, const CUtensorMap& b, const FwdParams& p, cudaStream_t st) {
+static int launch_fwd(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const FwdParams& p, cudaStream_t st) {
   constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  constexpr int smem = kStages * (kBlockM * kBlockK * 2 + BN * kBlockK * 2) + 1024 + 256;
+  constexpr int smem = kStages * (kBlockM * kBlockK * 2 + BN * kBlockK * 2) + 8 * 32 * 128 + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
     TP_CUDA_CHECK(cudaFuncSetAttribute(k_igemm_fwd<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -501,16 +565,30 @@ static int launch_fwd(const CUtensorMap& a, const CUtensorMap& b, const FwdParam
   }
   const long long tiles = (long long)((p.M + kBlockM - 1) / kBlockM) * ((p.N + BN - 1) / BN);
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  k_igemm_fwd<BN><<<grid, kThreads, smem, st>>>(a, b, p);
+  k_igemm_fwd<BN><<<grid, kThreads, smem, st>>>(a, b, c, p);
   TP_LAUNCH_CHECK();
   return TP_OK;
 }
 
-static int run_fwd(const CUtensorMap& a, const CUtensorMap& b, const FwdParams& p, cudaStream_t st) {
+// Output map for the TMA-store epilogue: [M rows][N cols] bf16, box = 32 rows x 64 cols, SW128.
+static int make_out_map(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld_elems) {
+  return make_tiled_map(m, ptr, cols, rows, ld_elems, 32);
+}
+
+static int run_fwd(const CUtensorMap& a, const CUtensorMap& b, FwdParams& p, cudaStream_t st) {
+  // linear output pixel order + 16-byte aligned rows -> stage through smem and store with TMA
+  CUtensorMap c = a;
+  const bool linear = p.osh == 1 && p.osw == 1 && p.oah == 0 && p.oaw == 0 &&
+                      p.out_row_pix == p.Q_it && p.out_img_pix == (long long)p.P_it * p.Q_it;
+  p.tma_store = 0;
+  if (linear && p.ldc % 8 == 0 && p.N % 8 == 0 && (((uintptr_t)p.out) & 15) == 0) {
+    int rc = make_out_map(&c, p.out, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldc); if (rc) return rc;
+    p.tma_store = 1;
+  }
   const int bn = pick_block_n((p.M + kBlockM - 1) / kBlockM, p.N);
-  if (bn == 256) return launch_fwd<256>(a, b, p, st);
-  if (bn == 128) return launch_fwd<128>(a, b, p, st);
-  return launch_fwd<64>(a, b, p, st);
+  if (bn == 256) return launch_fwd<256>(a, b, c, p, st);
+  if (bn == 128) return launch_fwd<128>(a, b, c, p, st);
+  return launch_fwd<64>(a, b, c, p, st);
 }
 
 }  // namespace tp
@@ -532,7 +610,7 @@ size_t tp_conv_workspace_bytes(const tp_conv_desc* d, int op) {
   const long long kpix = (long long)d->n * d->p * d->q;
   const int kblocks = (int)((kpix + 63) / 64);
   const int sms = sm_count();
-  int splits = (2 * sms + m_tiles * n_tiles - 1) / (m_tiles * n_tiles);
+  int splits = (2 * sms) / (m_tiles * n_tiles);          // fill two waves of CTAs, never spill into a third
   if (splits > kblocks) splits = kblocks;
   if (splits < 1) splits = 1;
   return (size_t)m_tiles * n_tiles * splits * kBlockM * nb * 64 * sizeof(float) + 1024;
@@ -677,7 +755,7 @@ int tp_conv_wgrad(const tp_conv_desc* d, const void* x, const void* dy, const vo
   p.n_tiles = (p.chunks + p.nb - 1) / p.nb;
   p.kblocks = (p.Kpix + 63) / 64;
   const int sms = sm_count();
-  int splits = (2 * sms + p.m_tiles * p.n_tiles - 1) / (p.m_tiles * p.n_tiles);
+  int splits = (2 * sms) / (p.m_tiles * p.n_tiles);      // fill two waves of CTAs, never spill into a third
   if (splits > p.kblocks) splits = p.kblocks;
   if (splits < 1) splits = 1;
   p.kb_per_split = (p.kblocks + splits - 1) / splits;
