@@ -145,6 +145,14 @@ int tp_bn_backward(const void* dz, const void* z, const void* y, int64_t m, int 
                    const void* save_mean, const void* save_invstd, int relu, void* dy, void* dres,
                    void* dweight, void* dbias, void* ws, size_t ws_bytes, void* stream);
 
+/* Max pooling on NHWC bf16 (square window k, stride, symmetric padding with -inf, NaN propagates like
+ * torch): forward writes y [n,p,q,c] and the uint8 arg-max window index idx [n,p,q,c]; backward gathers
+ * dx [n,h,w,c] from dy through idx (deterministic, no atomics).  c % 8 == 0. */
+int tp_maxpool_forward(const void* x, void* y, void* idx, int n, int h, int w, int c, int k, int stride, int pad,
+                       int p, int q, void* stream);
+int tp_maxpool_backward(const void* dy, const void* idx, void* dx, int n, int h, int w, int c, int k, int stride, int pad,
+                        int p, int q, void* stream);
+
 /* ---- optimizer ------------------------------------------------------------------------
  * torch.optim.SGD(momentum, weight_decay) as configured at
  * harness_definitions/standard_pruning_harness.py:70-75, one launch for all segments:

@@ -232,6 +232,16 @@ def g_bn():
         good = all(v < 1e-2 for v in e.values()) and int(bn.num_batches_tracked) == 1
         ok &= good
         print(f"  bn n{n} c{c} {h}x{w} relu={relu} res={res}: " + " ".join(f"{k}={v:.1e}" for k, v in e.items()) + (" OK" if good else " FAIL"))
+        if c % 8 == 0 and h >= 5:
+            from turboprune_b200.fused_norm import MaxPool2dB200
+            for (k_, s_, p_) in ((3, 2, 1), (2, 2, 0)):
+                xa2 = x.clone().requires_grad_(True); xb2 = x.clone().float().requires_grad_(True)
+                ya = MaxPool2dB200(k_, s_, p_)(xa2); yb = torch.nn.functional.max_pool2d(xb2, k_, s_, p_)
+                dyy = torch.randn(ya.shape, generator=g).to(dev).to(torch.bfloat16)
+                ya.backward(dyy); yb.backward(dyy.float())
+                mp_ok = torch.equal(ya.float(), yb) and _rel(xa2.grad, xb2.grad) < 1e-2
+                ok &= mp_ok
+                print(f"    maxpool k{k_} s{s_} p{p_}: fwd exact={torch.equal(ya.float(), yb)} bwd rel={_rel(xa2.grad, xb2.grad):.1e} {'OK' if mp_ok else 'FAIL'}")
         bn.eval(); ref.eval()
         with torch.no_grad():
             ze = bn(x, relu=relu); zre = ref(x.float()); zre = torch.relu(zre) if relu else zre

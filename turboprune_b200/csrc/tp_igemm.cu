@@ -111,7 +111,7 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int n_t = tile / m_tiles, m_t = tile % m_tiles;
+        const int m_t = tile / n_tiles, n_t = tile - m_t * n_tiles;   // m-major: the CTAs running together share A tiles (one HBM read), weights stay in L2
         const int m0 = m_t * kBlockM;
         int cn = 0, cp = 0, cq = 0;
         if (p.a_mode == 1) decompose_pixel(m0, p.P_it, p.Q_it, cn, cp, cq);
@@ -170,7 +170,7 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     int acc = 0; uint32_t acc_phase = 0;
     int stg_sel = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int n_t = tile / m_tiles, m_t = tile % m_tiles;
+      const int m_t = tile / n_tiles, n_t = tile - m_t * n_tiles;
       const int row = m_t * kBlockM + quarter * 32 + lane;
       const bool row_ok = row < p.M;
       long long opix = 0;

@@ -1,0 +1,130 @@
+// Max pooling (forward with saved arg-max, backward) for NHWC bf16 activations, sm_100a.
+// The torchvision stem's MaxPool2d(3, 2, 1) sits between the first masked conv block and layer1
+// (unmasked neighbours of the masked convs); ATen's NHWC kernels took 4.9 ms
+// per B=512 step (max_pool_backward_nhwc alone 3.4 ms), these stream at HBM rate.
+//   forward : one thread per (output pixel, 8 channels): 16-byte loads over the window, -inf padding,
+//             NaN propagates (torch semantics), first maximum wins; writes y and a uint8 window index
+//   backward: gather form (no atomics, deterministic): one thread per (input pixel, 8 channels) sums dy
+//             of the <= ceil(k/s)^2 windows whose arg-max is this pixel
+#include "tp_common.cuh"
+
+namespace tp {
+
+__device__ __forceinline__ void unpack8p(const uint4& v, float (&f)[8]) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
+}
+
+__global__ void __launch_bounds__(256) k_maxpool_fwd(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
+                                                     unsigned char* __restrict__ idx, int n, int h, int w, int c,
+                                                     int k, int stride, int pad, int p, int q) {
+  const int cv = c >> 3;
+  const long long total = (long long)n * p * q * cv;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int ci = (int)(i % cv); long long t = i / cv;
+    const int qi = (int)(t % q); t /= q;
+    const int pi = (int)(t % p); const int ni = (int)(t / p);
+    float best[8]; unsigned char bi[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
+    bool first = true;
+    for (int r = 0; r < k; ++r) {
+      const int hi = pi * stride - pad + r;
+      if (hi < 0 || hi >= h) continue;
+      for (int s = 0; s < k; ++s) {
+        const int wi = qi * stride - pad + s;
+        if (wi < 0 || wi >= w) continue;
+        float f[8];
+        unpack8p(*reinterpret_cast<const uint4*>(x + (((long long)ni * h + hi) * w + wi) * c + ci * 8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          // ATen: `if ((val > maxval) || isnan(val))` — the first in-bounds element seeds the index
+          if (first || f[j] > best[j] || f[j] != f[j]) { best[j] = first ? fmaxf(f[j], -INFINITY) : f[j]; bi[j] = (unsigned char)(r * k + s); if (first && f[j] != f[j]) best[j] = f[j]; }
+        }
+        first = false;
+      }
+    }
+    uint4 o; __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ho[j] = __floats2bfloat162_rn(best[2 * j], best[2 * j + 1]);
+    const long long ob = (((long long)ni * p + pi) * q + qi) * c + ci * 8;
+    *reinterpret_cast<uint4*>(y + ob) = o;
+    uint2 ib;
+    ib.x = bi[0] | (bi[1] << 8) | (bi[2] << 16) | ((unsigned)bi[3] << 24);
+    ib.y = bi[4] | (bi[5] << 8) | (bi[6] << 16) | ((unsigned)bi[7] << 24);
+    *reinterpret_cast<uint2*>(idx + ob) = ib;
+  }
+}
+
+__global__ void __launch_bounds__(256) k_maxpool_bwd(const __nv_bfloat16* __restrict__ dy, const unsigned char* __restrict__ idx,
+                                                     __nv_bfloat16* __restrict__ dx, int n, int h, int w, int c,
+                                                     int k, int stride, int pad, int p, int q) {
+  const int cv = c >> 3;
+  const long long total = (long long)n * h * w * cv;
+  for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int ci = (int)(i % cv); long long t = i / cv;
+    const int wi = (int)(t % w); t /= w;
+    const int hi = (int)(t % h); const int ni = (int)(t / h);
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    // output rows whose window covers input row hi: pi*stride - pad <= hi <= pi*stride - pad + k - 1
+    int p0 = hi + pad - (k - 1); p0 = p0 <= 0 ? 0 : (p0 + stride - 1) / stride;
+    int p1 = (hi + pad) / stride; if (p1 > p - 1) p1 = p - 1;
+    int q0 = wi + pad - (k - 1); q0 = q0 <= 0 ? 0 : (q0 + stride - 1) / stride;
+    int q1 = (wi + pad) / stride; if (q1 > q - 1) q1 = q - 1;
+    for (int pi = p0; pi <= p1; ++pi) {
+      const int r = hi + pad - pi * stride;
+      for (int qi = q0; qi <= q1; ++qi) {
+        const int s = wi + pad - qi * stride;
+        const unsigned char me = (unsigned char)(r * k + s);
+        const long long ob = (((long long)ni * p + pi) * q + qi) * c + ci * 8;
+        const uint2 ib = *reinterpret_cast<const uint2*>(idx + ob);
+        float g[8];
+        unpack8p(*reinterpret_cast<const uint4*>(dy + ob), g);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const unsigned char b = (unsigned char)(((j < 4 ? ib.x : ib.y) >> (8 * (j & 3))) & 0xff);
+          if (b == me) acc[j] += g[j];
+        }
+      }
+    }
+    uint4 o; __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) ho[j] = __floats2bfloat162_rn(acc[2 * j], acc[2 * j + 1]);
+    *reinterpret_cast<uint4*>(dx + (((long long)ni * h + hi) * w + wi) * c + ci * 8) = o;
+  }
+}
+
+}  // namespace tp
+
+using namespace tp;
+
+extern "C" {
+
+int tp_maxpool_forward(const void* x, void* y, void* idx, int n, int h, int w, int c, int k, int stride, int pad,
+                       int p, int q, void* stream) {
+  if (!x || !y || !idx || n <= 0 || c % 8 != 0 || k <= 0 || k * k > 255 || stride <= 0) return TP_ERR_INVALID;
+  int rc = bind_device_of(x); if (rc) return rc;
+  const long long total = (long long)n * p * q * (c / 8);
+  long long g = (total + 255) / 256, gm = (long long)sm_count() * 16;
+  k_maxpool_fwd<<<(unsigned)(g < gm ? g : gm), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y,
+      (unsigned char*)idx, n, h, w, c, k, stride, pad, p, q);
+  TP_LAUNCH_CHECK();
+  return TP_OK;
+}
+
+int tp_maxpool_backward(const void* dy, const void* idx, void* dx, int n, int h, int w, int c, int k, int stride, int pad,
+                        int p, int q, void* stream) {
+  if (!dy || !dx || !idx || n <= 0 || c % 8 != 0 || k <= 0 || stride <= 0) return TP_ERR_INVALID;
+  int rc = bind_device_of(dy); if (rc) return rc;
+  const long long total = (long long)n * h * w * (c / 8);
+  long long g = (total + 255) / 256, gm = (long long)sm_count() * 16;
+  k_maxpool_bwd<<<(unsigned)(g < gm ? g : gm), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const unsigned char*)idx,
+      (__nv_bfloat16*)dx, n, h, w, c, k, stride, pad, p, q);
+  TP_LAUNCH_CHECK();
+  return TP_OK;
+}
+
+}  // extern "C"

@@ -91,6 +91,51 @@ class BatchNorm2dB200(nn.BatchNorm2d):
                            momentum, self.eps, training, relu)
 
 
+class _MaxPoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k, stride, pad):
+        lib = _cabi.load()
+        n, c, h, w = x.shape
+        xn = ops.to_nhwc_bf16(x, c)
+        p = (h + 2 * pad - k) // stride + 1
+        q = (w + 2 * pad - k) // stride + 1
+        y = torch.empty(n, p, q, c, dtype=torch.bfloat16, device=x.device)
+        idx = torch.empty(n, p, q, c, dtype=torch.uint8, device=x.device)
+        with torch.cuda.device(x.device):
+            rc = lib.tp_maxpool_forward(_ptr(xn), _ptr(y), _ptr(idx), n, h, w, c, k, stride, pad, p, q, _cabi.stream_ptr(x.device))
+        _cabi.check(rc, "tp_maxpool_forward")
+        ops._count()
+        ctx.save_for_backward(idx)
+        ctx.geom = (n, h, w, c, k, stride, pad, p, q)
+        ctx.x_dtype = x.dtype
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = _cabi.load()
+        (idx,) = ctx.saved_tensors
+        n, h, w, c, k, stride, pad, p, q = ctx.geom
+        dyn = ops.to_nhwc_bf16(dy, c)
+        dx = torch.empty(n, h, w, c, dtype=torch.bfloat16, device=dy.device)
+        with torch.cuda.device(dy.device):
+            rc = lib.tp_maxpool_backward(_ptr(dyn), _ptr(idx), _ptr(dx), n, h, w, c, k, stride, pad, p, q, _cabi.stream_ptr(dy.device))
+        _cabi.check(rc, "tp_maxpool_backward")
+        ops._count()
+        gx = dx.permute(0, 3, 1, 2)
+        return (gx if gx.dtype == ctx.x_dtype else gx.to(ctx.x_dtype)), None, None, None
+
+
+class MaxPool2dB200(nn.MaxPool2d):
+    """nn.MaxPool2d whose CUDA/NHWC path is the sm_100a kernel pair (square window, no dilation / ceil_mode)."""
+
+    def forward(self, x):
+        k, s, p = self.kernel_size, self.stride, self.padding
+        simple = all(isinstance(v, int) for v in (k, s, p)) and self.dilation == 1 and not self.ceil_mode and not self.return_indices
+        if not (simple and x.is_cuda and x.dim() == 4 and x.shape[1] % 8 == 0 and k * k <= 255):
+            return super().forward(x)
+        return _MaxPoolFn.apply(x, k, s, p)
+
+
 # ---- fused forwards for the torchvision graphs the reference instantiates ------------------------------
 def _basic_block_forward(self, x):
     identity = x
@@ -143,6 +188,9 @@ def convert_batchnorm(module: nn.Module):
             new.load_state_dict(child.state_dict())
             new.train(child.training)
             setattr(module, name, new)
+        elif type(child) is nn.MaxPool2d:
+            setattr(module, name, MaxPool2dB200(child.kernel_size, child.stride, child.padding, child.dilation,
+                                                child.return_indices, child.ceil_mode))
         else:
             convert_batchnorm(child)
     return module
