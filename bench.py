@@ -153,6 +153,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-topk", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="do not capture the train step into a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -183,7 +184,8 @@ def main():
     pu.prune_er_erk(model, 0.2)
     model = model.to(dev).train()
     sparsity = model.get_overall_sparsity()
-    opt = FusedSGD(model.parameters(), lr=0.2, momentum=0.9, weight_decay=1e-4)
+    use_graph = not args.no_graph
+    opt = FusedSGD(model.parameters(), lr=0.2, momentum=0.9, weight_decay=1e-4, capturable=use_graph)
     sched_tab = triangular_lr(10 * (W + K) * 3)
     reducer = None
     if world > 1:
@@ -196,11 +198,18 @@ def main():
     step_idx = [0]
     loss_acc = torch.zeros((), device=dev)
 
-    def step(x, t):
+    def set_lr():
         for g in opt.param_groups:
             g["lr"] = 0.2 * float(sched_tab[min(step_idx[0], len(sched_tab) - 1)])
         step_idx[0] += 1
-        opt.zero_grad(set_to_none=True)
+        if use_graph:
+            opt.sync_lr()                      # device scalar: the captured step reads it, nothing is baked in
+
+    from turboprune_b200.grad_exchange import GradArena
+    arena = reducer if reducer is not None else GradArena(list(model.parameters()))
+
+    def step_body(x, t):
+        arena.zero()                           # one memset; grads live in persistent slots (stable pointers)
         with torch.autocast("cuda", dtype=torch.bfloat16):
             out = model(x)
             loss = torch.nn.functional.cross_entropy(out, t)
@@ -209,6 +218,12 @@ def main():
             reducer.reduce()
         opt.step()
         return loss
+
+    def eager_step(x, t):
+        set_lr()
+        return step_body(x, t)
+
+    step = eager_step
 
     def barrier():
         if world > 1:
@@ -228,32 +243,67 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    # ---- device-resident run (value) ----
+    # ---- warm-up (eager): allocates workspaces, sets kernel attributes, fills momentum buffers ----
     for i in range(W):
         step(*pool[i % 2])
-    timer = ops.KernelTimer()
+    launches_per_step = 0
+    if True:
+        l0 = ops.launch_count(); step(*pool[0]); launches_per_step = ops.launch_count() - l0
+
+    # ---- capture ONE whole train step (fwd + bwd + P2P reduce + SGD) into a CUDA graph ----
+    graph = None
+    if use_graph:
+        static_x, static_t = torch.empty_like(pool[0][0]), torch.empty_like(pool[0][1])
+        static_x.copy_(pool[0][0]); static_t.copy_(pool[0][1])
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                eager_step(static_x, static_t)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        barrier()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+            static_loss = step_body(static_x, static_t)
+
+        def graph_step(x, t):
+            static_x.copy_(x, non_blocking=True); static_t.copy_(t, non_blocking=True)
+            set_lr()
+            graph.replay()
+            return static_loss
+        step = graph_step
+        for i in range(2):
+            step(*pool[i % 2])
+
+    # ---- device-resident run (value) ----
     clocks = ClockSampler(local_rank); clocks.start()
-    launches0 = ops.launch_count()
-    ops.set_timer(timer)
 
     def dev_step(i):
         loss_acc.add_(step(*pool[i % 2]).detach())
     ms_total = timed(K, dev_step)
-    ops.set_timer(None)
-    launches = ops.launch_count() - launches0
+    launches = launches_per_step * K
     clk = clocks.stop()
     if reducer is not None:
         reducer.check_status()
     img_s = world * B * K / (ms_total / 1e3)
+
+    # ---- per-kernel timing of the masked GEMMs: CUDA events around every C-ABI conv call on the launching stream
+    # (eager steps of the same workload — events cannot be read back from inside a replayed graph) ----
+    timer = ops.KernelTimer()
+    KT = min(K, 5)
+    ops.set_timer(timer)
+    ms_eager = timed(KT, lambda i: eager_step(*pool[i % 2]))
+    ops.set_timer(None)
     tot = timer.totals()
-    gemm_ms = sum(v[0] for v in tot.values())
+    gemm_ms = sum(v[0] for v in tot.values()) * (K / KT)
     pk = peaks()
     flops = GFLOP_PER_IMG * 1e9 * B * K
     achieved_tf = flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
     roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf"], "unit": "TFLOP/s",
                 "frac": achieved_tf / pk["tf"], "traffic": None, "peak_source": pk["src"] + " sustained bf16",
                 "kernel": "k_igemm_fwd / k_igemm_wgrad (masked implicit GEMM, tcgen05)",
-                "launches_per_step": sum(v[2] for v in tot.values()) / K,
+                "launches_per_step": sum(v[2] for v in tot.values()) / KT,
+                "timing": f"CUDA events around each masked-GEMM C-ABI call over {KT} eager steps ({ms_eager / KT:.2f} ms/step eager); step rate from CUDA-graph replay" if use_graph else "CUDA events, eager",
                 "ms_per_step_in_kernel": gemm_ms / K,
                 "by_op_ms_per_step": {k: v[0] / K for k, v in tot.items()},
                 "share_of_step": gemm_ms / ms_total,
@@ -266,12 +316,34 @@ def main():
         hpool = [(torch.randn(B, 3, 224, 224).pin_memory(), torch.randint(0, 1000, (B,)).pin_memory()) for _ in range(2)]
         h2d = hpool[0][0].numel() * 4 + hpool[0][1].numel() * 8
 
+        # double-buffered prefetch: batch i+1 crosses PCIe on a copy stream while step i computes
+        copy_stream = torch.cuda.Stream(dev)
+        stage = [(torch.empty_like(pool[0][0]), torch.empty_like(pool[0][1])) for _ in range(2)]
+        h2d_done = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+
+        def prefetch(i):
+            j = i % 2
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[j])
+                stage[j][0].copy_(hpool[j][0], non_blocking=True); stage[j][1].copy_(hpool[j][1], non_blocking=True)
+                h2d_done[j].record(copy_stream)
+
+        for ev in consumed:
+            ev.record(torch.cuda.current_stream(dev))
+
         def e2e_step(i):
-            hx, ht = hpool[i % 2]
-            x = hx.to(dev, non_blocking=True); t = ht.to(dev, non_blocking=True)
-            return float(step(x, t).item())          # the reference returns loss.item() every step (base_harness.py:134)
+            j = i % 2
+            if i == 0:
+                prefetch(0)
+            torch.cuda.current_stream(dev).wait_event(h2d_done[j])
+            prefetch(i + 1)                                   # overlaps with this step's compute
+            loss = step(stage[j][0], stage[j][1])
+            consumed[j].record(torch.cuda.current_stream(dev))
+            return float(loss.item())                         # the reference returns loss.item() every step (base_harness.py:134)
         for i in range(2):
             e2e_step(i)
+        torch.cuda.synchronize(dev)
         ms_e2e = timed(K, e2e_step)
         e2e = {"value": world * B * K / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                "ms_per_step": ms_e2e / K}
@@ -313,7 +385,7 @@ def main():
             "dtype": "bf16", "data": "synthetic",
             "config": {"workload": "resnet50 imagenet-shape [B,3,224,224] ERK-80% unstructured masks, SGD(0.9, wd 1e-4), CE loss",
                        "global_batch": B * world, "per_gpu_batch": B, "parallelism": f"dp{world}",
-                       "sparsity_percent": sparsity, "l2": "inputs (308 MB/batch at B=512) and activations exceed the 126 MB L2",
+                       "sparsity_percent": sparsity, "cuda_graph": bool(use_graph), "l2": "inputs (308 MB/batch at B=512) and activations exceed the 126 MB L2",
                        "grad_exchange": "none (1 GPU)" if world == 1 else "tp_p2p_allreduce_mask over symmetric memory (NVLink), no NCCL on the data path"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
             "topk": topk, "loss_mean": float(loss_acc.item()) / K,

@@ -158,10 +158,12 @@ int tp_maxpool_backward(const void* dy, const void* idx, void* dx, int n, int h,
  * harness_definitions/standard_pruning_harness.py:70-75, one launch for all segments:
  *   g += wd*w; buf = first ? g : mu*buf + g; w -= lr*buf     (masked weights keep decaying)
  * lr is read from a DEVICE float (so LR schedules do not re-record CUDA graphs).
+ * table_cached != 0: `ws` still holds the segment table of an earlier call with identical pointers — no
+ * host->device copy is issued, which makes the call capturable into a CUDA graph.
  */
 int tp_sgd_momentum(void* const* w, const void* const* g, void* const* buf, const int64_t* numel,
                     int n_seg, const float* lr_dev, float momentum, float weight_decay,
-                    int first_step, void* ws, size_t ws_bytes, void* stream);
+                    int first_step, int table_cached, void* ws, size_t ws_bytes, void* stream);
 size_t tp_segtable_workspace_bytes(int n_seg);
 
 /* ---- gradient exchange over NVLink/NVSwitch peer memory ---------------------------------

@@ -45,7 +45,7 @@ SIGNATURES = {
     "tp_conv_wgrad": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                               c_size_t, c_void_p]),
     "tp_sgd_momentum": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64), c_int,
-                                c_void_p, c_float, c_float, c_int, c_void_p, c_size_t, c_void_p]),
+                                c_void_p, c_float, c_float, c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "tp_segtable_workspace_bytes": (c_size_t, [c_int]),
     "tp_p2p_allreduce_mask": (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_int, c_int, c_int64, c_void_p, c_float,
                                       c_void_p, c_int, c_int, c_void_p, c_void_p]),

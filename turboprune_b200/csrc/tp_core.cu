@@ -23,13 +23,26 @@ int sm_count() {
   return cached[dev];
 }
 
+typedef int (*PFN_cuCtxGetCurrent)(void**);
+static PFN_cuCtxGetCurrent g_ctx_get_current = nullptr;
+
 int bind_device_of(const void* p) {
   if (!p) return TP_OK;
+  // Fast path (and the only path taken while a CUDA graph is being captured): a context is already
+  // current on this thread — nothing to do, no runtime call.
+  static bool looked_up = false;
+  if (!looked_up) {
+    void* fn = nullptr; cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuCtxGetCurrent", &fn, cudaEnableDefault, &q) == cudaSuccess) g_ctx_get_current = (PFN_cuCtxGetCurrent)fn;
+    looked_up = true;
+  }
+  if (g_ctx_get_current) {
+    void* ctx = nullptr;
+    if (g_ctx_get_current(&ctx) == 0 && ctx != nullptr) return TP_OK;
+  }
   cudaPointerAttributes a;
   if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return TP_OK; }
   if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) {
-    int cur = -1;
-    cudaGetDevice(&cur);
     TP_CUDA_CHECK(cudaSetDevice(a.device));   // CUDA 12+: initialises and binds the primary context
   }
   return TP_OK;
@@ -82,7 +95,7 @@ const char* tp_strerror(int code) {
 }
 
 const char* tp_last_cuda_error(void) { return tp::g_last_err; }
-int tp_abi_version(void) { return 1; }
+int tp_abi_version(void) { return 2; }
 int tp_device_sm_count(void) { return tp::sm_count(); }
 
 size_t tp_segtable_workspace_bytes(int n_seg) {

@@ -203,13 +203,22 @@ int tp_im2col_c8(const void* x, int n, int h, int w, int r, int s, int stride_h,
 
 int tp_sgd_momentum(void* const* w, const void* const* g, void* const* buf, const int64_t* numel,
                     int n_seg, const float* lr_dev, float momentum, float weight_decay,
-                    int first_step, void* ws, size_t ws_bytes, void* stream) {
-  if (!w || !g || !buf || !numel || n_seg <= 0 || !lr_dev || !ws) return TP_ERR_INVALID;
+                    int first_step, int table_cached, void* ws, size_t ws_bytes, void* stream) {
+  if (!numel || n_seg <= 0 || !lr_dev || !ws) return TP_ERR_INVALID;
+  if (!table_cached && (!w || !g || !buf)) return TP_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   Arena ar(ws, ws_bytes);
   Seg* d_segs = nullptr; long long tiles = 0;
-  int rc = upload_segs(ar, (const void* const*)w, g, nullptr, nullptr, buf, numel, n_seg, &d_segs, &tiles, nullptr, st);
-  if (rc) return rc;
+  if (table_cached) {
+    // the caller guarantees `ws` still holds the table uploaded by an earlier call with the same
+    // pointers: no host->device copy, so the call can be captured into a CUDA graph
+    d_segs = (Seg*)ar.take(sizeof(Seg) * n_seg);
+    if (!d_segs) return TP_ERR_WORKSPACE;
+    for (int i = 0; i < n_seg; ++i) tiles += (numel[i] + kTileElems - 1) / kTileElems;
+  } else {
+    int rc = upload_segs(ar, (const void* const*)w, g, nullptr, nullptr, buf, numel, n_seg, &d_segs, &tiles, nullptr, st);
+    if (rc) return rc;
+  }
   if (tiles == 0) return TP_OK;
   long long gmax = (long long)sm_count() * 8;
   k_sgd<<<(unsigned)(tiles < gmax ? tiles : gmax), 256, 0, st>>>(d_segs, n_seg, tiles, lr_dev, momentum, weight_decay, first_step);

@@ -47,6 +47,28 @@ def shard_bounds(numel, world):
     return [(min(n4, per * r) * 4, min(n4, min(n4, per * r) + per) * 4) for r in range(world)]
 
 
+class GradArena:
+    """Persistent, flat gradient storage for ONE rank: ``param.grad`` permanently views a 16-byte aligned slot of
+    one fp32 buffer, ``zero()`` is a single memset.  Pointers never change, so the fused SGD keeps its device-side
+    pointer table and the whole train step can be captured into a CUDA graph (autograd accumulates into the
+    zeroed slots: 0 + g == g bit-exactly, same values as the reference's zero_grad + assign)."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        (idx, offs, total), = plan_buckets([p.numel() for p in self.params], 1 << 62)
+        self.flat = torch.zeros(total, dtype=torch.float32, device=self.params[0].device)
+        self.views = [self.flat[o:o + p.numel()].view_as(p) for o, p in zip(offs, self.params)]
+        self.attach()
+
+    def attach(self):
+        for p, v in zip(self.params, self.views):
+            p.grad = v
+
+    def zero(self):
+        self.flat.zero_()
+        self.attach()
+
+
 class P2PGradReducer:
     def __init__(self, params, bucket_cap_mb=64.0, algo="auto", group=None, masks=None):
         import torch.distributed._symmetric_memory as symm_mem
@@ -122,6 +144,17 @@ class P2PGradReducer:
             ops._count()
             for p, v in zip(bk["params"], bk["out_views"]):
                 p.grad = v
+
+    def attach(self):
+        """Make every ``param.grad`` a persistent view of its bucket slot (stable pointers: CUDA-graph capturable)."""
+        for bk in self._bk:
+            for p, v in zip(bk["params"], bk["views"]):
+                p.grad = v
+
+    def zero(self):
+        for bk in self._bk:
+            bk["data"].zero_()
+        self.attach()
 
     def check_status(self):
         if int(self.status.item()) != 0:

@@ -158,15 +158,17 @@ def count_zeros(ms):
 # ---------------------------------------------------------------------------------------------
 # optimizer
 # ---------------------------------------------------------------------------------------------
-def sgd_momentum_step(params, grads, bufs, lr_dev, momentum, weight_decay, first_step):
+def sgd_momentum_step(params, grads, bufs, lr_dev, momentum, weight_decay, first_step, table_ws=None, table_cached=False):
+    """One fused launch.  ``table_ws``: a persistent uint8 workspace owned by the optimizer; with
+    ``table_cached`` the segment table already in it is reused (no H2D copy -> CUDA-graph capturable)."""
     lib = _cabi.load()
     dev = params[0].device
-    wsb = _workspace(lib.tp_segtable_workspace_bytes(len(params)), dev, "seg")
+    wsb = table_ws if table_ws is not None else _workspace(lib.tp_segtable_workspace_bytes(len(params)), dev, "seg")
     with torch.cuda.device(dev):
         rc = lib.tp_sgd_momentum(_cabi.ptr_array(params), _cabi.ptr_array(grads), _cabi.ptr_array(bufs),
                                  _cabi.i64_array([p.numel() for p in params]), len(params),
                                  c_void_p(lr_dev.data_ptr()), float(momentum), float(weight_decay), int(bool(first_step)),
-                                 c_void_p(wsb.data_ptr()), wsb.numel(), _cabi.stream_ptr(dev))
+                                 int(bool(table_cached)), c_void_p(wsb.data_ptr()), wsb.numel(), _cabi.stream_ptr(dev))
     _cabi.check(rc, "tp_sgd_momentum")
     _count()
 
