@@ -113,3 +113,24 @@ def test_fused_sgd_state_dict_is_torch_compatible():
         assert ga[key] == gb[key]
     sched = torch.optim.lr_scheduler.LambdaLR(a, lambda i: 0.5)
     assert a.param_groups[0]["lr"] == pytest.approx(0.1)
+
+
+def test_config_composer_and_densities():
+    from turboprune_b200.utils import config as C
+    from turboprune_b200.utils.harness_utils import generate_densities
+    c = C.compose("synthetic_rn18_imp", ["experiment_params.epochs_per_level=3"], os.path.join(ROOT, "conf_b200"))
+    assert c.pruning_params.prune_method == "mag" and c.experiment_params.epochs_per_level == 3
+    assert isinstance(c.optimizer_params.weight_decay, float)             # '5e-4' is a float like under hydra
+    assert generate_densities(c, 0.0) == [1.0, 0.8]
+    with pytest.raises(KeyError):
+        C.compose("synthetic_rn18_imp", ["pruning_params.rewind_epoch=1"], os.path.join(ROOT, "conf_b200"))   # needs '+'
+    c = C.compose("synthetic_rn18_imp", ["+pruning_params.rewind_epoch=1", "pruning_params=er_erk_80"], os.path.join(ROOT, "conf_b200"))
+    assert c.pruning_params.prune_method == "er_erk" and c.pruning_params.rewind_epoch == 1
+    ref_conf = "/root/reference/conf"
+    if os.path.isdir(ref_conf):         # the reference's own tree, consumed unchanged
+        c = C.compose("cifar10_er_erk", ["pruning_params=iterative_imp", "pruning_params.target_sparsity=0.2"], ref_conf)
+        assert generate_densities(c, 0.0) == [1.0, 0.8] and c.model_params.model_name == "resnet18"
+        c = C.compose("imagenet_er_balanced", ["pruning_params=pai_er_erk", "+pruning_params.target_sparsity=0.8"], ref_conf)
+        assert c.dataset_params.total_batch_size == 512 and generate_densities(c, 0.0) == [1 - 0.8]
+        c = C.compose("imagenet_er_balanced", ["pruning_params=iterative_wr", "pruning_params.target_sparsity=0.988"], ref_conf)
+        assert len(generate_densities(c, 0.0)) == 21

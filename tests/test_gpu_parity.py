@@ -334,3 +334,32 @@ def test_train_step_loss_and_grads_vs_oracle(dev):
     for (_, m), (_, r) in zip(mine._masked(), om.masked_layers(ref)):
         assert bool((m.weight.grad[m.mask == 0] == 0).all())
         assert _rel(m.weight, r.weight) < 5e-3      # lr * (bf16 gradient noise) on top of identical decay
+
+
+def test_run_experiment_level_loop(dev, tmp_path):
+    """Config #1 (ResNet-18 / CIFAR-10-shape, IMP, 1 prune cycle) through run_experiment.main on synthetic data:
+    levels [1.0, 0.8], checkpoints in the reference's layout, 20 % sparsity after the cycle, weights rewound to init."""
+    import csv
+    import run_experiment
+    from turboprune_b200.utils import config as C
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = C.compose("synthetic_rn18_imp", ["dataset_params.total_batch_size=64", "dataset_params.synthetic_steps_per_epoch=3",
+                                           f"experiment_params.base_dir={tmp_path}"], os.path.join(root, "conf_b200"))
+    prefix, expt = run_experiment.main(cfg)
+    ck = os.path.join(expt, "checkpoints")
+    for name in ("model_init.pt", "model_level_0.pt", "model_level_1.pt"):
+        assert os.path.isfile(os.path.join(ck, name)), name
+    assert os.path.isfile(os.path.join(expt, "artifacts", "optimizer_init.pt"))
+    rows = list(csv.DictReader(open(os.path.join(expt, f"{prefix}_summary.csv"))))
+    assert [r["Level"] for r in rows] == ["0", "1"]
+    assert float(rows[0]["Sparsity"]) == 0.0 and abs(float(rows[1]["Sparsity"]) - 20.0) < 1e-3
+    init = torch.load(os.path.join(ck, "model_init.pt")); lvl0 = torch.load(os.path.join(ck, "model_level_0.pt"))
+    lvl1 = torch.load(os.path.join(ck, "model_level_1.pt"))
+    assert set(init) == set(lvl1) and init["fc.weight"].shape == (10, 512, 1) and "conv1.mask" in init
+    # the level-1 mask is the magnitude mask of the level-0 weights (global threshold, ties pruned)
+    from oracle import prune as P
+    names = [k[:-5] for k in lvl0 if k.endswith(".mask")]
+    ws = [lvl0[n + ".weight"].cpu().numpy() for n in names]; ms = [lvl0[n + ".mask"].cpu().numpy() for n in names]
+    ref_masks, _, _ = P.prune_global(ws, ms, 0.8)
+    for n, rm in zip(names, ref_masks):
+        assert np.array_equal(lvl1[n + ".mask"].cpu().numpy(), rm), n

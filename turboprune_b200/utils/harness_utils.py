@@ -1,0 +1,74 @@
+"""Host-side helpers kept from the reference's ``utils/harness_utils.py`` (only what the hot path touches)."""
+import os
+import random
+import uuid
+from datetime import datetime
+
+import numpy as np
+import torch
+import yaml
+
+
+def set_seed(cfg, is_deterministic: bool = False) -> None:
+    """np / random / torch / cuda seeds from experiment_params.seed (reference harness_utils.py:97-114)."""
+    seed = cfg.experiment_params.seed
+    np.random.seed(seed); random.seed(seed); torch.manual_seed(seed)
+    if torch.cuda.is_available():
+        torch.cuda.manual_seed(seed)
+    os.environ["PYTHONHASHSEED"] = str(seed)
+
+
+def generate_densities(cfg, current_sparsity: float):
+    """Density per level (reference harness_utils.py:117-145).  Float64 on the host on purpose:
+    ``k = int((1 - density) * N)`` must come out identical.  Level 0 of iterative methods is dense."""
+    method = cfg.pruning_params.prune_method
+    target = cfg.pruning_params.target_sparsity
+    if method in ("mag", "random_erk", "random_balanced"):
+        rate = cfg.pruning_params.prune_rate
+        out, cur, goal = [], 1 - current_sparsity, 1 - target
+        while cur > goal:
+            out.append(cur)
+            cur *= 1 - rate
+        if cur <= goal:
+            out.append(cur)
+        return out
+    if method in ("er_erk", "er_balanced", "synflow", "snip"):
+        return [1 - target]
+    if method == "just dont":
+        return [1.0]
+    raise ValueError(f"Unknown pruning method: {method}")
+
+
+def gen_expt_dir(cfg):
+    """<base_dir>/<prefix>__<uuid6>__<time>/{checkpoints,metrics/level_wise_metrics,artifacts} (reference :49-94)."""
+    prefix = (f"{cfg.dataset_params.dataset_name}_model_{cfg.model_params.model_name}"
+              f"_trainingtype_{cfg.pruning_params.training_type}_prunemethod_{cfg.pruning_params.prune_method}"
+              f"_target_{cfg.pruning_params.target_sparsity:.2f}_seed_{cfg.experiment_params.seed}"
+              f"_budget_{cfg.experiment_params.epochs_per_level}epochs_lr_{cfg.optimizer_params.lr:.3f}"
+              f"_mom_{cfg.optimizer_params.momentum:.1f}_wd_{cfg.optimizer_params.weight_decay:.4f}"
+              f"_sched_{cfg.optimizer_params.scheduler_type}")
+    expt_dir = os.path.join(cfg.experiment_params.base_dir,
+                            f"{prefix}__{uuid.uuid4().hex[:6]}__{datetime.now().strftime('%Y%m%d_%H%M%S')}")
+    for sub in ("checkpoints", "metrics/level_wise_metrics", "artifacts"):
+        os.makedirs(os.path.join(expt_dir, sub), exist_ok=True)
+    return prefix, expt_dir
+
+
+def save_config(expt_dir, cfg) -> None:
+    def plain(x):
+        return {k: plain(v) for k, v in x.items()} if isinstance(x, dict) else x
+    with open(os.path.join(expt_dir, "expt_config.yaml"), "w") as f:
+        yaml.dump(plain(cfg), f, default_flow_style=False)
+
+
+def unwrap(model):
+    """PruneModel.model of a possibly wrapped model (reference save_model, harness_utils.py:354-365)."""
+    m = getattr(model, "_orig_mod", model)
+    m = getattr(m, "module", m)
+    return m.model
+
+
+def save_model(model, save_path, distributed: bool = False) -> None:
+    """State dict of the INNER torchvision net: keys ``conv1.weight``, ``conv1.mask`` ... (checkpoint compatible)."""
+    torch.save(unwrap(model).state_dict(), save_path)
+    print(f"Model saved to {save_path}")

@@ -180,7 +180,8 @@ def prune_er_balanced(model: nn.Module, er_sparse_init: float):
 
 def prune_the_model(cfg, harness, target_density: float) -> None:
     """Dispatcher by ``cfg.pruning_params.prune_method`` (reference :23-58)."""
-    model = harness.model.module if harness.distributed else harness.model
+    # the reference unwraps DDP here (:25); our harness keeps the bare module and reduces gradients explicitly
+    model = getattr(harness.model, "module", harness.model)
     console = harness.console
     method = cfg.pruning_params.prune_method
     loader = harness.train_loader if method in {"synflow", "snip"} else None
