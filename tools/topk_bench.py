@@ -13,14 +13,15 @@ def run(n, nseg, density, kind=0, reps=7, flush=True):
     ms = [torch.ones(s, device=dev) for s in sizes]
     gs = [torch.randn(s, device=dev) * 1e-3 for s in sizes] if kind else None
     k = int((1 - density) * n)
+    plan = ops.TopKPlan(ws, ms, gs=gs, kind=kind)
     for _ in range(2):
-        ops.topk_threshold_mask(ws, ms, k, gs=gs, kind=kind)
+        plan.run(k)
     fl = torch.empty(64 << 20, dtype=torch.float32, device=dev)
     ts = []
     for _ in range(reps):
         if flush: fl.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); _, thr, info = ops.topk_threshold_mask(ws, ms, k, gs=gs, kind=kind); b.record(); torch.cuda.synchronize()
+        a.record(); _, thr, info = plan.run(k); b.record(); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
     t = statistics.median(ts); bpe = 12 if kind == 0 else 16
     print(f"N={n} segs={nseg} density={density} kind={kind}: {t*1e3:.1f} us  {bpe*n/t/1e6:.0f} GB/s  info={info}", flush=True)

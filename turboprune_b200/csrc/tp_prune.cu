@@ -112,12 +112,24 @@ __global__ void __launch_bounds__(256) k_sample_coarse(const Seg* __restrict__ s
   const int t = threadIdx.x;
   for (int i = t; i < kDigitBins; i += 256) s_h[i] = 0;
   __syncthreads();
-  for (long long j = blockIdx.x * 256ll + t; j < S; j += (long long)gridDim.x * 256) {
-    long long e = (long long)(((unsigned long long)j * (unsigned long long)N) / (unsigned long long)S);
-    int si = find_seg_by_elem(segs, n_seg, e);
-    unsigned int key = seg_key<KIND>(segs[si], e - segs[si].start);
-    skeys[j] = key;
-    atomicAdd(&s_h[key >> kCoarseShift], 1u);
+  // samples are taken in runs of 4 neighbouring elements: one 32-byte sector per operand serves 4 samples
+  // (a quarter of the scattered DRAM traffic and of the segment searches of single-element sampling)
+  const long long G = (S + 3) >> 2;
+  for (long long gi = blockIdx.x * 256ll + t; gi < G; gi += (long long)gridDim.x * 256) {
+    long long e = (long long)(((unsigned long long)gi * (unsigned long long)N) / (unsigned long long)G);
+    const int si = find_seg_by_elem(segs, n_seg, e);
+    const Seg& sg = segs[si];
+    long long l0 = (e - sg.start) & ~3ll;
+    if (l0 + 3 >= sg.n) l0 = sg.n >= 4 ? sg.n - 4 : 0;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long j = gi * 4 + u;
+      if (j >= S) break;
+      const long long l = l0 + u < sg.n ? l0 + u : sg.n - 1;
+      const unsigned int key = seg_key<KIND>(sg, l);
+      skeys[j] = key;
+      atomicAdd(&s_h[key >> kCoarseShift], 1u);
+    }
   }
   __syncthreads();
   for (int i = t; i < kDigitBins; i += 256) if (s_h[i]) atomicAdd(&hist_c[i], s_h[i]);
@@ -269,9 +281,34 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep(const Seg* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_resolve(const Seg* __restrict__ segs, int n_seg, SelState* st,
-                                                  uint2* __restrict__ cand, unsigned int cap,
-                                                  float* __restrict__ thr_out, int write_masks) {
+// Resolve, stage 1 (multi-CTA): decide success of the bracket and histogram the FIRST radix digit of all
+// candidates (the pass that touches every candidate) with shared-memory privatised bins.
+__device__ __forceinline__ int resolve_shift0(unsigned int lo, unsigned int hi) {
+  const unsigned int span = lo ^ (hi - 1u);
+  const int top = span ? (31 - __clz(span)) : 0;
+  return (top / 11) * 11;
+}
+
+__global__ void __launch_bounds__(256) k_cand_hist(const SelState* __restrict__ st, const uint2* __restrict__ cand,
+                                                   unsigned int cap, unsigned int* __restrict__ hist_r) {
+  __shared__ unsigned int s_h[kDigitBins];
+  const unsigned long long k = st->k, A = st->n_lt, B = st->n_eq, C = st->n_cand;
+  if (k <= A + B || C > cap || k > A + B + C) return;        // nothing to select (k_resolve decides what it means)
+  const int t = threadIdx.x;
+  for (int i = t; i < kDigitBins; i += 256) s_h[i] = 0;
+  __syncthreads();
+  const int shift = resolve_shift0(st->lo, st->hi);
+  const unsigned int n = (unsigned int)C;
+  for (unsigned int i = blockIdx.x * 256u + t; i < n; i += gridDim.x * 256u)
+    atomicAdd(&s_h[(cand[i].x >> shift) & (kDigitBins - 1)], 1u);
+  __syncthreads();
+  for (int i = t; i < kDigitBins; i += 256) if (s_h[i]) atomicAdd(&hist_r[i], s_h[i]);
+}
+
+// Resolve, stage 2 (one CTA): pick the first digit from the global histogram, finish the remaining digits over
+// the (now ~1/2048-th) matching candidates, publish threshold and status.
+__global__ void __launch_bounds__(1024) k_resolve(SelState* st, const uint2* __restrict__ cand, unsigned int cap,
+                                                  const unsigned int* __restrict__ hist_r, float* __restrict__ thr_out) {
   __shared__ unsigned int s_hist[kDigitBins];
   __shared__ unsigned int s_prefix, s_bin;
   __shared__ unsigned long long s_before, s_krem, s_warp[32];
@@ -284,7 +321,6 @@ __global__ void __launch_bounds__(1024) k_resolve(const Seg* __restrict__ segs, 
     else if (k <= A + B) { st->thr_key = st->lo; }
     else if (k > A + B + C) status = 1;           // k-th lies above the bracket
     s_status = status;
-    s_prefix = 0;
     s_krem = k - A - B;
   }
   __syncthreads();
@@ -292,20 +328,18 @@ __global__ void __launch_bounds__(1024) k_resolve(const Seg* __restrict__ segs, 
   const unsigned int n = (unsigned int)C;
   constexpr int U = 8;                            // independent L2 loads in flight per thread
   if (k > A + B) {
-    // exact select of the s_krem-th smallest candidate key: 11-bit radix passes, MSB first.
-    // Every candidate lies in (lo, hi), so the bits above the highest bit in which lo and hi-1
-    // differ are common to all of them: start below those (a narrow bracket needs 2 passes).
-    const unsigned int span = st->lo ^ (st->hi - 1u);
-    const int top = span ? (31 - __clz(span)) : 0;
-    const int shift0 = (top / 11) * 11;
-    if (t == 0) s_prefix = (shift0 + 11 >= 32) ? 0u : (st->lo & (0xFFFFFFFFu << (shift0 + 11)));
+    const int shift0 = resolve_shift0(st->lo, st->hi);
+    if (t == 0) { s_prefix = (shift0 + 11 >= 32) ? 0u : (st->lo & (0xFFFFFFFFu << (shift0 + 11))); s_bin = 0; s_before = 0; }
     __syncthreads();
-    for (int shift = shift0; shift >= 0; shift -= 11) {
+    block_find_rank<kDigitBins / 1024>(hist_r, s_krem, &s_bin, &s_before, s_warp);
+    if (t == 0) { s_prefix |= (s_bin << shift0); s_krem -= s_before; }
+    __syncthreads();
+    for (int shift = shift0 - 11; shift >= 0; shift -= 11) {
       for (int i = t; i < kDigitBins; i += 1024) s_hist[i] = 0;
       if (t == 0) { s_bin = 0; s_before = 0; }
       __syncthreads();
       const unsigned int prefix = s_prefix;
-      const unsigned int pmask = (shift + 11 >= 32) ? 0u : (0xFFFFFFFFu << (shift + 11));
+      const unsigned int pmask = 0xFFFFFFFFu << (shift + 11);
       for (unsigned int base = 0; base < n; base += 1024 * U) {
         unsigned int key[U]; bool ok[U];
 #pragma unroll
@@ -326,27 +360,22 @@ __global__ void __launch_bounds__(1024) k_resolve(const Seg* __restrict__ segs, 
     if (t == 0) st->thr_key = s_prefix;
   }
   __syncthreads();
-  const unsigned int thr = st->thr_key;
   if (t == 0) {
+    const unsigned int thr = st->thr_key;
     *thr_out = __uint_as_float(thr);
     st->status = (thr > 0x7f800000u) ? 2 : 0;
   }
-  if (write_masks && thr <= 0x7f800000u) {
-    for (unsigned int base = 0; base < n; base += 1024 * U) {
-      uint2 c[U]; bool ok[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const unsigned int i = base + u * 1024 + t;
-        ok[u] = i < n;
-        c[u] = ok[u] ? cand[i] : make_uint2(0u, 0u);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (!ok[u]) continue;
-        int si = find_seg_by_elem(segs, n_seg, (long long)c[u].y);
-        segs[si].mo[(long long)c[u].y - segs[si].start] = (c[u].x <= thr) ? 0.f : 1.f;
-      }
-    }
+}
+
+// Resolve, stage 3 (multi-CTA): final mask value of every candidate (the sweep wrote a provisional 0).
+__global__ void __launch_bounds__(256) k_cand_patch(const Seg* __restrict__ segs, int n_seg, const SelState* __restrict__ st,
+                                                    const uint2* __restrict__ cand, unsigned int cap) {
+  if (st->status != 0 || st->n_cand > cap) return;          // fallback / NaN threshold: another kernel rewrites every mask
+  const unsigned int thr = st->thr_key, n = (unsigned int)st->n_cand;
+  for (unsigned int i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
+    const uint2 c = cand[i];
+    const int si = find_seg_by_elem(segs, n_seg, (long long)c.y);
+    segs[si].mo[(long long)c.y - segs[si].start] = (c.x <= thr) ? 0.f : 1.f;
   }
 }
 
@@ -492,8 +521,8 @@ static int run_topk(const Seg* d_segs, int n_seg, long long tiles, long long N, 
   h.k = (unsigned long long)k;
   h.hi = 0x80000000u;
   TP_CUDA_CHECK(cudaMemcpyAsync(d_st, &h, sizeof(h), cudaMemcpyHostToDevice, st));
-  // d_hist layout: [0,2048) coarse sample histogram, [2048, 6144) two fine histograms
-  TP_CUDA_CHECK(cudaMemsetAsync(d_hist, 0, sizeof(unsigned int) * 3 * kDigitBins, st));
+  // d_hist layout: [0,2048) coarse sample histogram, [2048, 6144) two fine histograms, [6144, 8192) candidate digit
+  TP_CUDA_CHECK(cudaMemsetAsync(d_hist, 0, sizeof(unsigned int) * 4 * kDigitBins, st));
   const long long S = N < (1ll << kSampleBits) ? N : (1ll << kSampleBits);
   // sample rank of the population's k-th element and the +-5 sigma band of its sampling error
   long long rs = (long long)(((unsigned __int128)(unsigned long long)k * (unsigned long long)S + (unsigned long long)N - 1) /
@@ -501,7 +530,8 @@ static int run_topk(const Seg* d_segs, int n_seg, long long tiles, long long N, 
   if (rs < 1) rs = 1;
   if (rs > S) rs = S;
   const double pq = (double)rs / (double)S;
-  const long long delta = (S == N) ? 0 : (long long)(5.0 * sqrt((double)S * pq * (1.0 - pq)) + 8.0);
+  // +4 per segment: runs are clamped at segment ends, so a few samples may repeat (also when S == N)
+  const long long delta = (long long)(5.0 * sqrt((double)S * pq * (1.0 - pq)) + 8.0) + 4ll * n_seg;
   const long long r_lo = rs - delta, r_hi = rs + delta;
   const int sgrid = (int)((S + 255) / 256 < (long long)sm_count() * 4 ? (S + 255) / 256 : (long long)sm_count() * 4);
   k_sample_coarse<KIND><<<sgrid, 256, 0, st>>>(d_segs, n_seg, N, S, d_skeys, d_hist);
@@ -509,7 +539,9 @@ static int run_topk(const Seg* d_segs, int n_seg, long long tiles, long long N, 
   const int grid = sweep_grid(tiles);
   if (write) k_sweep<KIND, true><<<grid, kSweepThreads, 0, st>>>(d_segs, n_seg, tiles, d_st, d_cand, cap, d_hist + kDigitBins, r_lo, r_hi, S);
   else       k_sweep<KIND, false><<<grid, kSweepThreads, 0, st>>>(d_segs, n_seg, tiles, d_st, d_cand, cap, d_hist + kDigitBins, r_lo, r_hi, S);
-  k_resolve<<<1, 1024, 0, st>>>(d_segs, n_seg, d_st, d_cand, cap, thr_out, write ? 1 : 0);
+  k_cand_hist<<<64, 256, 0, st>>>(d_st, d_cand, cap, d_hist + 3 * kDigitBins);
+  k_resolve<<<1, 1024, 0, st>>>(d_st, d_cand, cap, d_hist + 3 * kDigitBins, thr_out);
+  if (write) k_cand_patch<<<64, 256, 0, st>>>(d_segs, n_seg, d_st, d_cand, cap);
   TP_LAUNCH_CHECK();
   TP_CUDA_CHECK(cudaMemcpyAsync(&h, d_st, sizeof(h), cudaMemcpyDeviceToHost, st));
   TP_CUDA_CHECK(cudaStreamSynchronize(st));
@@ -550,7 +582,7 @@ size_t tp_topk_workspace_bytes(int n_seg, int64_t total_numel) {
   size_t b = 0;
   b += align_up(sizeof(Seg) * (size_t)(n_seg > 0 ? n_seg : 1), 256);
   b += align_up(sizeof(SelState), 256);
-  b += align_up(sizeof(unsigned int) * 3 * kDigitBins, 256);
+  b += align_up(sizeof(unsigned int) * 4 * kDigitBins, 256);
   b += align_up(sizeof(unsigned int) * (size_t)(1u << kSampleBits), 256);
   b += align_up(sizeof(uint2) * (size_t)cand_cap(total_numel), 256);
   return b + 1024;
@@ -573,7 +605,7 @@ int tp_topk_threshold_mask(const void* const* w, const void* const* g, const voi
   int rc = upload_segs(ar, w, g, m, mask_out, nullptr, numel, n_seg, &d_segs, &tiles, &total, st);
   if (rc) return rc;
   SelState* d_st = (SelState*)ar.take(sizeof(SelState));
-  unsigned int* d_hist = (unsigned int*)ar.take(sizeof(unsigned int) * 3 * kDigitBins);
+  unsigned int* d_hist = (unsigned int*)ar.take(sizeof(unsigned int) * 4 * kDigitBins);
   unsigned int* d_skeys = (unsigned int*)ar.take(sizeof(unsigned int) * (size_t)(1u << kSampleBits));
   const unsigned int cap = cand_cap(N);
   uint2* d_cand = (uint2*)ar.take(sizeof(uint2) * (size_t)cap);

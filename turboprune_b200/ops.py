@@ -120,6 +120,39 @@ def topk_threshold_mask(ws, ms, k, gs=None, kind=_cabi.TP_SCORE_MAG, write_masks
     return outs, thr, {"path": int(info[0]), "candidates": int(info[1]), "n_lt": int(info[2]), "nan_thr": bool(info[3])}
 
 
+class TopKPlan:
+    """Pre-marshalled ``tp_topk_threshold_mask`` call (pointer tables, outputs, workspace built once): ``run(k)`` is
+    just the C-ABI call.  Used when the same tensors are pruned repeatedly (benchmarks, per-level IMP)."""
+
+    def __init__(self, ws, ms, gs=None, kind=_cabi.TP_SCORE_MAG):
+        self.lib = _cabi.load()
+        self.dev = ws[0].device
+        self.ws = [w.detach().contiguous() for w in ws]
+        self.ms = [m.detach().contiguous() for m in ms]
+        self.gs = None if gs is None else [g.detach().contiguous() for g in gs]
+        self.outs = [torch.empty_like(m) for m in self.ms]
+        self.thr = torch.empty((), dtype=torch.float32, device=self.dev)
+        self.n = len(self.ws)
+        self.total = sum(w.numel() for w in self.ws)
+        self.kind = int(kind)
+        self.wsb = torch.empty(self.lib.tp_topk_workspace_bytes(self.n, self.total), dtype=torch.uint8, device=self.dev)
+        self.args = (_cabi.ptr_array(self.ws), _cabi.ptr_array(self.gs), _cabi.ptr_array(self.ms), _cabi.ptr_array(self.outs),
+                     _cabi.i64_array([w.numel() for w in self.ws]))
+        self.info = (ctypes.c_int64 * 4)()
+
+    def run(self, k):
+        with torch.cuda.device(self.dev):
+            rc = self.lib.tp_topk_threshold_mask(*self.args, self.n, int(k), self.kind, c_void_p(self.thr.data_ptr()),
+                                                 c_void_p(self.wsb.data_ptr()), self.wsb.numel(), self.info,
+                                                 _cabi.stream_ptr(self.dev))
+        if rc == _cabi.TP_ERR_K_RANGE:
+            raise RuntimeError(f"kthvalue(): selected number k out of range for dimension 0 (k={k}, N={self.total})")
+        _cabi.check(rc, "tp_topk_threshold_mask")
+        _count(6)
+        return self.outs, self.thr, {"path": int(self.info[0]), "candidates": int(self.info[1]), "n_lt": int(self.info[2]),
+                                     "nan_thr": bool(self.info[3])}
+
+
 def apply_threshold(ws, ms, thr, gs=None, kind=_cabi.TP_SCORE_MAG):
     lib = _cabi.load()
     _require_cuda(*ws, *ms, thr)
