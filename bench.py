@@ -305,7 +305,7 @@ def main():
                 "launches_per_step": sum(v[2] for v in tot.values()) / KT,
                 "timing": f"CUDA events around each masked-GEMM C-ABI call over {KT} eager steps ({ms_eager / KT:.2f} ms/step eager); step rate from CUDA-graph replay" if use_graph else "CUDA events, eager",
                 "ms_per_step_in_kernel": gemm_ms / K,
-                "by_op_ms_per_step": {k: v[0] / K for k, v in tot.items()},
+                "by_op_ms_per_step": {k: v[0] / KT for k, v in tot.items()},
                 "share_of_step": gemm_ms / ms_total,
                 "flops_per_step": GFLOP_PER_IMG * 1e9 * B,
                 "frac_of_masked_gemm_roofline_img_s": (img_s / world) / ROOFLINE_IMG_S}

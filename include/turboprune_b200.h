@@ -117,8 +117,10 @@ size_t tp_conv_workspace_bytes(const tp_conv_desc* d, int op);   /* op: 0 fprop,
 /* y[n,p,q,cout] (bf16) = conv(x[n,h,w,cin] (bf16), wf (bf16, tp_stage_weights layout)) + bias */
 int tp_conv_fprop(const tp_conv_desc* d, const void* x, const void* wf, const void* bias_f32,
                   void* y, void* ws, size_t ws_bytes, void* stream);
-/* dx[n,h,w,cin] (bf16) = conv_dgrad(dy[n,p,q,cout] (bf16), wd (bf16, rotated layout)) */
-int tp_conv_dgrad(const tp_conv_desc* d, const void* dy, const void* wd,
+/* dx[n,h,w,cin] (bf16) = conv_dgrad(dy[n,p,q,cout] (bf16), wd (bf16, rotated layout)) [+ addend[n,h,w,cin]]
+ * addend (optional, bf16, same layout as dx): the gradient arriving over a skip connection, accumulated in the
+ * epilogue instead of by a separate elementwise add (autograd's grad accumulation at a ResNet block input). */
+int tp_conv_dgrad(const tp_conv_desc* d, const void* dy, const void* wd, const void* addend,
                   void* dx, void* ws, size_t ws_bytes, void* stream);
 /* dw[cout][cin_real][r][s] (fp32, OIHW) = mask * conv_wgrad(x, dy); db[cout] = sum dy (optional) */
 int tp_conv_wgrad(const tp_conv_desc* d, const void* x, const void* dy, const void* mask,
@@ -132,7 +134,8 @@ int tp_conv_wgrad(const tp_conv_desc* d, const void* x, const void* dy, const vo
  *             training != 0: batch statistics (biased var), running stats updated with `momentum`
  *             (unbiased var), *num_batches_tracked += 1, save_mean / save_invstd written (fp32 [C]);
  *             training == 0: running statistics.
- *   backward: g = relu ? dz * (z > 0) : dz;  dres = g (optional);  dweight = sum g*xhat; dbias = sum g;
+ *   backward: g = relu ? dz * gate : dz  (relu == 1: gate = z > 0 from the saved output; relu == 2: gate recomputed
+ *             from y, weight, bias — z is not read);  dres = g (optional);  dweight = sum g*xhat; dbias = sum g;
  *             dy = weight*invstd * (g - mean(g) - xhat * mean(g*xhat))
  * Reductions use per-CTA partials folded in fixed order (deterministic).
  */
@@ -141,7 +144,7 @@ int tp_bn_forward(const void* y, const void* residual, void* z, int64_t m, int c
                   const void* weight, const void* bias, void* running_mean, void* running_var,
                   void* num_batches_tracked, float momentum, float eps, int training, int relu,
                   void* save_mean, void* save_invstd, void* ws, size_t ws_bytes, void* stream);
-int tp_bn_backward(const void* dz, const void* z, const void* y, int64_t m, int c, const void* weight,
+int tp_bn_backward(const void* dz, const void* z, const void* y, int64_t m, int c, const void* weight, const void* bias,
                    const void* save_mean, const void* save_invstd, int relu, void* dy, void* dres,
                    void* dweight, void* dbias, void* ws, size_t ws_bytes, void* stream);
 

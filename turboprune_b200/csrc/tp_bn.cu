@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kBnThreads) k_bn_stats(const __nv_bfloat16* __
 
 // Fold the per-CTA partials of one channel in a fixed order: 8 part-lanes each sum a strided subset
 // (coalesced across the 32 channel-lanes), then the 8 lane sums are added in lane order.
-constexpr int kFinC = 32, kFinP = 8;
+constexpr int kFinC = 32, kFinP = 32;
 __device__ __forceinline__ void fold_partials(const float* __restrict__ partial, int nparts, int C, int c,
                                               float& s1, float& s2, float (*sm)[kFinP][kFinC]) {
   const int tx = threadIdx.x, ty = threadIdx.y;
@@ -137,7 +137,7 @@ __device__ __forceinline__ void fold_partials(const float* __restrict__ partial,
 
 // one thread per channel: fold the partials in fixed order; emit mean / invstd / scale / shift and
 // update the running statistics (torch semantics: momentum, unbiased running_var).
-__global__ void k_bn_finalize_stats(const float* __restrict__ partial, int nparts, const __nv_bfloat16* __restrict__ y,
+__global__ void __launch_bounds__(kFinC * kFinP) k_bn_finalize_stats(const float* __restrict__ partial, int nparts, const __nv_bfloat16* __restrict__ y,
                                     long long M, int C, const float* __restrict__ weight, const float* __restrict__ bias,
                                     float* running_mean, float* running_var, long long* nbt, float momentum, float eps,
                                     float* __restrict__ save_mean, float* __restrict__ save_invstd,
@@ -228,21 +228,30 @@ __global__ void __launch_bounds__(kBnThreads) k_bn_apply(const __nv_bfloat16* __
 
 // ---- backward ----------------------------------------------------------------------------------------
 // partial[b][0][c] = sum g, partial[b][1][c] = sum g * xhat, with g = dz * (z > 0) when RELU
-template <bool RELU>
+// RELU: 0 = no activation, 1 = gate from the saved output (z > 0), 2 = gate recomputed from y (same fp32
+// expression as the forward apply: no need to read z at all — one activation pass less)
+template <int RELU>
 __global__ void __launch_bounds__(kBnThreads) k_bn_bwd_reduce(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ z,
                                                               const __nv_bfloat16* __restrict__ y, long long M, int C,
                                                               const float* __restrict__ mean, const float* __restrict__ invstd,
+                                                              const float* __restrict__ weight, const float* __restrict__ bias,
                                                               float* __restrict__ partial) {
   __shared__ float s_acc[kBnThreads][17];
   const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
   const int cvec = blockIdx.y * TX + tx;
   const bool act = cvec * 8 < C;
-  float a1[8], a2[8], mu[8], is[8];
+  float a1[8], a2[8], mu[8], is[8], sc[8], sf[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { a1[i] = 0.f; a2[i] = 0.f; mu[i] = 0.f; is[i] = 0.f; }
+  for (int i = 0; i < 8; ++i) { a1[i] = 0.f; a2[i] = 0.f; mu[i] = 0.f; is[i] = 0.f; sc[i] = 0.f; sf[i] = 0.f; }
   if (act) {
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { mu[i] = mean[cvec * 8 + i]; is[i] = invstd[cvec * 8 + i]; }
+    for (int i = 0; i < 8; ++i) {
+      mu[i] = mean[cvec * 8 + i]; is[i] = invstd[cvec * 8 + i];
+      if (RELU == 2) {
+        const float w = weight ? weight[cvec * 8 + i] : 1.f, b = bias ? bias[cvec * 8 + i] : 0.f;
+        sc[i] = w * is[i]; sf[i] = fmaf(-mu[i], w * is[i], b);      // identical to k_bn_finalize_stats
+      }
+    }
     const long long stride = (long long)gridDim.x * TY;
     long long p = (long long)blockIdx.x * TY + ty;
     for (; p + 1 * stride < M; p += 2 * stride) {
@@ -251,15 +260,16 @@ __global__ void __launch_bounds__(kBnThreads) k_bn_bwd_reduce(const __nv_bfloat1
       for (int u = 0; u < 2; ++u) {
         const size_t off = (size_t)(p + u * stride) * C + (size_t)cvec * 8;
         vd[u] = ldg16(dz + off); vy[u] = ldg16(y + off);
-        if (RELU) vz[u] = ldg16(z + off);
+        if (RELU == 1) vz[u] = ldg16(z + off);
       }
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         float d[8], yy[8], zz[8]; unpack8(vd[u], d); unpack8(vy[u], yy);
-        if (RELU) unpack8(vz[u], zz);
+        if (RELU == 1) unpack8(vz[u], zz);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const float g = (RELU && !(zz[i] > 0.f)) ? 0.f : d[i];
+          const bool open = RELU == 0 ? true : (RELU == 1 ? (zz[i] > 0.f) : (fmaf(yy[i], sc[i], sf[i]) > 0.f));
+          const float g = open ? d[i] : 0.f;
           a1[i] += g; a2[i] = fmaf(g, (yy[i] - mu[i]) * is[i], a2[i]);
         }
       }
@@ -267,10 +277,11 @@ __global__ void __launch_bounds__(kBnThreads) k_bn_bwd_reduce(const __nv_bfloat1
     for (; p < M; p += stride) {
       const size_t off = (size_t)p * C + (size_t)cvec * 8;
       float d[8], yy[8], zz[8]; unpack8(ldg16(dz + off), d); unpack8(ldg16(y + off), yy);
-      if (RELU) unpack8(ldg16(z + off), zz);
+      if (RELU == 1) unpack8(ldg16(z + off), zz);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float g = (RELU && !(zz[i] > 0.f)) ? 0.f : d[i];
+        const bool open = RELU == 0 ? true : (RELU == 1 ? (zz[i] > 0.f) : (fmaf(yy[i], sc[i], sf[i]) > 0.f));
+        const float g = open ? d[i] : 0.f;
         a1[i] += g; a2[i] = fmaf(g, (yy[i] - mu[i]) * is[i], a2[i]);
       }
     }
@@ -295,8 +306,9 @@ __global__ void __launch_bounds__(kBnThreads) k_bn_bwd_reduce(const __nv_bfloat1
 // dweight = sum g*xhat, dbias = sum g; coefficients for the apply pass:
 //   dy = k0 * g + k1 * y + k2   with  k0 = w*invstd,  k1 = -k0*invstd*mean(g*xhat),
 //                                     k2 = -k0*mean(g) - k1*mu
-__global__ void k_bn_finalize_bwd(const float* __restrict__ partial, int nparts, long long M, int C,
-                                  const float* __restrict__ weight, const float* __restrict__ mean, const float* __restrict__ invstd,
+__global__ void __launch_bounds__(kFinC * kFinP) k_bn_finalize_bwd(const float* __restrict__ partial, int nparts, long long M, int C,
+                                  const float* __restrict__ weight, const float* __restrict__ bias,
+                                  const float* __restrict__ mean, const float* __restrict__ invstd,
                                   float* __restrict__ dweight, float* __restrict__ dbias, float* __restrict__ coef) {
   __shared__ float sm[2][kFinP][kFinC];
   const int c = blockIdx.x * kFinC + threadIdx.x;
@@ -311,9 +323,11 @@ __global__ void k_bn_finalize_bwd(const float* __restrict__ partial, int nparts,
   const float k1 = -k0 * invstd[c] * (s2 * inv_m);
   const float k2 = -k0 * (s1 * inv_m) - k1 * mean[c];
   coef[c] = k0; coef[C + c] = k1; coef[2 * C + c] = k2;
+  coef[3 * C + c] = k0;                                        // forward scale  (w * invstd)
+  coef[4 * C + c] = fmaf(-mean[c], k0, bias ? bias[c] : 0.f);  // forward shift
 }
 
-template <bool RELU, bool RES>
+template <int RELU, bool RES>
 __global__ void __launch_bounds__(kBnThreads) k_bn_bwd_apply(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ z,
                                                              const __nv_bfloat16* __restrict__ y, long long M, int C,
                                                              const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy,
@@ -321,9 +335,12 @@ __global__ void __launch_bounds__(kBnThreads) k_bn_bwd_apply(const __nv_bfloat16
   const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
   const int cvec = blockIdx.y * TX + tx;
   if (cvec * 8 >= C) return;
-  float k0[8], k1[8], k2[8];
+  float k0[8], k1[8], k2[8], sf[8];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) { k0[i] = coef[cvec * 8 + i]; k1[i] = coef[C + cvec * 8 + i]; k2[i] = coef[2 * C + cvec * 8 + i]; }
+  for (int i = 0; i < 8; ++i) {
+    k0[i] = coef[cvec * 8 + i]; k1[i] = coef[C + cvec * 8 + i]; k2[i] = coef[2 * C + cvec * 8 + i];
+    sf[i] = RELU == 2 ? coef[4 * C + cvec * 8 + i] : 0.f;         // forward scale == k0
+  }
   const long long stride = (long long)gridDim.x * TY;
   long long p = (long long)blockIdx.x * TY + ty;
   for (; p + 1 * stride < M; p += 2 * stride) {
@@ -332,16 +349,17 @@ __global__ void __launch_bounds__(kBnThreads) k_bn_bwd_apply(const __nv_bfloat16
     for (int u = 0; u < 2; ++u) {
       const size_t off = (size_t)(p + u * stride) * C + (size_t)cvec * 8;
       vd[u] = ldg16(dz + off); vy[u] = ldg16(y + off);
-      if (RELU) vz[u] = ldg16(z + off);
+      if (RELU == 1) vz[u] = ldg16(z + off);
     }
 #pragma unroll
     for (int u = 0; u < 2; ++u) {
       const size_t off = (size_t)(p + u * stride) * C + (size_t)cvec * 8;
       float d[8], yy[8], zz[8], o[8]; unpack8(vd[u], d); unpack8(vy[u], yy);
-      if (RELU) unpack8(vz[u], zz);
+      if (RELU == 1) unpack8(vz[u], zz);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const float g = (RELU && !(zz[i] > 0.f)) ? 0.f : d[i];
+        const bool open = RELU == 0 ? true : (RELU == 1 ? (zz[i] > 0.f) : (fmaf(yy[i], k0[i], sf[i]) > 0.f));
+        const float g = open ? d[i] : 0.f;
         d[i] = g;
         o[i] = fmaf(k0[i], g, fmaf(k1[i], yy[i], k2[i]));
       }
@@ -352,10 +370,11 @@ __global__ void __launch_bounds__(kBnThreads) k_bn_bwd_apply(const __nv_bfloat16
   for (; p < M; p += stride) {
     const size_t off = (size_t)p * C + (size_t)cvec * 8;
     float d[8], yy[8], zz[8], o[8]; unpack8(ldg16(dz + off), d); unpack8(ldg16(y + off), yy);
-    if (RELU) unpack8(ldg16(z + off), zz);
+    if (RELU == 1) unpack8(ldg16(z + off), zz);
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float g = (RELU && !(zz[i] > 0.f)) ? 0.f : d[i];
+      const bool open = RELU == 0 ? true : (RELU == 1 ? (zz[i] > 0.f) : (fmaf(yy[i], k0[i], sf[i]) > 0.f));
+      const float g = open ? d[i] : 0.f;
       d[i] = g;
       o[i] = fmaf(k0[i], g, fmaf(k1[i], yy[i], k2[i]));
     }
@@ -411,11 +430,11 @@ int tp_bn_forward(const void* y, const void* residual, void* z, int64_t M, int C
   return TP_OK;
 }
 
-int tp_bn_backward(const void* dz, const void* z, const void* y, int64_t M, int C, const void* weight,
+int tp_bn_backward(const void* dz, const void* z, const void* y, int64_t M, int C, const void* weight, const void* bias,
                    const void* save_mean, const void* save_invstd, int relu, void* dy, void* dres,
                    void* dweight, void* dbias, void* ws, size_t ws_bytes, void* stream) {
   if (!dz || !y || !dy || !save_mean || !save_invstd || M <= 0 || C <= 0 || C % 8 != 0 || !ws) return TP_ERR_INVALID;
-  if (relu && !z) return TP_ERR_INVALID;
+  if (relu < 0 || relu > 2 || (relu == 1 && !z)) return TP_ERR_INVALID;
   if (ws_bytes < tp_bn_workspace_bytes(M, C)) return TP_ERR_WORKSPACE;
   int rc = bind_device_of(y); if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
@@ -424,15 +443,19 @@ int tp_bn_backward(const void* dz, const void* z, const void* y, int64_t M, int 
   float* coef = partial + (size_t)g.grid_x * 2 * C;
   dim3 block(g.tx, g.ty), grid(g.grid_x, g.ctiles);
   const __nv_bfloat16 *d = (const __nv_bfloat16*)dz, *zz = (const __nv_bfloat16*)z, *yy = (const __nv_bfloat16*)y;
-  if (relu) k_bn_bwd_reduce<true><<<grid, block, 0, st>>>(d, zz, yy, M, C, (const float*)save_mean, (const float*)save_invstd, partial);
-  else k_bn_bwd_reduce<false><<<grid, block, 0, st>>>(d, zz, yy, M, C, (const float*)save_mean, (const float*)save_invstd, partial);
-  k_bn_finalize_bwd<<<(C + kFinC - 1) / kFinC, dim3(kFinC, kFinP), 0, st>>>(partial, g.grid_x, M, C, (const float*)weight, (const float*)save_mean,
-                                                      (const float*)save_invstd, (float*)dweight, (float*)dbias, coef);
+  const float *mu = (const float*)save_mean, *is = (const float*)save_invstd, *wp = (const float*)weight, *bp = (const float*)bias;
+  if (relu == 1) k_bn_bwd_reduce<1><<<grid, block, 0, st>>>(d, zz, yy, M, C, mu, is, wp, bp, partial);
+  else if (relu == 2) k_bn_bwd_reduce<2><<<grid, block, 0, st>>>(d, zz, yy, M, C, mu, is, wp, bp, partial);
+  else k_bn_bwd_reduce<0><<<grid, block, 0, st>>>(d, zz, yy, M, C, mu, is, wp, bp, partial);
+  k_bn_finalize_bwd<<<(C + kFinC - 1) / kFinC, dim3(kFinC, kFinP), 0, st>>>(partial, g.grid_x, M, C, wp, bp, mu, is,
+                                                                          (float*)dweight, (float*)dbias, coef);
   __nv_bfloat16* o = (__nv_bfloat16*)dy; __nv_bfloat16* r = (__nv_bfloat16*)dres;
-  if (relu && r) k_bn_bwd_apply<true, true><<<grid, block, 0, st>>>(d, zz, yy, M, C, coef, o, r);
-  else if (relu) k_bn_bwd_apply<true, false><<<grid, block, 0, st>>>(d, zz, yy, M, C, coef, o, r);
-  else if (r) k_bn_bwd_apply<false, true><<<grid, block, 0, st>>>(d, zz, yy, M, C, coef, o, r);
-  else k_bn_bwd_apply<false, false><<<grid, block, 0, st>>>(d, zz, yy, M, C, coef, o, r);
+  if (relu == 1 && r) k_bn_bwd_apply<1, true><<<grid, block, 0, st>>>(d, zz, yy, M, C, coef, o, r);
+  else if (relu == 1) k_bn_bwd_apply<1, false><<<grid, block, 0, st>>>(d, zz, yy, M, C, coef, o, r);
+  else if (relu == 2 && r) k_bn_bwd_apply<2, true><<<grid, block, 0, st>>>(d, zz, yy, M, C, coef, o, r);
+  else if (relu == 2) k_bn_bwd_apply<2, false><<<grid, block, 0, st>>>(d, zz, yy, M, C, coef, o, r);
+  else if (r) k_bn_bwd_apply<0, true><<<grid, block, 0, st>>>(d, zz, yy, M, C, coef, o, r);
+  else k_bn_bwd_apply<0, false><<<grid, block, 0, st>>>(d, zz, yy, M, C, coef, o, r);
   TP_LAUNCH_CHECK();
   return TP_OK;
 }

@@ -46,6 +46,7 @@ struct FwdParams {
   int tma_store;            // 1: epilogue stages 32x64 sub-tiles in smem and stores them with TMA (tmC)
   __nv_bfloat16* out;
   const float* bias;
+  const __nv_bfloat16* addend;   // optional: out = acc (+ bias) + addend[pixel][channel] (same layout as out)
   TapEntry taps[kMaxTaps];
 };
 
@@ -205,6 +206,19 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int j = 0; j < 32; ++j) if (n0 + 32 * h + j < p.N) f[j] += p.bias[n0 + 32 * h + j];
             }
+            if (p.addend && row_ok) {
+              // fused residual-gradient accumulation (dX = dgrad(dY) + d_skip): 64 contiguous bytes per thread
+              const __nv_bfloat16* ar = p.addend + opix * p.ldc + n0 + 32 * h;
+#pragma unroll
+              for (int j = 0; j < 32; j += 8) {
+                if (n0 + 32 * h + j + 8 <= p.N) {
+                  const uint4 a = *reinterpret_cast<const uint4*>(ar + j);
+                  const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+                  for (int q = 0; q < 4; ++q) { const float2 t2 = __bfloat1622float2(ah[q]); f[j + 2 * q] += t2.x; f[j + 2 * q + 1] += t2.y; }
+                }
+              }
+            }
 #pragma unroll
             for (int j = 0; j < 32; j += 8) {
               __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]);
@@ -236,6 +250,10 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (p.bias) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) if (n0 + j < p.N) f[j] += p.bias[n0 + j];
+          }
+          if (p.addend) {
+            const __nv_bfloat16* ar = p.addend + opix * p.ldc + n0;
+            for (int j = 0; j < 32; ++j) if (n0 + j < p.N) f[j] += __bfloat162float(ar[j]);
           }
           __nv_bfloat16* dst = orow + n0;
           if (n0 + 32 <= p.N && (((uintptr_t)dst) & 15) == 0) {
@@ -652,7 +670,7 @@ int tp_conv_fprop(const tp_conv_desc* d, const void* x, const void* wf, const vo
   return run_fwd(ta, tb, p, st);
 }
 
-int tp_conv_dgrad(const tp_conv_desc* d, const void* dy, const void* wd,
+int tp_conv_dgrad(const tp_conv_desc* d, const void* dy, const void* wd, const void* addend,
                   void* dx, void* ws, size_t ws_bytes, void* stream) {
   (void)ws; (void)ws_bytes;
   if (!d || !dy || !wd || !dx) return TP_ERR_INVALID;
@@ -673,7 +691,7 @@ int tp_conv_dgrad(const tp_conv_desc* d, const void* dy, const void* wd,
     p.cchunks = (cop + 63) / 64; p.ntaps = R * S;
     p.out_img_pix = (long long)d->h * d->w; p.out_row_pix = d->w;
     p.osh = 1; p.oah = 0; p.osw = 1; p.oaw = 0;
-    p.ldc = d->cin; p.out = (__nv_bfloat16*)dx; p.bias = nullptr;
+    p.ldc = d->cin; p.out = (__nv_bfloat16*)dx; p.bias = nullptr; p.addend = (const __nv_bfloat16*)addend;
     for (int r = 0; r < R; ++r) for (int s = 0; s < S; ++s) {
       TapEntry& t = p.taps[r * S + s];
       t.off_w = (uint16_t)s; t.off_h = (uint16_t)r; t.kofs = (r * S + s) * cop;
@@ -695,7 +713,9 @@ int tp_conv_dgrad(const tp_conv_desc* d, const void* dy, const void* wd,
   // strided conv: decompose dX into stride_h x stride_w parity classes; each class is a
   // stride-1 gather over dY with its own subset of taps, scattered to every stride-th pixel.
   const int sh = d->stride_h, sw = d->stride_w;
-  TP_CUDA_CHECK(cudaMemsetAsync(dx, 0, (size_t)d->n * d->h * d->w * d->cin * 2, st));
+  // pixels no tap reaches keep this initial value: zero, or the fused addend
+  if (addend) TP_CUDA_CHECK(cudaMemcpyAsync(dx, addend, (size_t)d->n * d->h * d->w * d->cin * 2, cudaMemcpyDeviceToDevice, st));
+  else TP_CUDA_CHECK(cudaMemsetAsync(dx, 0, (size_t)d->n * d->h * d->w * d->cin * 2, st));
   for (int a = 0; a < sh; ++a) for (int b = 0; b < sw; ++b) {
     const int Hc = (d->h - a + sh - 1) / sh, Wc = (d->w - b + sw - 1) / sw;   // pixels of this class
     if (Hc <= 0 || Wc <= 0) continue;
@@ -712,7 +732,7 @@ int tp_conv_dgrad(const tp_conv_desc* d, const void* dy, const void* wd,
     p.base_w = dw_min; p.base_h = dh_min; p.step_w = 1; p.step_h = 1;
     p.out_img_pix = (long long)d->h * d->w; p.out_row_pix = d->w;
     p.osh = sh; p.oah = a; p.osw = sw; p.oaw = b;
-    p.ldc = d->cin; p.out = (__nv_bfloat16*)dx; p.bias = nullptr;
+    p.ldc = d->cin; p.out = (__nv_bfloat16*)dx; p.bias = nullptr; p.addend = (const __nv_bfloat16*)addend;
     for (int r = 0; r < R; ++r) {
       if ((a + d->pad_h - r) % sh != 0) continue;
       for (int s = 0; s < S; ++s) {

@@ -39,8 +39,9 @@ class _BNFn(torch.autograd.Function):
         _cabi.check(rc, "tp_bn_forward")
         ops._count(3 if training else 2)
         if training:
-            ctx.save_for_backward(xn, z if relu else None, weight, save_mean, save_invstd)
-            ctx.relu = relu
+            # ReLU gate: recomputed from y in the backward unless a residual was added (then z itself is needed)
+            ctx.relu = 0 if not relu else (1 if residual is not None else 2)
+            ctx.save_for_backward(xn, z if ctx.relu == 1 else None, weight, bias, save_mean, save_invstd)
             ctx.has_res = residual is not None
             ctx.res_dtype = residual.dtype if residual is not None else None
             ctx.x_dtype = x.dtype
@@ -49,7 +50,7 @@ class _BNFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dz):
         lib = _cabi.load()
-        xn, z, weight, save_mean, save_invstd = ctx.saved_tensors
+        xn, z, weight, bias, save_mean, save_invstd = ctx.saved_tensors
         n, h, w, c = xn.shape
         m = n * h * w
         dev = xn.device
@@ -60,7 +61,7 @@ class _BNFn(torch.autograd.Function):
         dbias = torch.empty(c, dtype=torch.float32, device=dev)
         wsb = ops._workspace(lib.tp_bn_workspace_bytes(m, c), dev, "bn")
         with torch.cuda.device(dev):
-            rc = lib.tp_bn_backward(_ptr(dzn), _ptr(z), _ptr(xn), m, c, _ptr(weight), _ptr(save_mean), _ptr(save_invstd),
+            rc = lib.tp_bn_backward(_ptr(dzn), _ptr(z), _ptr(xn), m, c, _ptr(weight), _ptr(bias), _ptr(save_mean), _ptr(save_invstd),
                                     int(ctx.relu), _ptr(dy), _ptr(dres), _ptr(dweight), _ptr(dbias), _ptr(wsb), wsb.numel(),
                                     _cabi.stream_ptr(dev))
         _cabi.check(rc, "tp_bn_backward")
@@ -137,22 +138,30 @@ class MaxPool2dB200(nn.MaxPool2d):
 
 
 # ---- fused forwards for the torchvision graphs the reference instantiates ------------------------------
+def _conv_with_skip(conv, x):
+    """(conv(x), x') where x' aliases x and routes its gradient into conv's dgrad epilogue (no separate add kernel)."""
+    from .utils.mask_layers import ConvMask
+    if isinstance(conv, ConvMask) and x.requires_grad and x.shape[1] % 64 == 0:
+        return conv(x, want_skip=True)
+    return conv(x), x
+
+
 def _basic_block_forward(self, x):
-    identity = x
-    out = self.bn1(self.conv1(x), relu=True)
+    out, identity = _conv_with_skip(self.conv1, x)
+    out = self.bn1(out, relu=True)
     out = self.conv2(out)
     if self.downsample is not None:
-        identity = self.downsample(x)
+        identity = self.downsample(identity)
     return self.bn2(out, residual=identity, relu=True)
 
 
 def _bottleneck_forward(self, x):
-    identity = x
-    out = self.bn1(self.conv1(x), relu=True)
+    out, identity = _conv_with_skip(self.conv1, x)
+    out = self.bn1(out, relu=True)
     out = self.bn2(self.conv2(out), relu=True)
     out = self.conv3(out)
     if self.downsample is not None:
-        identity = self.downsample(x)
+        identity = self.downsample(identity)
     return self.bn3(out, residual=identity, relu=True)
 
 

@@ -284,12 +284,14 @@ def conv_fprop(desc, x_nhwc, wf, bias=None):
     return y
 
 
-def conv_dgrad(desc, dy_nhwc, wd):
+def conv_dgrad(desc, dy_nhwc, wd, addend=None):
+    """dx = dgrad(dy) [+ addend]: ``addend`` (NHWC bf16, dx's shape) is accumulated in the kernel epilogue."""
     lib = _cabi.load()
     dev = dy_nhwc.device
     dx = torch.empty(desc.n, desc.h, desc.w, desc.cin, dtype=torch.bfloat16, device=dev)
     with torch.cuda.device(dev), _Timed("dgrad", desc):
         rc = lib.tp_conv_dgrad(ctypes.byref(desc), c_void_p(dy_nhwc.data_ptr()), c_void_p(wd.data_ptr()),
+                               c_void_p(addend.data_ptr()) if addend is not None else None,
                                c_void_p(dx.data_ptr()), None, 0, _cabi.stream_ptr(dev))
     _cabi.check(rc, "tp_conv_dgrad")
     _count(1 if desc.stride_h == 1 and desc.stride_w == 1 else desc.stride_h * desc.stride_w)
@@ -323,8 +325,10 @@ class MaskedConv2dFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, weight, mask, bias, stride, padding):
+    def forward(ctx, x, weight, mask, bias, stride, padding, want_skip=False):
         _require_cuda(x, weight, mask)
+        ctx.set_materialize_grads(False)
+        ctx.want_skip = want_skip
         cout, cin, r, s = weight.shape
         n, _, h, w = x.shape
         need_dx = ctx.needs_input_grad[0]
@@ -358,11 +362,18 @@ class MaskedConv2dFn(torch.autograd.Function):
         ctx.has_bias = bias is not None
         ctx.cout_p = cout_p
         ctx.x_dtype = x.dtype
+        if want_skip:
+            # second output = the input itself: whatever gradient reaches it (the identity path of a residual
+            # block, or a downsample branch) comes back to backward() as ``dskip`` and is accumulated inside
+            # the dgrad epilogue instead of by autograd's separate elementwise add
+            return y.permute(0, 3, 1, 2), x
         return y.permute(0, 3, 1, 2)
 
     @staticmethod
-    def backward(ctx, dy):
+    def backward(ctx, dy, dskip=None):
         desc = ctx.desc
+        if dy is None:          # only the skip output was used downstream
+            return dskip, None, None, None, None, None, None
         cout = desc.cout
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         need_db = ctx.has_bias and ctx.needs_input_grad[3]
@@ -385,7 +396,10 @@ class MaskedConv2dFn(torch.autograd.Function):
                 ddesc = _cabi.ConvDesc(desc.n, desc.h, desc.w, desc.cin, ctx.cout_p, desc.r, desc.s, desc.stride_h,
                                        desc.stride_w, desc.pad_h, desc.pad_w, desc.p, desc.q)
             if need_dx:
-                dx = conv_dgrad(ddesc, dyn, wd).permute(0, 3, 1, 2)
+                addend = None
+                if dskip is not None:
+                    addend = to_nhwc_bf16(dskip, desc.cin)
+                dx = conv_dgrad(ddesc, dyn, wd, addend).permute(0, 3, 1, 2)
                 if dx.dtype != ctx.x_dtype:
                     dx = dx.to(ctx.x_dtype)
             if need_dw:
@@ -399,11 +413,13 @@ class MaskedConv2dFn(torch.autograd.Function):
                     dw, db = conv_wgrad(desc, xn, dyn, m32, desc.cin, need_db)
         if need_db and db is None:
             db = dy.float().sum(dim=(0, 2, 3))
-        return dx, dw, None, db, None, None
+        if dskip is not None and dx is None and need_dx is False:
+            dx = None
+        return dx, dw, None, db, None, None, None
 
 
-def masked_conv2d(x, weight, mask, bias=None, stride=(1, 1), padding=(0, 0)):
-    return MaskedConv2dFn.apply(x, weight, mask, bias, tuple(stride), tuple(padding))
+def masked_conv2d(x, weight, mask, bias=None, stride=(1, 1), padding=(0, 0), want_skip=False):
+    return MaskedConv2dFn.apply(x, weight, mask, bias, tuple(stride), tuple(padding), want_skip)
 
 
 def masked_linear(x, weight2d, mask2d, bias=None):
@@ -411,5 +427,5 @@ def masked_linear(x, weight2d, mask2d, bias=None):
     shp = x.shape
     x2 = x.reshape(-1, shp[-1])
     y = MaskedConv2dFn.apply(x2.view(x2.shape[0], x2.shape[1], 1, 1), weight2d.view(*weight2d.shape, 1, 1),
-                             mask2d.view(*mask2d.shape, 1, 1), bias, (1, 1), (0, 0))
+                             mask2d.view(*mask2d.shape, 1, 1), bias, (1, 1), (0, 0), False)
     return y.reshape(*shp[:-1], weight2d.shape[0])

@@ -39,11 +39,13 @@ class ConvMask(_MaskMixin, nn.Conv2d):
         super().__init__(**kwargs)
         self._init_mask()
 
-    def forward(self, x):
+    def forward(self, x, want_skip=False):
+        """``want_skip=True`` additionally returns ``x`` as a second output whose gradient is accumulated inside
+        this layer's dgrad kernel (used by the fused ResNet block forwards for the identity / downsample paths)."""
         self._check_plain()
         if isinstance(self.padding, str):
             raise NotImplementedError("string padding modes")
-        return ops.masked_conv2d(x, self.weight, self.mask, self.bias, _pair(self.stride), _pair(self.padding))
+        return ops.masked_conv2d(x, self.weight, self.mask, self.bias, _pair(self.stride), _pair(self.padding), want_skip)
 
 
 class LinearMask(_MaskMixin, nn.Linear):
