@@ -67,6 +67,17 @@ __device__ __forceinline__ void decompose_pixel(int m, int P, int Q, int& n, int
   q = m % Q; int t = m / Q; p = t % P; n = t / P;
 }
 
+// 32 x 64 addend sub-tile -> registers (linear output order is a precondition, so addend row = output row)
+__device__ __forceinline__ void load_addend(uint4 (&a)[8], const FwdParams& p, int m_t, int quarter, int r_in, int c16, int n0) {
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long grow = (long long)m_t * kBlockM + quarter * 32 + i * 4 + r_in;
+    a[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (grow < p.M && n0 + c16 * 8 + 8 <= p.N)
+      a[i] = *reinterpret_cast<const uint4*>(p.addend + grow * p.ldc + n0 + c16 * 8);
+  }
+}
+
 // ============================================================================================
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -187,6 +198,7 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         // TMEM -> registers -> 128B-swizzled smem sub-tile (32 rows x 64 cols) -> TMA store: every
         // output line leaves the SM as full 128-byte rows instead of 32 scattered 16-byte pieces.
         uint8_t* my_stg = stg_base + (warp - 2) * 2 * kStgBytes;
+        uint4 a_pref[8];
 #pragma unroll 1
         for (int c = 0; c < BLOCK_N; c += 64) {
           const int n0 = n_t * BLOCK_N + c;
@@ -194,6 +206,19 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           uint8_t* buf = my_stg + stg_sel * kStgBytes;
           if (lane == 0) bulk_wait_read<1>();            // the store that last used this buffer has read it
           __syncwarp();
+          if (p.addend) {
+            // addend sub-tile of THIS chunk was prefetched into registers one chunk earlier (coalesced: 8 lanes
+            // cover one 128-byte row, 4 rows per instruction); stage it, then prefetch the next chunk's
+            const int r_in = lane >> 3, c16 = lane & 7;
+            if (c == 0) load_addend(a_pref, p, m_t, quarter, r_in, c16, n0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int row_l = i * 4 + r_in;
+              *(uint4*)(buf + row_l * 128 + ((c16 ^ (row_l & 7)) << 4)) = a_pref[i];
+            }
+            if (c + 64 < BLOCK_N && n0 + 64 < p.N) load_addend(a_pref, p, m_t, quarter, r_in, c16, n0 + 64);
+            __syncwarp();
+          }
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             uint32_t v[32];
@@ -206,17 +231,16 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int j = 0; j < 32; ++j) if (n0 + 32 * h + j < p.N) f[j] += p.bias[n0 + 32 * h + j];
             }
-            if (p.addend && row_ok) {
-              // fused residual-gradient accumulation (dX = dgrad(dY) + d_skip): 64 contiguous bytes per thread
-              const __nv_bfloat16* ar = p.addend + opix * p.ldc + n0 + 32 * h;
+            if (p.addend) {
+              // fused skip-gradient accumulation: the addend sub-tile was staged (coalesced) in `buf`; each
+              // thread reads its own row back before overwriting it with the result
 #pragma unroll
               for (int j = 0; j < 32; j += 8) {
-                if (n0 + 32 * h + j + 8 <= p.N) {
-                  const uint4 a = *reinterpret_cast<const uint4*>(ar + j);
-                  const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
+                const int chunk16 = h * 4 + (j >> 3);
+                const uint4 a = *(const uint4*)(buf + lane * 128 + ((chunk16 ^ (lane & 7)) << 4));
+                const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
 #pragma unroll
-                  for (int q = 0; q < 4; ++q) { const float2 t2 = __bfloat1622float2(ah[q]); f[j + 2 * q] += t2.x; f[j + 2 * q + 1] += t2.y; }
-                }
+                for (int q = 0; q < 4; ++q) { const float2 t2 = __bfloat1622float2(ah[q]); f[j + 2 * q] += t2.x; f[j + 2 * q + 1] += t2.y; }
               }
             }
 #pragma unroll
