@@ -43,6 +43,7 @@ struct FwdParams {
   int out_row_pix;          // output pixels per row
   int osh, oah, osw, oaw;   // output pixel = (p*osh+oah, q*osw+oaw)
   int ldc;                  // elements between consecutive output pixels
+  int cluster;              // thread-block cluster size along M (1 or 2): weight tile multicast
   int tma_store;            // 1: epilogue stages 32x64 sub-tiles in smem and stores them with TMA (tmC)
   __nv_bfloat16* out;
   const float* bias;
@@ -79,7 +80,11 @@ __device__ __forceinline__ void load_addend(uint4 (&a)[8], const FwdParams& p, i
 }
 
 // ============================================================================================
-template <int BLOCK_N>
+// CL = thread-block cluster size along M (1 or 2).  With CL = 2 the two CTAs of a cluster work on neighbouring
+// M tiles of the SAME N tile: each loads its own A tile and HALF of the weight tile, multicast into both CTAs'
+// shared memory, so the L2 -> SM operand traffic per MMA drops from 48 KB to 32 KB per K block (the compute-bound
+// layers were pinned at the ~12 TB/s L2 delivery rate: 85 FLOP/B * 12 TB/s = 1.0 PFLOP/s).
+template <int BLOCK_N, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ FwdParams p) {
@@ -103,18 +108,24 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m_tiles = (p.M + kBlockM - 1) / kBlockM;
   const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
-  const int total_tiles = m_tiles * n_tiles;
+  // work items are CLUSTER tiles: (group of CL neighbouring M tiles) x (N tile); CTA rank r takes M tile g*CL + r
+  // (an M tile past the end simply has no valid rows: its loads are zero-filled and its stores are masked)
+  const int cta_rank = (CL > 1) ? (int)cluster_ctarank() : 0;
+  const int cl_id = (int)blockIdx.x / CL, n_cl = (int)gridDim.x / CL;
+  const int m_groups = (m_tiles + CL - 1) / CL;
+  const int total_tiles = m_groups * n_tiles;
   const int kiters = p.ntaps * p.cchunks;
+  constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmC);
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CL); }
     for (int i = 0; i < kAccStages; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();      // peers' barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -122,8 +133,9 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int m_t = tile / n_tiles, n_t = tile - m_t * n_tiles;   // m-major: the CTAs running together share A tiles (one HBM read), weights stay in L2
+      for (int tile = cl_id; tile < total_tiles; tile += n_cl) {
+        const int m_g = tile / n_tiles, n_t = tile - m_g * n_tiles;   // m-major: CTAs running together share A tiles, weights stay in L2
+        const int m_t = m_g * CL + cta_rank;
         const int m0 = m_t * kBlockM;
         int cn = 0, cp = 0, cq = 0;
         if (p.a_mode == 1) decompose_pixel(m0, p.P_it, p.Q_it, cn, cp, cq);
@@ -141,7 +153,11 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               tma_load_im2col_4d(sA, &tmA, &full_bar[stage], cc * kBlockK, cw, ch, cn, te.off_w, te.off_h);
             else
               tma_load_2d(sA, &tmA, &full_bar[stage], te.kofs + cc * kBlockK, m0);
-            tma_load_2d(sB, &tmB, &full_bar[stage], te.kofs + cc * kBlockK, n_t * BLOCK_N);
+            if (CL == 1)
+              tma_load_2d(sB, &tmB, &full_bar[stage], te.kofs + cc * kBlockK, n_t * BLOCK_N);
+            else      // my 1/CL slice of the weight tile, delivered to every CTA of the cluster
+              tma_load_2d_mc(sB + cta_rank * (kBBytes / CL), &tmB, &full_bar[stage], te.kofs + cc * kBlockK,
+                             n_t * BLOCK_N + cta_rank * (BLOCK_N / CL), kMask);
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -153,7 +169,7 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = cl_id; tile < total_tiles; tile += n_cl) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
@@ -169,7 +185,9 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in 16-B units
             umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0);
           }
-          umma_commit(&empty_bar[stage]);     // frees this smem stage when the MMAs have read it
+          // frees this smem stage when the MMAs have read it; with a cluster the stage is also written by the
+          // peers' multicasts, so every CTA's producer must see all CL consumers release it
+          if (CL == 1) umma_commit(&empty_bar[stage]); else umma_commit_mc(&empty_bar[stage], kMask);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull_bar[acc]);         // accumulator complete -> epilogue
@@ -181,8 +199,9 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
     int acc = 0; uint32_t acc_phase = 0;
     int stg_sel = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const int m_t = tile / n_tiles, n_t = tile - m_t * n_tiles;
+    for (int tile = cl_id; tile < total_tiles; tile += n_cl) {
+      const int m_g = tile / n_tiles, n_t = tile - m_g * n_tiles;
+      const int m_t = m_g * CL + cta_rank;
       const int row = m_t * kBlockM + quarter * 32 + lane;
       const bool row_ok = row < p.M;
       long long opix = 0;
@@ -204,8 +223,6 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const int n0 = n_t * BLOCK_N + c;
           if (n0 >= p.N) break;
           uint8_t* buf = my_stg + stg_sel * kStgBytes;
-          if (lane == 0) bulk_wait_read<1>();            // the store that last used this buffer has read it
-          __syncwarp();
           if (p.addend) {
             // addend sub-tile of THIS chunk was prefetched into registers one chunk earlier (coalesced: 8 lanes
             // cover one 128-byte row, 4 rows per instruction); stage it, then prefetch the next chunk's
@@ -255,9 +272,26 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               *(uint4*)(buf + lane * 128 + ((chunk16 ^ (lane & 7)) << 4)) = pk;
             }
           }
-          fence_proxy_async();
           __syncwarp();
-          if (lane == 0) { tma_store_2d(&tmC, buf, n0, m_t * kBlockM + quarter * 32); bulk_commit(); }
+          // smem -> global, coalesced: 8 lanes write one full 128-byte output row, 4 rows per instruction.
+          // Plain stores are fire-and-forget, so the staging buffer is free again after this read-back
+          // (a TMA store here made every chunk wait ~2 us for the previous store to drain: 9 us per tile).
+          {
+            const int r_in = lane >> 3, c16 = lane & 7;
+            uint4 o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int row_l = i * 4 + r_in;
+              o[i] = *(const uint4*)(buf + row_l * 128 + ((c16 ^ (row_l & 7)) << 4));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const long long grow = (long long)m_t * kBlockM + quarter * 32 + i * 4 + r_in;
+              if (grow < p.M && n0 + c16 * 8 + 8 <= p.N)
+                *reinterpret_cast<uint4*>(p.out + grow * p.ldc + n0 + c16 * 8) = o[i];
+            }
+          }
+          __syncwarp();
           stg_sel ^= 1;
         }
       } else {
@@ -302,10 +336,9 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (lane == 0) mbar_arrive(&tempty_bar[acc]);
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
-    if (p.tma_store && lane == 0) bulk_wait_all();     // outstanding tile stores must land before exit
   }
   tc_fence_before();
-  __syncthreads();
+  if (CL > 1) cluster_sync_all(); else __syncthreads();      // nobody exits while a peer may still multicast into it
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
 }
 
@@ -596,18 +629,26 @@ static int pick_block_n(long long m_tiles, int n) {
   return best;
 }
 
-template <int BN>
+template <int BN, int CL>
 static int launch_fwd(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const FwdParams& p, cudaStream_t st) {
   constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
   constexpr int smem = kStages * (kBlockM * kBlockK * 2 + BN * kBlockK * 2) + 8 * 32 * 128 + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
-    TP_CUDA_CHECK(cudaFuncSetAttribute(k_igemm_fwd<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TP_CUDA_CHECK(cudaFuncSetAttribute(k_igemm_fwd<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  const long long tiles = (long long)((p.M + kBlockM - 1) / kBlockM) * ((p.N + BN - 1) / BN);
-  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  k_igemm_fwd<BN><<<grid, kThreads, smem, st>>>(a, b, c, p);
+  const long long m_tiles = (p.M + kBlockM - 1) / kBlockM;
+  const long long ctiles = ((m_tiles + CL - 1) / CL) * ((p.N + BN - 1) / BN);
+  const long long max_cl = sm_count() / CL;
+  const int grid = (int)(ctiles < max_cl ? ctiles : max_cl) * CL;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  TP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_igemm_fwd<BN, CL>, a, b, c, p));
   TP_LAUNCH_CHECK();
   return TP_OK;
 }
@@ -628,9 +669,26 @@ static int run_fwd(const CUtensorMap& a, const CUtensorMap& b, FwdParams& p, cud
     p.tma_store = 1;
   }
   const int bn = pick_block_n((p.M + kBlockM - 1) / kBlockM, p.N);
-  if (bn == 256) return launch_fwd<256>(a, b, c, p, st);
-  if (bn == 128) return launch_fwd<128>(a, b, c, p, st);
-  return launch_fwd<64>(a, b, c, p, st);
+  if (p.cluster == 2) {
+    if (bn == 256) return launch_fwd<256, 2>(a, b, c, p, st);
+    if (bn == 128) return launch_fwd<128, 2>(a, b, c, p, st);
+    return launch_fwd<64, 2>(a, b, c, p, st);
+  }
+  if (bn == 256) return launch_fwd<256, 1>(a, b, c, p, st);
+  if (bn == 128) return launch_fwd<128, 1>(a, b, c, p, st);
+  return launch_fwd<64, 1>(a, b, c, p, st);
+}
+
+// Cluster size for a problem: pairs of M tiles share the weight tile (multicast) whenever there are enough tiles.
+static int pick_cluster(long long m_tiles) {
+  static int forced = -1;
+  if (forced < 0) { const char* e = getenv("TP_IGEMM_CLUSTER"); forced = e ? atoi(e) : 0; }
+  if (forced == 1 || forced == 2) return forced;
+  (void)m_tiles;
+  // Measured on B200 (profiles/r01_notes.md): multicast halves the L2->SM weight traffic but does not move the
+  // step time — the mainloop is bound by bytes-in-flight (4 x 48 KB stages vs ~1.5 us load latency), not by L2
+  // bandwidth.  Kept behind TP_IGEMM_CLUSTER=2 (parity-tested) as the stepping stone to cta_group::2 tiles.
+  return 1;
 }
 
 }  // namespace tp
@@ -689,7 +747,8 @@ int tp_conv_fprop(const tp_conv_desc* d, const void* x, const void* wf, const vo
     if (rc) return rc;
   }
   const int bn = pick_block_n((p.M + kBlockM - 1) / kBlockM, p.N);
-  rc = make_tiled_map(&tb, wf, (uint64_t)d->r * d->s * d->cin, (uint64_t)d->cout, (uint64_t)d->r * d->s * d->cin, (uint32_t)bn);
+  p.cluster = pick_cluster((p.M + kBlockM - 1) / kBlockM);
+  rc = make_tiled_map(&tb, wf, (uint64_t)d->r * d->s * d->cin, (uint64_t)d->cout, (uint64_t)d->r * d->s * d->cin, (uint32_t)(bn / p.cluster));
   if (rc) return rc;
   return run_fwd(ta, tb, p, st);
 }
@@ -731,7 +790,8 @@ int tp_conv_dgrad(const tp_conv_desc* d, const void* dy, const void* wd, const v
       if (rc) return rc;
     }
     const int bn = pick_block_n((p.M + kBlockM - 1) / kBlockM, p.N);
-    rc = make_tiled_map(&tb, wd, (uint64_t)ktot, (uint64_t)d->cin, (uint64_t)ktot, (uint32_t)bn); if (rc) return rc;
+    p.cluster = pick_cluster((p.M + kBlockM - 1) / kBlockM);
+    rc = make_tiled_map(&tb, wd, (uint64_t)ktot, (uint64_t)d->cin, (uint64_t)ktot, (uint32_t)(bn / p.cluster)); if (rc) return rc;
     return run_fwd(ta, tb, p, st);
   }
   // strided conv: decompose dX into stride_h x stride_w parity classes; each class is a
@@ -772,7 +832,8 @@ int tp_conv_dgrad(const tp_conv_desc* d, const void* dy, const void* wd, const v
     CUtensorMap ta, tb;
     rc = make_im2col_map(&ta, dy, d->n, d->p, d->q, cop, p.base_w, p.base_h, 1, 1, Hc, Wc, kBlockM); if (rc) return rc;
     const int bn = pick_block_n((p.M + kBlockM - 1) / kBlockM, p.N);
-    rc = make_tiled_map(&tb, wd, (uint64_t)ktot, (uint64_t)d->cin, (uint64_t)ktot, (uint32_t)bn); if (rc) return rc;
+    p.cluster = pick_cluster((p.M + kBlockM - 1) / kBlockM);
+    rc = make_tiled_map(&tb, wd, (uint64_t)ktot, (uint64_t)d->cin, (uint64_t)ktot, (uint32_t)(bn / p.cluster)); if (rc) return rc;
     rc = run_fwd(ta, tb, p, st); if (rc) return rc;
   }
   return TP_OK;
