@@ -28,7 +28,8 @@ using namespace ptx;
 
 constexpr int kBlockM = 128;         // UMMA M
 constexpr int kBlockK = 64;          // 64 bf16 = 128 B = one swizzle row
-constexpr int kThreads = 192;
+constexpr int kThreads = 192;          // wgrad kernel: TMA warp, MMA warp, 4 epilogue warps
+constexpr int kFwdThreads = 320;       // fwd kernel: TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
 constexpr int kMaxTaps = 64;
 
 struct TapEntry { uint16_t off_w, off_h; int32_t kofs; };
@@ -85,7 +86,7 @@ __device__ __forceinline__ void load_addend(uint4 (&a)[8], const FwdParams& p, i
 // shared memory, so the L2 -> SM operand traffic per MMA drops from 48 KB to 32 KB per K block (the compute-bound
 // layers were pinned at the ~12 TB/s L2 delivery rate: 85 FLOP/B * 12 TB/s = 1.0 PFLOP/s).
 template <int BLOCK_N, int CL>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kFwdThreads, 1)
 k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ FwdParams p) {
   constexpr int kABytes = kBlockM * kBlockK * 2;           // 16 KB
@@ -120,7 +121,7 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmC);
     for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CL); }
-    for (int i = 0; i < kAccStages; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+    for (int i = 0; i < kAccStages; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
     fence_mbar_init();
   }
   if (warp == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
@@ -196,9 +197,12 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else {
     // ------------------------------ epilogue ------------------------------
+    // 8 epilogue warps: the HBM-bound layers were limited by how fast 4 warps could drain TMEM (ncu: 3.5 TB/s of
+    // DRAM traffic at 30 % tensor activity).  Two warps share each TMEM lane quarter and split the columns.
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;         // which half of the 64-column chunks this warp drains
     int acc = 0; uint32_t acc_phase = 0;
-    int stg_sel = 0;
+    constexpr int stg_sel = 0;
     for (int tile = cl_id; tile < total_tiles; tile += n_cl) {
       const int m_g = tile / n_tiles, n_t = tile - m_g * n_tiles;
       const int m_t = m_g * CL + cta_rank;
@@ -216,10 +220,10 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       if (p.tma_store) {
         // TMEM -> registers -> 128B-swizzled smem sub-tile (32 rows x 64 cols) -> TMA store: every
         // output line leaves the SM as full 128-byte rows instead of 32 scattered 16-byte pieces.
-        uint8_t* my_stg = stg_base + (warp - 2) * 2 * kStgBytes;
+        uint8_t* my_stg = stg_base + (warp - 2) * kStgBytes;
         uint4 a_pref[8];
 #pragma unroll 1
-        for (int c = 0; c < BLOCK_N; c += 64) {
+        for (int c = half * 64; c < BLOCK_N; c += 128) {
           const int n0 = n_t * BLOCK_N + c;
           if (n0 >= p.N) break;
           uint8_t* buf = my_stg + stg_sel * kStgBytes;
@@ -227,13 +231,13 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             // addend sub-tile of THIS chunk was prefetched into registers one chunk earlier (coalesced: 8 lanes
             // cover one 128-byte row, 4 rows per instruction); stage it, then prefetch the next chunk's
             const int r_in = lane >> 3, c16 = lane & 7;
-            if (c == 0) load_addend(a_pref, p, m_t, quarter, r_in, c16, n0);
+            if (c == half * 64) load_addend(a_pref, p, m_t, quarter, r_in, c16, n0);
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const int row_l = i * 4 + r_in;
               *(uint4*)(buf + row_l * 128 + ((c16 ^ (row_l & 7)) << 4)) = a_pref[i];
             }
-            if (c + 64 < BLOCK_N && n0 + 64 < p.N) load_addend(a_pref, p, m_t, quarter, r_in, c16, n0 + 64);
+            if (c + 128 < BLOCK_N && n0 + 128 < p.N) load_addend(a_pref, p, m_t, quarter, r_in, c16, n0 + 128);
             __syncwarp();
           }
 #pragma unroll
@@ -292,11 +296,10 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             }
           }
           __syncwarp();
-          stg_sel ^= 1;
         }
       } else {
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N; c += 32) {
+      for (int c = half * 32; c < BLOCK_N; c += 64) {
         uint32_t v[32];
         tmem_ld_32x32(t_base + (uint32_t)c, v);
         tmem_ld_wait();
@@ -381,7 +384,11 @@ k_igemm_wgrad(const __grid_constant__ CUtensorMap tmA /* dY [Kpix, Cout] */,
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        const int split = item % p.splits, tile = item / p.splits;
+        // split-major order: the CTAs running at the same time work on the SAME pixel range for different
+        // (m, n) tiles, so each X / dY chunk comes from HBM once and from L2 for the siblings (ncu: 35.7 GB of
+        // DRAM reads per step with tile-major order vs ~23 GB algorithmic)
+        const int ntile = p.m_tiles * p.n_tiles;
+        const int split = item / ntile, tile = item - split * ntile;
         const int n_t = tile / p.m_tiles, m_t = tile % p.m_tiles;
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
@@ -430,7 +437,7 @@ k_igemm_wgrad(const __grid_constant__ CUtensorMap tmA /* dY [Kpix, Cout] */,
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
-        const int split = item % p.splits;
+        const int split = item / (p.m_tiles * p.n_tiles);
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 12);
@@ -461,7 +468,9 @@ k_igemm_wgrad(const __grid_constant__ CUtensorMap tmA /* dY [Kpix, Cout] */,
     const int quarter = warp & 3;
     int acc = 0; uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
-      float* prow = p.partial + ((long long)item * kBlockM + quarter * 32 + lane) * ncols;
+      const int ntile = p.m_tiles * p.n_tiles;
+      const int split = item / ntile, tile = item - split * ntile;
+      float* prow = p.partial + (((long long)tile * p.splits + split) * kBlockM + quarter * 32 + lane) * ncols;
       mbar_wait(&tfull_bar[acc], acc_phase, 14);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * 256);
@@ -643,7 +652,7 @@ static int launch_fwd(const CUtensorMap& a, const CUtensorMap& b, const CUtensor
   const long long max_cl = sm_count() / CL;
   const int grid = (int)(ctiles < max_cl ? ctiles : max_cl) * CL;
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kFwdThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
