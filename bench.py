@@ -299,15 +299,41 @@ def main():
     pk = peaks()
     flops = GFLOP_PER_IMG * 1e9 * B * K
     achieved_tf = flops / (gemm_ms / 1e3) / 1e12 if gemm_ms > 0 else 0.0
-    roofline = {"bound": "tensor", "achieved": achieved_tf, "peak": pk["tf"], "unit": "TFLOP/s",
-                "frac": achieved_tf / pk["tf"], "traffic": None, "peak_source": pk["src"] + " sustained bf16",
-                "kernel": "k_igemm_fwd / k_igemm_wgrad (masked implicit GEMM, tcgen05)",
-                "launches_per_step": sum(v[2] for v in tot.values()) / KT,
+    # Algorithmic bytes of the masked convs/linears (bf16 activations in + out per op):
+    # fprop x+y, dgrad dy+dx (the stem has no dgrad), wgrad x+dy.  Shapes taken from the live model.
+    io = {}
+    hooks = []
+    for name, m in model._masked():
+        hooks.append(m.register_forward_hook(lambda mod, inp, out, name=name: io.__setitem__(name, (inp[0].numel(), (out[0] if isinstance(out, tuple) else out).numel()))))
+    model.eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        model(pool[0][0][:2])
+    model.train()
+    for h in hooks:
+        h.remove()
+    first = next(iter(io))
+    per_img = sum(3 * (a + b) for a, b in io.values()) - sum(io[first])          # elements per 2 images
+    alg_bytes_step = 2.0 * per_img / 2 * B
+    achieved_gbs = alg_bytes_step * K / (gemm_ms / 1e3) / 1e9 if gemm_ms > 0 else 0.0
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "r01_igemm_traffic.json")
+    if os.path.isfile(tpath) and B == 512:
+        traffic = json.load(open(tpath))["dram_bytes_per_launch"]
+    n_launch = sum(v[2] for v in tot.values()) / KT
+    roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": pk["hbm"], "unit": "GB/s",
+                "frac": achieved_gbs / pk["hbm"], "traffic": traffic,
+                "traffic_note": "dram read+write per igemm kernel launch, ncu over one eager step at B=512 (profiles/r01_igemm_traffic.json)" if traffic else None,
+                "peak_source": pk["src"] + " HBM copy bandwidth",
+                "kernel": "k_igemm_fwd (fprop+dgrad) / k_igemm_wgrad — masked implicit GEMM, tcgen05 + TMA",
+                "why_hbm": "sum over the 54 layers: conv I/O bytes / HBM peak (11.4 ms at B=512) exceeds FLOPs / tensor peak (8.5 ms); 30 of 54 layers are HBM-bound",
+                "algorithmic_bytes_per_step": alg_bytes_step, "algorithmic_bytes_per_launch": alg_bytes_step / n_launch,
+                "launches_per_step": n_launch,
                 "timing": f"CUDA events around each masked-GEMM C-ABI call over {KT} eager steps ({ms_eager / KT:.2f} ms/step eager); step rate from CUDA-graph replay" if use_graph else "CUDA events, eager",
                 "ms_per_step_in_kernel": gemm_ms / K,
                 "by_op_ms_per_step": {k: v[0] / KT for k, v in tot.items()},
                 "share_of_step": gemm_ms / ms_total,
-                "flops_per_step": GFLOP_PER_IMG * 1e9 * B,
+                "tensor": {"achieved_tflops": achieved_tf, "peak_tflops": pk["tf"], "frac": achieved_tf / pk["tf"],
+                           "flops_per_step": GFLOP_PER_IMG * 1e9 * B, "peak_source": pk["src"] + " sustained bf16"},
                 "frac_of_masked_gemm_roofline_img_s": (img_s / world) / ROOFLINE_IMG_S}
 
     # ---- end-to-end run: pinned host inputs copied every step, loss read back every step ----
