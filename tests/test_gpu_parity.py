@@ -363,3 +363,132 @@ def test_run_experiment_level_loop(dev, tmp_path):
     ref_masks, _, _ = P.prune_global(ws, ms, 0.8)
     for n, rm in zip(names, ref_masks):
         assert np.array_equal(lvl1[n + ".mask"].cpu().numpy(), rm), n
+
+
+# ---------------------------------------------------------------- fused BN / pooling / graph / other configs -----
+BN_CASES = [(4, 64, 9, 7, True, False), (8, 256, 14, 14, True, True), (3, 2048, 7, 7, False, False), (16, 64, 56, 56, True, False),
+            (2, 192, 5, 5, False, True)]
+
+
+@pytest.mark.parametrize("case", BN_CASES)
+def test_fused_batchnorm_vs_torch(dev, case):
+    """BatchNorm2dB200 (+residual)(+ReLU) vs torch's BatchNorm2d evaluated in fp32 on the same bf16 inputs:
+    outputs / input grads are bf16 (<= 1e-2 of max), parameter grads and running statistics fp32 (<= 1e-4)."""
+    from turboprune_b200.fused_norm import BatchNorm2dB200
+    n, c, h, w, relu, res = case
+    g = torch.Generator().manual_seed(c + n)
+    x = (torch.randn(n, c, h, w, generator=g) * 1.7 + 0.3).to(dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    r = torch.randn(n, c, h, w, generator=g).to(dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last) if res else None
+    bn = BatchNorm2dB200(c).to(dev); ref = torch.nn.BatchNorm2d(c).to(dev)
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(c, generator=g) + 0.5); bn.bias.copy_(torch.randn(c, generator=g) * 0.1)
+    ref.load_state_dict(bn.state_dict())
+    xa = x.clone().requires_grad_(True); xb = x.clone().float().requires_grad_(True)
+    ra = r.clone().requires_grad_(True) if res else None; rb = r.clone().float().requires_grad_(True) if res else None
+    z = bn(xa, residual=ra, relu=relu)
+    zr = ref(xb)
+    zr = zr + rb if res else zr
+    zr = torch.relu(zr) if relu else zr
+    dz = torch.randn(z.shape, generator=g).to(dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    z.backward(dz); zr.backward(dz.float())
+    assert _rel(z, zr) < 1e-2 and _rel(xa.grad, xb.grad) < 1e-2
+    assert _rel(bn.weight.grad, ref.weight.grad) < 1e-4 and _rel(bn.bias.grad, ref.bias.grad) < 1e-4
+    assert _rel(bn.running_mean, ref.running_mean) < 1e-4 and _rel(bn.running_var, ref.running_var) < 1e-4
+    assert int(bn.num_batches_tracked) == 1
+    if res:
+        assert _rel(ra.grad, rb.grad) < 1e-2
+    bn.eval(); ref.eval()
+    with torch.no_grad():
+        assert _rel(bn(x, relu=relu), torch.relu(ref(x.float())) if relu else ref(x.float())) < 1e-2
+
+
+def test_maxpool_vs_torch(dev):
+    from turboprune_b200.fused_norm import MaxPool2dB200
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(6, 64, 23, 17, generator=g).to(dev).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    for k, s, p in ((3, 2, 1), (2, 2, 0), (3, 1, 1)):
+        xa = x.clone().requires_grad_(True); xb = x.clone().float().requires_grad_(True)
+        ya = MaxPool2dB200(k, s, p)(xa); yb = torch.nn.functional.max_pool2d(xb, k, s, p)
+        assert torch.equal(ya.float(), yb)                                    # selection is exact
+        dy = torch.randn(ya.shape, generator=g).to(dev).to(torch.bfloat16)
+        ya.backward(dy); yb.backward(dy.float())
+        assert _rel(xa.grad, xb.grad) < 1e-2                                  # sums of <= 4 bf16 values, rounded once
+
+
+def test_cuda_graph_step_is_bit_identical_to_eager(dev):
+    """The captured train step (persistent gradient arena, device-scalar LR, cached SGD table) replays the same
+    kernels: two eager steps and two graph replays from the same state give bit-identical weights."""
+    import copy
+    import refshim
+    from turboprune_b200.grad_exchange import GradArena
+    from turboprune_b200.optim import FusedSGD
+    from turboprune_b200.utils import custom_models as cm, pruning_utils as pu
+    torch.manual_seed(0)
+    base = cm.TorchVisionModel(refshim.make_cfg("resnet18", "cifar10"))
+    torch.manual_seed(1)
+    pu.prune_er_erk(base, 0.2)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(64, 3, 32, 32, generator=g).to(dev); t = torch.randint(0, 10, (64,), generator=g).to(dev)
+
+    def make():
+        m = copy.deepcopy(base).to(dev).train()
+        opt = FusedSGD(m.parameters(), lr=0.05, momentum=0.9, weight_decay=5e-4, capturable=True)
+        return m, opt, GradArena(list(m.parameters()))
+
+    def body(m, opt, arena):
+        arena.zero()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = torch.nn.functional.cross_entropy(m(x), t)
+        loss.backward()
+        opt.step()
+        return loss
+
+    m1, o1, a1 = make()
+    for _ in range(4):
+        body(m1, o1, a1)
+    m2, o2, a2 = make()
+    side = torch.cuda.Stream(dev); side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            body(m2, o2, a2)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(gr, capture_error_mode="thread_local"):
+        body(m2, o2, a2)
+    gr.replay(); gr.replay()
+    torch.cuda.synchronize()
+    for (n1, p1), (n2, p2) in zip(m1.named_parameters(), m2.named_parameters()):
+        assert torch.equal(p1, p2), n1
+    for (n1, b1), (n2, b2) in zip(m1.named_buffers(), m2.named_buffers()):
+        if "num_batches_tracked" not in n1:
+            assert torch.equal(b1, b2), n1
+
+
+def test_config4_vgg16_synflow_and_config5_deit_snip(dev):
+    """BASELINE.json configs 4 and 5 as parity-test cases: VGG-16 / CIFAR-100 shape with one-shot SynFlow to 95 %,
+    DeiT-small with SNIP to 50 % (masked Linear path): pruning hits the target sparsity, masks are {0,1}, a train
+    step through the kernels gives a finite loss."""
+    import refshim
+    from turboprune_b200.utils import custom_models as cm, pruning_utils as pu
+    from turboprune_b200.utils.dataset import SyntheticLoader
+    for model, cfg, shape, ncls, method, density in (
+            (None, refshim.make_cfg("vgg16", "cifar100", precision="bfloat16", prune_method="synflow"), (3, 32, 32), 100, pu.prune_synflow, 0.05),
+            ("deit", refshim.make_cfg("local_deit_small_patch16_224", "imagenet", mask_layer_type="LinearMask", precision="bfloat16",
+                                      prune_method="snip"), (3, 224, 224), 1000, pu.prune_snip, 0.5)):
+        torch.manual_seed(0)
+        net = (cm.CustomModel(cfg) if model == "deit" else cm.TorchVisionModel(cfg)).to(dev).train()
+        loader = SyntheticLoader(8, 2, shape, ncls, dev, seed=1)
+        method(cfg, net, loader, density)
+        sp = net.get_overall_sparsity()
+        assert abs(sp - (1 - density) * 100) < 0.01, sp
+        for _, m in net._masked():
+            assert bool(((m.mask == 0) | (m.mask == 1)).all())
+        opt = torch.optim.SGD(net.parameters(), lr=0.01, momentum=0.9)
+        xb, tb = next(iter(loader))
+        opt.zero_grad()                                   # prune_snip leaves its scoring gradients in .grad (like the reference)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = torch.nn.functional.cross_entropy(net(xb), tb)
+        loss.backward(); opt.step()
+        assert bool(torch.isfinite(loss))
+        for _, m in net._masked():
+            assert bool((m.weight.grad[m.mask == 0] == 0).all())

@@ -28,7 +28,7 @@ class _BNFn(torch.autograd.Function):
         rn = ops.to_nhwc_bf16(residual, c) if residual is not None else None
         m = n * h * w
         dev = x.device
-        z = torch.empty(n, h, w, c, dtype=torch.bfloat16, device=dev)
+        z = ops.empty_cl(n, c, h, w, dev)
         save_mean = torch.empty(c, dtype=torch.float32, device=dev) if training else None
         save_invstd = torch.empty(c, dtype=torch.float32, device=dev) if training else None
         wsb = ops._workspace(lib.tp_bn_workspace_bytes(m, c), dev, "bn")
@@ -41,11 +41,11 @@ class _BNFn(torch.autograd.Function):
         if training:
             # ReLU gate: recomputed from y in the backward unless a residual was added (then z itself is needed)
             ctx.relu = 0 if not relu else (1 if residual is not None else 2)
-            ctx.save_for_backward(xn, z if ctx.relu == 1 else None, weight, bias, save_mean, save_invstd)
+            ctx.save_for_backward(xn, z.permute(0, 2, 3, 1) if ctx.relu == 1 else None, weight, bias, save_mean, save_invstd)
             ctx.has_res = residual is not None
             ctx.res_dtype = residual.dtype if residual is not None else None
             ctx.x_dtype = x.dtype
-        return z.permute(0, 3, 1, 2)
+        return z
 
     @staticmethod
     def backward(ctx, dz):
@@ -100,7 +100,7 @@ class _MaxPoolFn(torch.autograd.Function):
         xn = ops.to_nhwc_bf16(x, c)
         p = (h + 2 * pad - k) // stride + 1
         q = (w + 2 * pad - k) // stride + 1
-        y = torch.empty(n, p, q, c, dtype=torch.bfloat16, device=x.device)
+        y = ops.empty_cl(n, c, p, q, x.device)
         idx = torch.empty(n, p, q, c, dtype=torch.uint8, device=x.device)
         with torch.cuda.device(x.device):
             rc = lib.tp_maxpool_forward(_ptr(xn), _ptr(y), _ptr(idx), n, h, w, c, k, stride, pad, p, q, _cabi.stream_ptr(x.device))
@@ -109,7 +109,7 @@ class _MaxPoolFn(torch.autograd.Function):
         ctx.save_for_backward(idx)
         ctx.geom = (n, h, w, c, k, stride, pad, p, q)
         ctx.x_dtype = x.dtype
-        return y.permute(0, 3, 1, 2)
+        return y
 
     @staticmethod
     def backward(ctx, dy):

@@ -271,10 +271,16 @@ def im2col_c8(x_nhwc8, desc, kp):
     return out
 
 
-def conv_fprop(desc, x_nhwc, wf, bias=None):
+def empty_cl(n, c, h, w, device):
+    """[n, c, h, w] bf16 with channels_last strides: the memory IS an NHWC array, and the tensor is not a view
+    (autograd forbids in-place ops such as nn.ReLU(inplace=True) on views created inside a custom Function)."""
+    return torch.empty((n, c, h, w), dtype=torch.bfloat16, device=device, memory_format=torch.channels_last)
+
+
+def conv_fprop(desc, x_nhwc, wf, bias=None, out=None):
     lib = _cabi.load()
     dev = x_nhwc.device
-    y = torch.empty(desc.n, desc.p, desc.q, desc.cout, dtype=torch.bfloat16, device=dev)
+    y = out if out is not None else torch.empty(desc.n, desc.p, desc.q, desc.cout, dtype=torch.bfloat16, device=dev)
     with torch.cuda.device(dev), _Timed("fprop", desc):
         rc = lib.tp_conv_fprop(ctypes.byref(desc), c_void_p(x_nhwc.data_ptr()), c_void_p(wf.data_ptr()),
                                c_void_p(bias.data_ptr()) if bias is not None else None, c_void_p(y.data_ptr()),
@@ -348,14 +354,16 @@ class MaskedConv2dFn(torch.autograd.Function):
             xg = im2col_c8(x8, desc, kp)
             gdesc = _cabi.ConvDesc(n * desc.p * desc.q, 1, 1, kp, cout, 1, 1, 1, 1, 0, 0, 1, 1)
             wf, wd = stage_weights(w32, m32, 8, False)
-            y = conv_fprop(gdesc, xg, wf, bias).view(n, desc.p, desc.q, cout)
+            y = empty_cl(n, cout, desc.p, desc.q, x.device)
+            conv_fprop(gdesc, xg, wf, bias, out=y)
             ctx.mode = "stem"
             ctx.gdesc = gdesc
             ctx.save_for_backward(xg, m32)
         else:
             xn = to_nhwc_bf16(x, cin)
             wf, wd = stage_weights(w32, m32, cin, need_dx, cout_p)
-            y = conv_fprop(desc, xn, wf, bias)
+            y = empty_cl(n, cout, desc.p, desc.q, x.device)
+            conv_fprop(desc, xn, wf, bias, out=y)
             ctx.mode = "conv"
             ctx.save_for_backward(xn, m32, wd)
         ctx.desc = desc
@@ -366,8 +374,8 @@ class MaskedConv2dFn(torch.autograd.Function):
             # second output = the input itself: whatever gradient reaches it (the identity path of a residual
             # block, or a downsample branch) comes back to backward() as ``dskip`` and is accumulated inside
             # the dgrad epilogue instead of by autograd's separate elementwise add
-            return y.permute(0, 3, 1, 2), x
-        return y.permute(0, 3, 1, 2)
+            return y, x
+        return y
 
     @staticmethod
     def backward(ctx, dy, dskip=None):
