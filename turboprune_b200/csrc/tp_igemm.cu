@@ -498,26 +498,47 @@ k_igemm_wgrad(const __grid_constant__ CUtensorMap tmA /* dY [Kpix, Cout] */,
 // One CTA per output channel; K index kk = tap*cin_p + ci is the column of the partial tiles.
 __global__ void __launch_bounds__(256) k_wgrad_finalize(const float* __restrict__ partial, const float* __restrict__ mask,
                                                         float* __restrict__ dw, int cout, int cin_real, int cin_p, int rs,
-                                                        int nb, int m_tiles, int n_tiles, int splits) {
-  extern __shared__ float s_row[];      // [rs * cin_p] when rs > 1
+                                                        int nb, int m_tiles, int n_tiles, int splits, int sl) {
+  // One CTA per output channel.  256 threads = KT k-lanes x `sl` split-lanes (sl = power of two <= min(splits, 8)):
+  // split lane j folds splits j, j+sl, ... with four independent loads in flight, then the lanes are combined in
+  // lane order — a fixed summation order (deterministic), but no longer one long serial chain of L2 round trips
+  // per thread (the skinny layers run with ~300 splits; this kernel was 17 % of the B=64 step).
+  extern __shared__ float s_mem[];       // [sl][KT] lane sums, then [rs * cin_p] row when rs > 1
   const int co = blockIdx.x;
   const int m_t = co / kBlockM, r = co % kBlockM;
   const int ktot = rs * cin_p;
   const int ncols = nb * 64;
+  const int KT = 256 / sl;
+  const int kl = threadIdx.x % KT, sj = threadIdx.x / KT;
+  float* s_lane = s_mem;                 // sl * KT floats = 256
+  float* s_row = s_mem + 256;
   const long long obase = (long long)co * cin_real * rs;
-  for (int kk = threadIdx.x; kk < ktot; kk += blockDim.x) {
-    const int chunk = kk >> 6, n_t = chunk / nb, col = (chunk - n_t * nb) * 64 + (kk & 63);
-    const long long item0 = ((long long)n_t * m_tiles + m_t) * splits;
-    float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += partial[((item0 + s) * kBlockM + r) * ncols + col];
-    if (rs == 1) {
-      if (kk < cin_real) dw[obase + kk] = mask[obase + kk] * acc;
-    } else {
-      s_row[kk] = acc;
+  const long long sstride = (long long)kBlockM * ncols;          // floats between consecutive splits of a tile
+  for (int k0 = 0; k0 < ktot; k0 += KT) {
+    const int kk = k0 + kl;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (kk < ktot) {
+      const int chunk = kk >> 6, n_t = chunk / nb, col = (chunk - n_t * nb) * 64 + (kk & 63);
+      const float* base = partial + ((((long long)n_t * m_tiles + m_t) * splits) * kBlockM + r) * ncols + col;
+      int sp = sj;
+      for (; sp + 3 * sl < splits; sp += 4 * sl) {
+        const float v0 = base[(long long)sp * sstride], v1 = base[(long long)(sp + sl) * sstride];
+        const float v2 = base[(long long)(sp + 2 * sl) * sstride], v3 = base[(long long)(sp + 3 * sl) * sstride];
+        a0 += v0; a1 += v1; a2 += v2; a3 += v3;
+      }
+      for (; sp < splits; sp += sl) a0 += base[(long long)sp * sstride];
     }
+    s_lane[sj * KT + kl] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (sj == 0 && kk < ktot) {
+      float acc = 0.f;
+      for (int j = 0; j < sl; ++j) acc += s_lane[j * KT + kl];
+      if (rs == 1) { if (kk < cin_real) dw[obase + kk] = mask[obase + kk] * acc; }
+      else s_row[kk] = acc;
+    }
+    __syncthreads();
   }
   if (rs > 1) {
-    __syncthreads();
     const int nout = cin_real * rs;
     for (int o = threadIdx.x; o < nout; o += blockDim.x) {
       const int ci = o / rs, tap = o - ci * rs;
@@ -903,10 +924,12 @@ int tp_conv_wgrad(const tp_conv_desc* d, const void* x, const void* dy, const vo
   const int items = p.m_tiles * p.n_tiles * splits;
   k_igemm_wgrad<<<items < sms ? items : sms, kThreads, smem, st>>>(ta, tb, p);
   TP_LAUNCH_CHECK();
-  const size_t fin_smem = rs > 1 ? (size_t)rs * d->cin * sizeof(float) : 0;
+  const size_t fin_smem = 256 * sizeof(float) + (rs > 1 ? (size_t)rs * d->cin * sizeof(float) : 0);
   if (fin_smem > 64 * 1024) return TP_ERR_UNSUPPORTED;
+  // split lanes only pay when there are many splits (skinny layers); wide-K layers keep all 256 threads on K
+  const int sl = splits >= 64 ? 8 : (splits >= 32 ? 4 : (splits >= 16 ? 2 : 1));
   k_wgrad_finalize<<<d->cout, 256, fin_smem, st>>>(p.partial, (const float*)mask, (float*)dw, d->cout, cin_real, d->cin, rs,
-                                                    p.nb, p.m_tiles, p.n_tiles, splits);
+                                                    p.nb, p.m_tiles, p.n_tiles, splits, sl);
   TP_LAUNCH_CHECK();
   if (db) {
     k_colsum<<<(d->cout + 31) / 32, 256, 0, st>>>((const __nv_bfloat16*)dy, (long long)p.Kpix, d->cout, d->cout, (float*)db);
