@@ -98,6 +98,12 @@ int tp_to_nhwc_bf16(const void* src, int src_dtype, int64_t sn, int64_t sc, int6
 int tp_im2col_c8(const void* x, int n, int h, int w, int r, int s, int stride_h, int stride_w,
                  int pad_h, int pad_w, int p, int q, void* xcol, int kp, void* stream);
 
+/* Same expansion straight from the framework's input tensor (src_dtype 0 = fp32, 1 = bf16; element strides; c <= 8):
+ * the precision/layout conversion is fused in, the NHWC8 intermediate never exists. */
+int tp_im2col_stem(const void* src, int src_dtype, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
+                   int n, int c, int h, int w, int r, int s, int stride_h, int stride_w, int pad_h, int pad_w,
+                   int p, int q, void* xcol, int kp, void* stream);
+
 /* ---- masked implicit-GEMM convolution / linear on tcgen05 tensor cores -----------------
  * Replaces F.conv2d / F.linear / F.conv1d(k=1) on the masked weight
  * (utils/mask_layers.py:26-34, :70, :110-118) and their autograd backward.

@@ -103,6 +103,39 @@ __global__ void __launch_bounds__(256) k_im2col_c8(const uint4* __restrict__ x, 
   }
 }
 
+// Stem im2col straight from the framework's input tensor (fp32 or bf16, any strides, c <= 8 channels): fuses the
+// layout/precision conversion (k_to_nhwc) into the expansion, so the 3-channel image is read once and the
+// intermediate NHWC8 copy never exists.  Column (r*S + s)*8 + ch, channels >= c are zero.
+template <typename T>
+__global__ void __launch_bounds__(256) k_im2col_stem(const T* __restrict__ src, long long sn, long long sc, long long sh, long long sw,
+                                                     int n, int c, int h, int w, int R, int S, int stride_h, int stride_w,
+                                                     int pad_h, int pad_w, int P, int Q, uint4* __restrict__ xcol, int kp8) {
+  const long long total = (long long)n * P * Q * kp8;
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const long long step = (long long)gridDim.x * blockDim.x;
+  for (; i < total; i += step) {
+    const int cell = (int)(i % kp8);
+    const long long pix = i / kp8;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (cell < R * S) {
+      const int r = cell / S, s = cell - r * S;
+      const int q = (int)(pix % Q); const long long t2 = pix / Q;
+      const int pp = (int)(t2 % P); const int ni = (int)(t2 / P);
+      const int hi = pp * stride_h - pad_h + r, wi = q * stride_w - pad_w + s;
+      if (hi >= 0 && hi < h && wi >= 0 && wi < w) {
+        const T* sp = src + ni * sn + hi * sh + wi * sw;
+        float f[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = j < c ? (float)sp[j * sc] : 0.f;
+        __nv_bfloat162* hv = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) hv[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+      }
+    }
+    xcol[i] = v;
+  }
+}
+
 // torch.optim.SGD (momentum, weight_decay, dampening 0, nesterov False) — one launch for all
 // parameters.  20 B/elem: read w,g,buf; write w,buf.
 __global__ void __launch_bounds__(256) k_sgd(const Seg* __restrict__ segs, int n_seg, long long tiles,
@@ -197,6 +230,20 @@ int tp_im2col_c8(const void* x, int n, int h, int w, int r, int s, int stride_h,
   const long long total = (long long)n * p * q * (kp / 8);
   unsigned grid = (unsigned)min((total + 255) / 256, (long long)sm_count() * 32);
   k_im2col_c8<<<grid, 256, 0, st>>>((const uint4*)x, n, h, w, r, s, stride_h, stride_w, pad_h, pad_w, p, q, (uint4*)xcol, kp / 8);
+  TP_LAUNCH_CHECK();
+  return TP_OK;
+}
+
+int tp_im2col_stem(const void* src, int src_dtype, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
+                   int n, int c, int h, int w, int r, int s, int stride_h, int stride_w, int pad_h, int pad_w,
+                   int p, int q, void* xcol, int kp, void* stream) {
+  if (!src || !xcol || n <= 0 || c <= 0 || c > 8 || kp % 8 != 0 || kp < r * s * 8) return TP_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  const long long total = (long long)n * p * q * (kp / 8);
+  unsigned grid = (unsigned)min((total + 255) / 256, (long long)sm_count() * 32);
+  if (src_dtype == 0) k_im2col_stem<float><<<grid, 256, 0, st>>>((const float*)src, sn, sc, sh, sw, n, c, h, w, r, s, stride_h, stride_w, pad_h, pad_w, p, q, (uint4*)xcol, kp / 8);
+  else if (src_dtype == 1) k_im2col_stem<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, sn, sc, sh, sw, n, c, h, w, r, s, stride_h, stride_w, pad_h, pad_w, p, q, (uint4*)xcol, kp / 8);
+  else return TP_ERR_INVALID;
   TP_LAUNCH_CHECK();
   return TP_OK;
 }

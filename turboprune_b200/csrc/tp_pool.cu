@@ -25,24 +25,23 @@ __global__ void __launch_bounds__(256) k_maxpool_fwd(const __nv_bfloat16* __rest
     const int ci = (int)(i % cv); long long t = i / cv;
     const int qi = (int)(t % q); t /= q;
     const int pi = (int)(t % p); const int ni = (int)(t / p);
+    // window clipped to the image; the first in-bounds tap seeds the arg-max (ATen: `if (val > max || isnan(val))`)
+    const int h0 = pi * stride - pad, w0 = qi * stride - pad;
+    const int r0 = h0 < 0 ? -h0 : 0, s0 = w0 < 0 ? -w0 : 0;
+    const int r1 = (h0 + k > h) ? h - h0 : k, s1 = (w0 + k > w) ? w - w0 : k;
     float best[8]; unsigned char bi[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = 0; }
-    bool first = true;
-    for (int r = 0; r < k; ++r) {
-      const int hi = pi * stride - pad + r;
-      if (hi < 0 || hi >= h) continue;
-      for (int s = 0; s < k; ++s) {
-        const int wi = qi * stride - pad + s;
-        if (wi < 0 || wi >= w) continue;
+    for (int j = 0; j < 8; ++j) { best[j] = -INFINITY; bi[j] = (unsigned char)(r0 * k + s0); }
+    const __nv_bfloat16* xb = x + ((long long)ni * h * w) * c + ci * 8;
+    for (int r = r0; r < r1; ++r) {
+      const __nv_bfloat16* xr = xb + ((long long)(h0 + r) * w + w0) * c;
+      for (int s = s0; s < s1; ++s) {
         float f[8];
-        unpack8p(*reinterpret_cast<const uint4*>(x + (((long long)ni * h + hi) * w + wi) * c + ci * 8), f);
+        unpack8p(*reinterpret_cast<const uint4*>(xr + (long long)s * c), f);
+        const unsigned char id = (unsigned char)(r * k + s);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          // ATen: `if ((val > maxval) || isnan(val))` — the first in-bounds element seeds the index
-          if (first || f[j] > best[j] || f[j] != f[j]) { best[j] = first ? fmaxf(f[j], -INFINITY) : f[j]; bi[j] = (unsigned char)(r * k + s); if (first && f[j] != f[j]) best[j] = f[j]; }
-        }
-        first = false;
+        for (int j = 0; j < 8; ++j)
+          if (f[j] > best[j] || f[j] != f[j]) { best[j] = f[j]; bi[j] = id; }
       }
     }
     uint4 o; __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&o);

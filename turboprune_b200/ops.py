@@ -277,6 +277,23 @@ def empty_cl(n, c, h, w, device):
     return torch.empty((n, c, h, w), dtype=torch.bfloat16, device=device, memory_format=torch.channels_last)
 
 
+def im2col_stem(x, desc, kp):
+    """[N, C<=8, H, W] fp32/bf16 (any strides) -> [N*P*Q, kp] bf16 im2col matrix, conversion fused in."""
+    lib = _cabi.load()
+    n, c, h, w = x.shape
+    if x.dtype not in (torch.float32, torch.bfloat16):
+        x = x.float()
+    out = torch.empty(n * desc.p * desc.q, kp, dtype=torch.bfloat16, device=x.device)
+    sn, sc, sh, sw = x.stride()
+    with torch.cuda.device(x.device):
+        rc = lib.tp_im2col_stem(c_void_p(x.data_ptr()), 0 if x.dtype == torch.float32 else 1, sn, sc, sh, sw, n, c, h, w,
+                                desc.r, desc.s, desc.stride_h, desc.stride_w, desc.pad_h, desc.pad_w, desc.p, desc.q,
+                                c_void_p(out.data_ptr()), kp, _cabi.stream_ptr(x.device))
+    _cabi.check(rc, "tp_im2col_stem")
+    _count()
+    return out
+
+
 def conv_fprop(desc, x_nhwc, wf, bias=None, out=None):
     lib = _cabi.load()
     dev = x_nhwc.device
@@ -349,9 +366,8 @@ class MaskedConv2dFn(torch.autograd.Function):
             if need_dx:
                 raise NotImplementedError("input gradient of a small-channel stem convolution")
             # stem conv: pad channels to 8, explicit im2col, then a plain GEMM
-            x8 = to_nhwc_bf16(x, 8)
             kp = r * s * 8
-            xg = im2col_c8(x8, desc, kp)
+            xg = im2col_stem(x, desc, kp)
             gdesc = _cabi.ConvDesc(n * desc.p * desc.q, 1, 1, kp, cout, 1, 1, 1, 1, 0, 0, 1, 1)
             wf, wd = stage_weights(w32, m32, 8, False)
             y = empty_cl(n, cout, desc.p, desc.q, x.device)
