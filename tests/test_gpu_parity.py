@@ -464,6 +464,44 @@ def test_cuda_graph_step_is_bit_identical_to_eager(dev):
             assert torch.equal(b1, b2), n1
 
 
+def test_arena_direct_gradient_writes_equal_autograd_accumulation(dev):
+    """With a GradArena attached, wgrad / BN backward write dW, db, dgamma, dbeta straight into the slots (no
+    AccumulateGrad kernel); the values must be the ones autograd would have accumulated into a fresh .grad, and a
+    model whose grads were detached (zero_grad(set_to_none=True)) must fall back to the ordinary path."""
+    import copy
+    import refshim
+    from turboprune_b200.grad_exchange import GradArena
+    from turboprune_b200.utils import custom_models as cm, pruning_utils as pu
+    torch.manual_seed(0)
+    base = cm.TorchVisionModel(refshim.make_cfg("resnet18", "cifar10"))
+    torch.manual_seed(1)
+    pu.prune_er_erk(base, 0.3)
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(32, 3, 32, 32, generator=g).to(dev); t = torch.randint(0, 10, (32,), generator=g).to(dev)
+
+    def run(m):
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            torch.nn.functional.cross_entropy(m(x), t).backward()
+
+    plain = copy.deepcopy(base).to(dev).train()
+    run(plain)
+    direct = copy.deepcopy(base).to(dev).train()
+    arena = GradArena(list(direct.parameters()))
+    assert all(hasattr(p, "_tp_grad_slot") for p in direct.parameters())
+    arena.zero()
+    run(direct)
+    for (n, a), (_, b) in zip(plain.named_parameters(), direct.named_parameters()):
+        assert b.grad.data_ptr() == b._tp_grad_slot.data_ptr(), n
+        assert torch.equal(a.grad, b.grad), n
+    # detached grads: the ordinary autograd path must be used and the arena left alone
+    direct.zero_grad(set_to_none=True)
+    before = arena.flat.clone()
+    run(direct)
+    assert torch.equal(arena.flat, before)
+    for (n, a), (_, b) in zip(plain.named_parameters(), direct.named_parameters()):
+        assert torch.equal(a.grad, b.grad), n
+
+
 def test_config4_vgg16_synflow_and_config5_deit_snip(dev):
     """BASELINE.json configs 4 and 5 as parity-test cases: VGG-16 / CIFAR-100 shape with one-shot SynFlow to 95 %,
     DeiT-small with SNIP to 50 % (masked Linear path): pruning hits the target sparsity, masks are {0,1}, a train

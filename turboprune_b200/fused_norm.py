@@ -13,6 +13,7 @@ import torch
 import torch.nn as nn
 
 from . import _cabi, ops
+from .utils.mask_layers import grad_slots
 
 
 def _ptr(t):
@@ -21,8 +22,10 @@ def _ptr(t):
 
 class _BNFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, residual, weight, bias, running_mean, running_var, nbt, momentum, eps, training, relu):
+    def forward(ctx, x, residual, weight, bias, running_mean, running_var, nbt, momentum, eps, training, relu, grad_slots=None):
         lib = _cabi.load()
+        ctx.set_materialize_grads(False)
+        ctx.grad_slots = grad_slots
         n, c, h, w = x.shape
         xn = ops.to_nhwc_bf16(x, c)
         rn = ops.to_nhwc_bf16(residual, c) if residual is not None else None
@@ -57,8 +60,10 @@ class _BNFn(torch.autograd.Function):
         dzn = ops.to_nhwc_bf16(dz, c)
         dy = torch.empty_like(xn)
         dres = torch.empty_like(xn) if ctx.has_res else None
-        dweight = torch.empty(c, dtype=torch.float32, device=dev)
-        dbias = torch.empty(c, dtype=torch.float32, device=dev)
+        ws_, bs_ = ctx.grad_slots if ctx.grad_slots is not None else (None, None)
+        direct = ws_ is not None and bs_ is not None
+        dweight = ws_ if direct else torch.empty(c, dtype=torch.float32, device=dev)
+        dbias = bs_ if direct else torch.empty(c, dtype=torch.float32, device=dev)
         wsb = ops._workspace(lib.tp_bn_workspace_bytes(m, c), dev, "bn")
         with torch.cuda.device(dev):
             rc = lib.tp_bn_backward(_ptr(dzn), _ptr(z), _ptr(xn), m, c, _ptr(weight), _ptr(bias), _ptr(save_mean), _ptr(save_invstd),
@@ -72,7 +77,9 @@ class _BNFn(torch.autograd.Function):
         gr = dres.permute(0, 3, 1, 2) if dres is not None else None
         if gr is not None and gr.dtype != ctx.res_dtype:
             gr = gr.to(ctx.res_dtype)
-        return gx, gr, dweight, dbias, None, None, None, None, None, None, None
+        if direct:
+            dweight = dbias = None
+        return gx, gr, dweight, dbias, None, None, None, None, None, None, None, None
 
 
 class BatchNorm2dB200(nn.BatchNorm2d):
@@ -87,9 +94,10 @@ class BatchNorm2dB200(nn.BatchNorm2d):
                 y = y + residual
             return torch.relu(y) if relu else y
         momentum = 0.1 if self.momentum is None else self.momentum
+        slots = grad_slots(self.weight, self.bias)
         return _BNFn.apply(x, residual, self.weight, self.bias, self.running_mean, self.running_var,
                            self.num_batches_tracked if (training and self.track_running_stats) else None,
-                           momentum, self.eps, training, relu)
+                           momentum, self.eps, training, relu, slots)
 
 
 class _MaxPoolFn(torch.autograd.Function):

@@ -63,6 +63,7 @@ class GradArena:
     def attach(self):
         for p, v in zip(self.params, self.views):
             p.grad = v
+            p._tp_grad_slot = v          # masked layers / fused BN write their gradients straight into the slot
 
     def zero(self):
         self.flat.zero_()
@@ -150,6 +151,7 @@ class P2PGradReducer:
         for bk in self._bk:
             for p, v in zip(bk["params"], bk["views"]):
                 p.grad = v
+                p._tp_grad_slot = v
 
     def zero(self):
         for bk in self._bk:

@@ -321,11 +321,13 @@ def conv_dgrad(desc, dy_nhwc, wd, addend=None):
     return dx
 
 
-def conv_wgrad(desc, x_nhwc, dy_nhwc, mask4d, cin_real, want_db=False):
+def conv_wgrad(desc, x_nhwc, dy_nhwc, mask4d, cin_real, want_db=False, dw_out=None, db_out=None):
+    """``dw_out`` / ``db_out``: write the gradients straight into these (contiguous fp32) buffers — used with the
+    persistent gradient arena so no separate accumulate kernel runs."""
     lib = _cabi.load()
     dev = x_nhwc.device
-    dw = torch.empty(desc.cout, cin_real, desc.r, desc.s, dtype=torch.float32, device=dev)
-    db = torch.empty(desc.cout, dtype=torch.float32, device=dev) if want_db else None
+    dw = dw_out if dw_out is not None else torch.empty(desc.cout, cin_real, desc.r, desc.s, dtype=torch.float32, device=dev)
+    db = (db_out if db_out is not None else torch.empty(desc.cout, dtype=torch.float32, device=dev)) if want_db else None
     nbytes = lib.tp_conv_workspace_bytes(ctypes.byref(desc), 2)
     wsb = _workspace(nbytes, dev, "wgrad")
     with torch.cuda.device(dev), _Timed("wgrad", desc):
@@ -348,10 +350,13 @@ class MaskedConv2dFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, weight, mask, bias, stride, padding, want_skip=False):
+    def forward(ctx, x, weight, mask, bias, stride, padding, want_skip=False, grad_slots=None):
         _require_cuda(x, weight, mask)
         ctx.set_materialize_grads(False)
         ctx.want_skip = want_skip
+        # (w_slot, b_slot): persistent arena slots; when given, backward writes dW / db there and returns None for
+        # them (no AccumulateGrad add kernel; the slot IS param.grad)
+        ctx.grad_slots = grad_slots
         cout, cin, r, s = weight.shape
         n, _, h, w = x.shape
         need_dx = ctx.needs_input_grad[0]
@@ -397,7 +402,7 @@ class MaskedConv2dFn(torch.autograd.Function):
     def backward(ctx, dy, dskip=None):
         desc = ctx.desc
         if dy is None:          # only the skip output was used downstream
-            return dskip, None, None, None, None, None, None
+            return dskip, None, None, None, None, None, None, None
         cout = desc.cout
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         need_db = ctx.has_bias and ctx.needs_input_grad[3]
@@ -434,22 +439,30 @@ class MaskedConv2dFn(torch.autograd.Function):
                     dw = dwp[:cout].contiguous()
                     db = dbp[:cout].contiguous() if dbp is not None else None
                 else:
-                    dw, db = conv_wgrad(desc, xn, dyn, m32, desc.cin, need_db)
+                    ws_, bs_ = ctx.grad_slots if ctx.grad_slots is not None else (None, None)
+                    direct_w = ws_ is not None and ws_.is_contiguous() and ws_.numel() == m32.numel()
+                    direct_b = need_db and bs_ is not None
+                    dw, db = conv_wgrad(desc, xn, dyn, m32, desc.cin, need_db, dw_out=ws_ if direct_w else None,
+                                        db_out=bs_ if direct_b else None)
+                    if direct_w:
+                        dw = None
+                    if direct_b:
+                        db = None
         if need_db and db is None:
             db = dy.float().sum(dim=(0, 2, 3))
         if dskip is not None and dx is None and need_dx is False:
             dx = None
-        return dx, dw, None, db, None, None, None
+        return dx, dw, None, db, None, None, None, None
 
 
-def masked_conv2d(x, weight, mask, bias=None, stride=(1, 1), padding=(0, 0), want_skip=False):
-    return MaskedConv2dFn.apply(x, weight, mask, bias, tuple(stride), tuple(padding), want_skip)
+def masked_conv2d(x, weight, mask, bias=None, stride=(1, 1), padding=(0, 0), want_skip=False, grad_slots=None):
+    return MaskedConv2dFn.apply(x, weight, mask, bias, tuple(stride), tuple(padding), want_skip, grad_slots)
 
 
-def masked_linear(x, weight2d, mask2d, bias=None):
+def masked_linear(x, weight2d, mask2d, bias=None, grad_slots=None):
     """y = x @ (mask*w)^T + b for x [..., in]; runs as a 1x1 convolution over a [rows,1,1,in] image."""
     shp = x.shape
     x2 = x.reshape(-1, shp[-1])
     y = MaskedConv2dFn.apply(x2.view(x2.shape[0], x2.shape[1], 1, 1), weight2d.view(*weight2d.shape, 1, 1),
-                             mask2d.view(*mask2d.shape, 1, 1), bias, (1, 1), (0, 0), False)
+                             mask2d.view(*mask2d.shape, 1, 1), bias, (1, 1), (0, 0), False, grad_slots)
     return y.reshape(*shp[:-1], weight2d.shape[0])

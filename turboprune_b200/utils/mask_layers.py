@@ -20,6 +20,29 @@ def _pair(v):
     return (v, v) if isinstance(v, int) else tuple(v)
 
 
+def _live_slot(p):
+    # the slot only counts while it still IS p.grad (zero_grad(set_to_none=True) or a user assignment detaches it)
+    if p is None:
+        return None
+    slot = getattr(p, "_tp_grad_slot", None)
+    g = p.grad
+    if slot is None or g is None or g.data_ptr() != slot.data_ptr():
+        return None
+    return slot
+
+
+def grad_slots(weight, bias):
+    ws = _live_slot(weight)
+    if ws is None:
+        return None
+    return (ws, _live_slot(bias))
+
+
+def _slots(layer):
+    """Persistent gradient slots attached by GradArena / P2PGradReducer (None when training with plain .grad)."""
+    return grad_slots(layer.weight, layer.bias)
+
+
 class _MaskMixin:
     def _init_mask(self):
         self.register_buffer("mask", torch.ones_like(self.weight))
@@ -45,7 +68,7 @@ class ConvMask(_MaskMixin, nn.Conv2d):
         self._check_plain()
         if isinstance(self.padding, str):
             raise NotImplementedError("string padding modes")
-        return ops.masked_conv2d(x, self.weight, self.mask, self.bias, _pair(self.stride), _pair(self.padding), want_skip)
+        return ops.masked_conv2d(x, self.weight, self.mask, self.bias, _pair(self.stride), _pair(self.padding), want_skip, _slots(self))
 
 
 class LinearMask(_MaskMixin, nn.Linear):
@@ -54,7 +77,7 @@ class LinearMask(_MaskMixin, nn.Linear):
         self._init_mask()
 
     def forward(self, x):
-        return ops.masked_linear(x, self.weight, self.mask, self.bias)
+        return ops.masked_linear(x, self.weight, self.mask, self.bias, _slots(self))
 
 
 class Conv1dMask(_MaskMixin, nn.Conv1d):
@@ -66,7 +89,7 @@ class Conv1dMask(_MaskMixin, nn.Conv1d):
 
     def forward(self, x):
         w = self.weight
-        return ops.masked_linear(x, w.view(w.shape[0], w.shape[1]), self.mask.view(w.shape[0], w.shape[1]), self.bias)
+        return ops.masked_linear(x, w.view(w.shape[0], w.shape[1]), self.mask.view(w.shape[0], w.shape[1]), self.bias, _slots(self))
 
 
 MASKED_LAYER_TYPES = (ConvMask, Conv1dMask, LinearMask)
