@@ -280,6 +280,30 @@ def test_conv_full_size_linearity_property(dev):
     assert float(ops.masked_conv2d(x1, w, torch.zeros_like(m)).abs().max()) == 0.0
 
 
+@pytest.mark.parametrize("case", [(5, 64, 64, 3, 1, 1, 14), (3, 128, 512, 1, 1, 0, 20), (4, 64, 96, 3, 2, 1, 16), (2, 256, 1000, 1, 1, 0, 9)])
+def test_cta_pair_kernel_bit_identical_to_single_cta(dev, case, monkeypatch):
+    """The cta_group::2 pair kernel (two 128-pixel tiles per UMMA, each CTA loads half of the weight tile) computes
+    the same dot products in the same K order as the single-CTA kernel: fprop and dgrad outputs are bit-identical,
+    including an odd number of M tiles (the pair's second tile is empty) and N tiles that are not full."""
+    from turboprune_b200 import ops
+    b, cin, cout, k, s, p, hw = case
+    g = torch.Generator(device=dev).manual_seed(sum(case))
+    x = torch.randn(b, cin, hw, hw, device=dev, generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = torch.randn(cout, cin, k, k, device=dev, generator=g) / (cin * k * k) ** 0.5
+    m = (torch.rand(cout, cin, k, k, device=dev, generator=g) < 0.3).float()
+    outs = {}
+    for cl in ("1", "2"):
+        monkeypatch.setenv("TP_IGEMM_CLUSTER", cl)
+        xx = x.clone().requires_grad_(True)
+        y = ops.masked_conv2d(xx, w, m, stride=(s, s), padding=(p, p))
+        gy = torch.Generator(device=dev).manual_seed(7)
+        dy = torch.randn(y.shape, device=dev, generator=gy).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        y.backward(dy)
+        outs[cl] = (y.detach().clone(), xx.grad.detach().clone())
+    assert torch.equal(outs["1"][0], outs["2"][0])
+    assert torch.equal(outs["1"][1], outs["2"][1])
+
+
 # ---------------------------------------------------------------- optimizer / train step ---------------------
 def test_fused_sgd_matches_oracle_and_torch(dev):
     from turboprune_b200.optim import FusedSGD

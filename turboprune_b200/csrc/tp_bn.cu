@@ -10,6 +10,8 @@
 //   backward : k_bn_bwd_reduce: g = dz*(z>0); sum g, sum g*xhat                 (2-3 reads)
 //              -> k_bn_finalize_bwd -> k_bn_bwd_apply: dy = w*invstd*(g - mean(g) - xhat*mean(g*xhat))
 //                 (+ dres = g)                                                  (2-3 reads, 1-2 writes)
+//              With a residual the reduce pass already writes g (= dres), and the apply pass reads g and y
+//              only: 3r+1w + 2r+1w instead of 3r + 3r+2w — one pass less over the widest activations.
 //
 // Layout: activations are [M pixels][C channels] bf16, C % 8 == 0; a thread owns one 16-byte vector
 // (8 channels) and walks over pixels, so per-channel constants live in registers.
@@ -230,12 +232,12 @@ __global__ void __launch_bounds__(kBnThreads) k_bn_apply(const __nv_bfloat16* __
 // partial[b][0][c] = sum g, partial[b][1][c] = sum g * xhat, with g = dz * (z > 0) when RELU
 // RELU: 0 = no activation, 1 = gate from the saved output (z > 0), 2 = gate recomputed from y (same fp32
 // expression as the forward apply: no need to read z at all — one activation pass less)
-template <int RELU>
+template <int RELU, bool WRITE_G>
 __global__ void __launch_bounds__(kBnThreads) k_bn_bwd_reduce(const __nv_bfloat16* __restrict__ dz, const __nv_bfloat16* __restrict__ z,
                                                               const __nv_bfloat16* __restrict__ y, long long M, int C,
                                                               const float* __restrict__ mean, const float* __restrict__ invstd,
                                                               const float* __restrict__ weight, const float* __restrict__ bias,
-                                                              float* __restrict__ partial) {
+                                                              float* __restrict__ partial, __nv_bfloat16* __restrict__ gout) {
   __shared__ float s_acc[kBnThreads][17];
   const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
   const int cvec = blockIdx.y * TX + tx;
@@ -270,8 +272,10 @@ __global__ void __launch_bounds__(kBnThreads) k_bn_bwd_reduce(const __nv_bfloat1
         for (int i = 0; i < 8; ++i) {
           const bool open = RELU == 0 ? true : (RELU == 1 ? (zz[i] > 0.f) : (fmaf(yy[i], sc[i], sf[i]) > 0.f));
           const float g = open ? d[i] : 0.f;
+          if (WRITE_G) d[i] = g;
           a1[i] += g; a2[i] = fmaf(g, (yy[i] - mu[i]) * is[i], a2[i]);
         }
+        if (WRITE_G) stg16(gout + (size_t)(p + u * stride) * C + (size_t)cvec * 8, pack8(d));
       }
     }
     for (; p < M; p += stride) {
@@ -282,8 +286,10 @@ __global__ void __launch_bounds__(kBnThreads) k_bn_bwd_reduce(const __nv_bfloat1
       for (int i = 0; i < 8; ++i) {
         const bool open = RELU == 0 ? true : (RELU == 1 ? (zz[i] > 0.f) : (fmaf(yy[i], sc[i], sf[i]) > 0.f));
         const float g = open ? d[i] : 0.f;
+        if (WRITE_G) d[i] = g;
         a1[i] += g; a2[i] = fmaf(g, (yy[i] - mu[i]) * is[i], a2[i]);
       }
+      if (WRITE_G) stg16(gout + off, pack8(d));
     }
   }
   const int tid = ty * TX + tx;
@@ -444,13 +450,18 @@ int tp_bn_backward(const void* dz, const void* z, const void* y, int64_t M, int 
   dim3 block(g.tx, g.ty), grid(g.grid_x, g.ctiles);
   const __nv_bfloat16 *d = (const __nv_bfloat16*)dz, *zz = (const __nv_bfloat16*)z, *yy = (const __nv_bfloat16*)y;
   const float *mu = (const float*)save_mean, *is = (const float*)save_invstd, *wp = (const float*)weight, *bp = (const float*)bias;
-  if (relu == 1) k_bn_bwd_reduce<1><<<grid, block, 0, st>>>(d, zz, yy, M, C, mu, is, wp, bp, partial);
-  else if (relu == 2) k_bn_bwd_reduce<2><<<grid, block, 0, st>>>(d, zz, yy, M, C, mu, is, wp, bp, partial);
-  else k_bn_bwd_reduce<0><<<grid, block, 0, st>>>(d, zz, yy, M, C, mu, is, wp, bp, partial);
+  __nv_bfloat16* o = (__nv_bfloat16*)dy; __nv_bfloat16* r = (__nv_bfloat16*)dres;
+  // with an activation AND a residual the gated gradient g is the residual's gradient: write it in the reduce pass
+  const bool g_first = relu != 0 && r != nullptr;
+  if (relu == 1 && g_first) k_bn_bwd_reduce<1, true><<<grid, block, 0, st>>>(d, zz, yy, M, C, mu, is, wp, bp, partial, r);
+  else if (relu == 2 && g_first) k_bn_bwd_reduce<2, true><<<grid, block, 0, st>>>(d, zz, yy, M, C, mu, is, wp, bp, partial, r);
+  else if (relu == 1) k_bn_bwd_reduce<1, false><<<grid, block, 0, st>>>(d, zz, yy, M, C, mu, is, wp, bp, partial, nullptr);
+  else if (relu == 2) k_bn_bwd_reduce<2, false><<<grid, block, 0, st>>>(d, zz, yy, M, C, mu, is, wp, bp, partial, nullptr);
+  else k_bn_bwd_reduce<0, false><<<grid, block, 0, st>>>(d, zz, yy, M, C, mu, is, wp, bp, partial, nullptr);
   k_bn_finalize_bwd<<<(C + kFinC - 1) / kFinC, dim3(kFinC, kFinP), 0, st>>>(partial, g.grid_x, M, C, wp, bp, mu, is,
                                                                           (float*)dweight, (float*)dbias, coef);
-  __nv_bfloat16* o = (__nv_bfloat16*)dy; __nv_bfloat16* r = (__nv_bfloat16*)dres;
-  if (relu == 1 && r) k_bn_bwd_apply<1, true><<<grid, block, 0, st>>>(d, zz, yy, M, C, coef, o, r);
+  if (g_first) k_bn_bwd_apply<0, false><<<grid, block, 0, st>>>(r, zz, yy, M, C, coef, o, nullptr);     // g is final: no gate, no second write
+  else if (relu == 1 && r) k_bn_bwd_apply<1, true><<<grid, block, 0, st>>>(d, zz, yy, M, C, coef, o, r);
   else if (relu == 1) k_bn_bwd_apply<1, false><<<grid, block, 0, st>>>(d, zz, yy, M, C, coef, o, r);
   else if (relu == 2 && r) k_bn_bwd_apply<2, true><<<grid, block, 0, st>>>(d, zz, yy, M, C, coef, o, r);
   else if (relu == 2) k_bn_bwd_apply<2, false><<<grid, block, 0, st>>>(d, zz, yy, M, C, coef, o, r);

@@ -32,6 +32,11 @@ constexpr int kThreads = 192;          // wgrad kernel: TMA warp, MMA warp, 4 ep
 constexpr int kFwdThreads = 320;       // fwd kernel: TMA warp, MMA warp, 8 epilogue warps (two per TMEM lane quarter)
 constexpr int kMaxTaps = 64;
 
+// smem pipeline depth of the fwd kernel: stage = A tile (16 KB) + this CTA's share of the weight tile
+__host__ __device__ constexpr int fwd_stages(int block_n, int cl) {
+  return cl == 2 ? (block_n == 256 ? 6 : 8) : (block_n == 256 ? 4 : (block_n == 128 ? 6 : 8));
+}
+
 struct TapEntry { uint16_t off_w, off_h; int32_t kofs; };
 
 struct FwdParams {
@@ -69,31 +74,24 @@ __device__ __forceinline__ void decompose_pixel(int m, int P, int Q, int& n, int
   q = m % Q; int t = m / Q; p = t % P; n = t / P;
 }
 
-// 32 x 64 addend sub-tile -> registers (linear output order is a precondition, so addend row = output row)
-__device__ __forceinline__ void load_addend(uint4 (&a)[8], const FwdParams& p, int m_t, int quarter, int r_in, int c16, int n0) {
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const long long grow = (long long)m_t * kBlockM + quarter * 32 + i * 4 + r_in;
-    a[i] = make_uint4(0u, 0u, 0u, 0u);
-    if (grow < p.M && n0 + c16 * 8 + 8 <= p.N)
-      a[i] = *reinterpret_cast<const uint4*>(p.addend + grow * p.ldc + n0 + c16 * 8);
-  }
-}
-
 // ============================================================================================
-// CL = thread-block cluster size along M (1 or 2).  With CL = 2 the two CTAs of a cluster work on neighbouring
-// M tiles of the SAME N tile: each loads its own A tile and HALF of the weight tile, multicast into both CTAs'
-// shared memory, so the L2 -> SM operand traffic per MMA drops from 48 KB to 32 KB per K block (the compute-bound
-// layers were pinned at the ~12 TB/s L2 delivery rate: 85 FLOP/B * 12 TB/s = 1.0 PFLOP/s).
+// CL = 1: one CTA per 128 x BLOCK_N tile (tcgen05 cta_group::1).
+// CL = 2: a CTA PAIR (cluster of 2, tcgen05 cta_group::2) works on two neighbouring M tiles of the SAME N tile as one
+// 256 x BLOCK_N UMMA: each CTA loads its own 128-pixel A tile and only HALF of the weight tile (BLOCK_N/2 rows), the
+// leader CTA's MMA thread issues the pair MMAs (they read both CTAs' shared memory), each CTA's TMEM receives its
+// own 128 rows.  L2 -> SM operand bytes per K block drop from 2 x 48 KB to 2 x 32 KB and the 32 KB stages leave room
+// for 6 of them in flight: the ncu captures showed the mainloop pinned at ~10 TB/s of L2 -> SM traffic with every
+// role waiting (profiles/r01_notes.md); TMA multicast does not reduce L2 reads at cluster size 2, operand halving does.
 template <int BLOCK_N, int CL>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ CUtensorMap tmC, const __grid_constant__ FwdParams p) {
   constexpr int kABytes = kBlockM * kBlockK * 2;           // 16 KB
-  constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+  constexpr int kBRows = BLOCK_N / CL;                     // weight rows THIS CTA loads
+  constexpr int kBBytes = kBRows * kBlockK * 2;
   constexpr int kStageBytes = kABytes + kBBytes;
-  constexpr int kStages = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
-  constexpr int kAccStages = 2;
+  constexpr int kStages = fwd_stages(BLOCK_N, CL);
+  constexpr int kAccStages = BLOCK_N == 256 ? 2 : 4;      // TMEM accumulator ring (512 columns at most)
   constexpr uint32_t kTmemCols = (kAccStages * BLOCK_N <= 32) ? 32 : (kAccStages * BLOCK_N <= 64) ? 64 :
                                  (kAccStages * BLOCK_N <= 128) ? 128 : (kAccStages * BLOCK_N <= 256) ? 256 : 512;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -120,11 +118,17 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmC);
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], CL); }
-    for (int i = 0; i < kAccStages; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8); }
+    // full / tempty are only used in the leader CTA of a pair: full gets ONE arrive (the leader's expect_tx for both
+    // CTAs' bytes), tempty gets one arrive per epilogue warp of both CTAs; empty / tfull exist in both CTAs and get
+    // one (multicast) commit arrival from the leader's MMA thread
+    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < kAccStages; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8 * CL); }
     fence_mbar_init();
   }
-  if (warp == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
+  if (warp == 1) {
+    if (CL == 1) { tmem_alloc(tmem_slot, kTmemCols); tmem_relinquish(); }
+    else { tmem_alloc_pair(tmem_slot, kTmemCols); tmem_relinquish_pair(); }
+  }
   tc_fence_before();
   if (CL > 1) cluster_sync_all(); else __syncthreads();      // peers' barriers are initialised before anyone signals them
   tc_fence_after();
@@ -147,18 +151,26 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           const TapEntry te = p.taps[tap];
           for (int cc = 0; cc < p.cchunks; ++cc) {
             mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-            mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
             uint8_t* sA = smem + stage * kStageBytes;
             uint8_t* sB = sA + kABytes;
-            if (p.a_mode == 1)
-              tma_load_im2col_4d(sA, &tmA, &full_bar[stage], cc * kBlockK, cw, ch, cn, te.off_w, te.off_h);
-            else
-              tma_load_2d(sA, &tmA, &full_bar[stage], te.kofs + cc * kBlockK, m0);
-            if (CL == 1)
+            if (CL == 1) {
+              mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+              if (p.a_mode == 1)
+                tma_load_im2col_4d(sA, &tmA, &full_bar[stage], cc * kBlockK, cw, ch, cn, te.off_w, te.off_h);
+              else
+                tma_load_2d(sA, &tmA, &full_bar[stage], te.kofs + cc * kBlockK, m0);
               tma_load_2d(sB, &tmB, &full_bar[stage], te.kofs + cc * kBlockK, n_t * BLOCK_N);
-            else      // my 1/CL slice of the weight tile, delivered to every CTA of the cluster
-              tma_load_2d_mc(sB + cta_rank * (kBBytes / CL), &tmB, &full_bar[stage], te.kofs + cc * kBlockK,
-                             n_t * BLOCK_N + cta_rank * (BLOCK_N / CL), kMask);
+            } else {
+              // pair: my A tile and my half of the weight tile land in MY shared memory, the bytes are credited to the
+              // LEADER's full barrier (which expects both CTAs' stage bytes)
+              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], kStageBytes * CL);
+              const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+              if (p.a_mode == 1)
+                tma_load_im2col_4d_pair(sA, &tmA, lead_full, cc * kBlockK, cw, ch, cn, te.off_w, te.off_h);
+              else
+                tma_load_2d_pair(sA, &tmA, lead_full, te.kofs + cc * kBlockK, m0);
+              tma_load_2d_pair(sB, &tmB, lead_full, te.kofs + cc * kBlockK, n_t * BLOCK_N + cta_rank * kBRows);
+            }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
@@ -166,8 +178,8 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ------------------------------ MMA issuer ------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc_bf16(kBlockM * CL, BLOCK_N, 0, 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = cl_id; tile < total_tiles; tile += n_cl) {
@@ -184,14 +196,15 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int k = 0; k < kBlockK / 16; ++k) {
             // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in 16-B units
-            umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0);
+            if (CL == 1) umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0);
+            else umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0);
           }
-          // frees this smem stage when the MMAs have read it; with a cluster the stage is also written by the
-          // peers' multicasts, so every CTA's producer must see all CL consumers release it
-          if (CL == 1) umma_commit(&empty_bar[stage]); else umma_commit_mc(&empty_bar[stage], kMask);
+          // frees this smem stage (in both CTAs of a pair) when the MMAs have read it
+          if (CL == 1) umma_commit(&empty_bar[stage]); else umma_commit_pair(&empty_bar[stage], kMask);
           if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);         // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (of both CTAs of a pair)
+        if (CL == 1) umma_commit(&tfull_bar[acc]); else umma_commit_pair(&tfull_bar[acc], kMask);
         if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -202,14 +215,13 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;         // which half of the 64-column chunks this warp drains
     int acc = 0; uint32_t acc_phase = 0;
-    constexpr int stg_sel = 0;
     for (int tile = cl_id; tile < total_tiles; tile += n_cl) {
       const int m_g = tile / n_tiles, n_t = tile - m_g * n_tiles;
       const int m_t = m_g * CL + cta_rank;
       const int row = m_t * kBlockM + quarter * 32 + lane;
       const bool row_ok = row < p.M;
       long long opix = 0;
-      if (row_ok) {
+      if (row_ok && !p.tma_store) {       // strided output mapping (dgrad parity classes): one division chain per tile
         int n, pp, qq; decompose_pixel(row, p.P_it, p.Q_it, n, pp, qq);
         opix = (long long)n * p.out_img_pix + (long long)(pp * p.osh + p.oah) * p.out_row_pix + (qq * p.osw + p.oaw);
       }
@@ -218,83 +230,94 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
       if (p.tma_store) {
-        // TMEM -> registers -> 128B-swizzled smem sub-tile (32 rows x 64 cols) -> TMA store: every
-        // output line leaves the SM as full 128-byte rows instead of 32 scattered 16-byte pieces.
-        uint8_t* my_stg = stg_base + (warp - 2) * kStgBytes;
+        // Linear output: TMEM -> registers -> 128B-swizzled smem sub-tile (32 rows x 64 cols) -> coalesced global
+        // stores, so every output line leaves the SM as full 128-byte rows instead of 32 scattered 16-byte pieces.
+        // Everything that does not depend on the column chunk is hoisted (row pointers, validity, swizzled
+        // staging offsets) and the staging buffer is addressed through the shared window (st/ld.shared, not
+        // generic): the ncu source view of the first version had this loop at 2.3 us per 128x256 tile — longer
+        // than the tile's MMAs (1.1 us) — with its stalls on generic LD/ST and re-loaded kernel parameters.
+        const uint32_t buf = smem_u32(stg_base + (warp - 2) * kStgBytes);
+        const int r_in = lane >> 3, c16 = lane & 7;
+        const long long wrow0 = (long long)m_t * kBlockM + quarter * 32;        // first row of this warp's 32
+        const int rows_left = (int)(p.M - wrow0 < 32 ? (p.M - wrow0 < 0 ? 0 : p.M - wrow0) : 32);
+        const long long ldc = p.ldc;
+        const int N = p.N;
+        __nv_bfloat16* gout = p.out + (wrow0 + r_in) * ldc + c16 * 8;           // + i*4*ldc + n0
+        const __nv_bfloat16* gadd = p.addend ? p.addend + (wrow0 + r_in) * ldc + c16 * 8 : nullptr;
+        const float* bias = p.bias;
+        const uint32_t wr_base = buf + lane * 128;                              // my row (TMEM lane) in the staging tile
+        const uint32_t wr_sw = (uint32_t)(lane & 7);
+        const uint32_t rd_even = buf + r_in * 128 + ((uint32_t)(c16 ^ r_in) << 4);          // rows r_in + 8j
+        const uint32_t rd_odd = buf + (r_in + 4) * 128 + ((uint32_t)(c16 ^ (r_in + 4)) << 4);  // rows r_in + 4 + 8j
         uint4 a_pref[8];
 #pragma unroll 1
         for (int c = half * 64; c < BLOCK_N; c += 128) {
           const int n0 = n_t * BLOCK_N + c;
-          if (n0 >= p.N) break;
-          uint8_t* buf = my_stg + stg_sel * kStgBytes;
-          if (p.addend) {
+          if (n0 >= N) break;
+          const bool col_ok = n0 + c16 * 8 + 8 <= N;
+          // both 32-column halves of the chunk are requested before the one wait
+          uint32_t v[64];
+          tmem_ld_32x32(t_base + (uint32_t)c, v);
+          tmem_ld_32x32(t_base + (uint32_t)(c + 32), v + 32);
+          if (gadd) {
             // addend sub-tile of THIS chunk was prefetched into registers one chunk earlier (coalesced: 8 lanes
             // cover one 128-byte row, 4 rows per instruction); stage it, then prefetch the next chunk's
-            const int r_in = lane >> 3, c16 = lane & 7;
-            if (c == half * 64) load_addend(a_pref, p, m_t, quarter, r_in, c16, n0);
+            if (c == half * 64) {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int row_l = i * 4 + r_in;
-              *(uint4*)(buf + row_l * 128 + ((c16 ^ (row_l & 7)) << 4)) = a_pref[i];
-            }
-            if (c + 128 < BLOCK_N && n0 + 128 < p.N) load_addend(a_pref, p, m_t, quarter, r_in, c16, n0 + 128);
-            __syncwarp();
-          }
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            uint32_t v[32];
-            tmem_ld_32x32(t_base + (uint32_t)(c + 32 * h), v);
-            tmem_ld_wait();
-            float f[32];
-#pragma unroll
-            for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-            if (p.bias) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) if (n0 + 32 * h + j < p.N) f[j] += p.bias[n0 + 32 * h + j];
-            }
-            if (p.addend) {
-              // fused skip-gradient accumulation: the addend sub-tile was staged (coalesced) in `buf`; each
-              // thread reads its own row back before overwriting it with the result
-#pragma unroll
-              for (int j = 0; j < 32; j += 8) {
-                const int chunk16 = h * 4 + (j >> 3);
-                const uint4 a = *(const uint4*)(buf + lane * 128 + ((chunk16 ^ (lane & 7)) << 4));
-                const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
-#pragma unroll
-                for (int q = 0; q < 4; ++q) { const float2 t2 = __bfloat1622float2(ah[q]); f[j + 2 * q] += t2.x; f[j + 2 * q + 1] += t2.y; }
+              for (int i = 0; i < 8; ++i) {
+                a_pref[i] = make_uint4(0u, 0u, 0u, 0u);
+                if (i * 4 + r_in < rows_left && col_ok) a_pref[i] = *reinterpret_cast<const uint4*>(gadd + (long long)(i * 4) * ldc + n0);
               }
             }
 #pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(f[j], f[j + 1]);
-              __nv_bfloat162 h1 = __floats2bfloat162_rn(f[j + 2], f[j + 3]);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(f[j + 4], f[j + 5]);
-              __nv_bfloat162 h3 = __floats2bfloat162_rn(f[j + 6], f[j + 7]);
-              uint4 pk;
-              pk.x = *(uint32_t*)&h0; pk.y = *(uint32_t*)&h1; pk.z = *(uint32_t*)&h2; pk.w = *(uint32_t*)&h3;
-              const int chunk16 = h * 4 + (j >> 3);                    // 16-byte chunk index within the 128-B row
-              *(uint4*)(buf + lane * 128 + ((chunk16 ^ (lane & 7)) << 4)) = pk;
+            for (int i = 0; i < 8; ++i) sts128(((i & 1) ? rd_odd : rd_even) + (uint32_t)((i >> 1) * 1024), a_pref[i]);
+            if (c + 128 < BLOCK_N && n0 + 128 < N) {
+              const bool col_ok2 = n0 + 128 + c16 * 8 + 8 <= N;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                a_pref[i] = make_uint4(0u, 0u, 0u, 0u);
+                if (i * 4 + r_in < rows_left && col_ok2) a_pref[i] = *reinterpret_cast<const uint4*>(gadd + (long long)(i * 4) * ldc + n0 + 128);
+              }
             }
+            __syncwarp();
+          }
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 64; j += 8) {
+            float f[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) f[q] = __uint_as_float(v[j + q]);
+            if (bias) {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) if (n0 + j + q < N) f[q] += bias[n0 + j + q];
+            }
+            const uint32_t waddr = wr_base + (((uint32_t)(j >> 3) ^ wr_sw) << 4);   // 16-byte chunk j/8 of my row, swizzled
+            if (gadd) {
+              // fused skip-gradient accumulation: each thread reads its own row of the staged addend back before
+              // overwriting it with the result
+              const uint4 a = lds128(waddr);
+              const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&a);
+#pragma unroll
+              for (int q = 0; q < 4; ++q) { const float2 t2 = __bfloat1622float2(ah[q]); f[2 * q] += t2.x; f[2 * q + 1] += t2.y; }
+            }
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(f[0], f[1]);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(f[2], f[3]);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(f[4], f[5]);
+            __nv_bfloat162 h3 = __floats2bfloat162_rn(f[6], f[7]);
+            uint4 pk;
+            pk.x = *(uint32_t*)&h0; pk.y = *(uint32_t*)&h1; pk.z = *(uint32_t*)&h2; pk.w = *(uint32_t*)&h3;
+            sts128(waddr, pk);
           }
           __syncwarp();
           // smem -> global, coalesced: 8 lanes write one full 128-byte output row, 4 rows per instruction.
           // Plain stores are fire-and-forget, so the staging buffer is free again after this read-back
           // (a TMA store here made every chunk wait ~2 us for the previous store to drain: 9 us per tile).
-          {
-            const int r_in = lane >> 3, c16 = lane & 7;
-            uint4 o[8];
+          uint4 o[8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int row_l = i * 4 + r_in;
-              o[i] = *(const uint4*)(buf + row_l * 128 + ((c16 ^ (row_l & 7)) << 4));
-            }
+          for (int i = 0; i < 8; ++i) o[i] = lds128(((i & 1) ? rd_odd : rd_even) + (uint32_t)((i >> 1) * 1024));
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const long long grow = (long long)m_t * kBlockM + quarter * 32 + i * 4 + r_in;
-              if (grow < p.M && n0 + c16 * 8 + 8 <= p.N)
-                *reinterpret_cast<uint4*>(p.out + grow * p.ldc + n0 + c16 * 8) = o[i];
-            }
-          }
+          for (int i = 0; i < 8; ++i)
+            if (i * 4 + r_in < rows_left && col_ok) *reinterpret_cast<uint4*>(gout + (long long)(i * 4) * ldc + n0) = o[i];
           __syncwarp();
         }
       } else {
@@ -336,13 +359,19 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (CL == 1) mbar_arrive(&tempty_bar[acc]);
+        else mbar_arrive_cluster(mapa_u32(smem_u32(&tempty_bar[acc]), 0));     // the leader's MMA thread owns the accumulators
+      }
       if (++acc == kAccStages) { acc = 0; acc_phase ^= 1; }
     }
   }
   tc_fence_before();
-  if (CL > 1) cluster_sync_all(); else __syncthreads();      // nobody exits while a peer may still multicast into it
-  if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
+  if (CL > 1) cluster_sync_all(); else __syncthreads();      // nobody exits while the pair may still touch its smem / TMEM
+  if (warp == 1) {
+    tc_fence_after();
+    if (CL == 1) tmem_dealloc(tmem_base, kTmemCols); else tmem_dealloc_pair(tmem_base, kTmemCols);
+  }
 }
 
 // ============================================================================================
@@ -494,55 +523,46 @@ k_igemm_wgrad(const __grid_constant__ CUtensorMap tmA /* dY [Kpix, Cout] */,
   if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, kTmemCols); }
 }
 
-// dW[co][ci][tap] (fp32 OIHW) = mask * sum_split partial   — fixed summation order.
-// One CTA per output channel; K index kk = tap*cin_p + ci is the column of the partial tiles.
+// dW[co][ci][tap] (fp32 OIHW) = mask * sum_split partial   — fixed summation order (deterministic, no atomics).
+// Grid (Cout, K chunks): a CTA owns KT = 256 / sl consecutive K columns (kk = tap*cin_p + ci) of one output channel;
+// its 256 threads are KT k-lanes x `sl` split-lanes.  Split lane j folds splits j, j+sl, ... with eight independent
+// loads in flight, the lanes are then combined in lane order.  (The first version looped over the K chunks inside one
+// CTA per channel: 18 dependent rounds of L2/DRAM latency for a 3x3x64 layer — 50-80 us for 150 KB of output.)
 __global__ void __launch_bounds__(256) k_wgrad_finalize(const float* __restrict__ partial, const float* __restrict__ mask,
                                                         float* __restrict__ dw, int cout, int cin_real, int cin_p, int rs,
                                                         int nb, int m_tiles, int n_tiles, int splits, int sl) {
-  // One CTA per output channel.  256 threads = KT k-lanes x `sl` split-lanes (sl = power of two <= min(splits, 8)):
-  // split lane j folds splits j, j+sl, ... with four independent loads in flight, then the lanes are combined in
-  // lane order — a fixed summation order (deterministic), but no longer one long serial chain of L2 round trips
-  // per thread (the skinny layers run with ~300 splits; this kernel was 17 % of the B=64 step).
-  extern __shared__ float s_mem[];       // [sl][KT] lane sums, then [rs * cin_p] row when rs > 1
+  __shared__ float s_lane[256];
   const int co = blockIdx.x;
   const int m_t = co / kBlockM, r = co % kBlockM;
   const int ktot = rs * cin_p;
   const int ncols = nb * 64;
   const int KT = 256 / sl;
   const int kl = threadIdx.x % KT, sj = threadIdx.x / KT;
-  float* s_lane = s_mem;                 // sl * KT floats = 256
-  float* s_row = s_mem + 256;
-  const long long obase = (long long)co * cin_real * rs;
+  const int kk = blockIdx.y * KT + kl;
   const long long sstride = (long long)kBlockM * ncols;          // floats between consecutive splits of a tile
-  for (int k0 = 0; k0 < ktot; k0 += KT) {
-    const int kk = k0 + kl;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    if (kk < ktot) {
-      const int chunk = kk >> 6, n_t = chunk / nb, col = (chunk - n_t * nb) * 64 + (kk & 63);
-      const float* base = partial + ((((long long)n_t * m_tiles + m_t) * splits) * kBlockM + r) * ncols + col;
-      int sp = sj;
-      for (; sp + 3 * sl < splits; sp += 4 * sl) {
-        const float v0 = base[(long long)sp * sstride], v1 = base[(long long)(sp + sl) * sstride];
-        const float v2 = base[(long long)(sp + 2 * sl) * sstride], v3 = base[(long long)(sp + 3 * sl) * sstride];
-        a0 += v0; a1 += v1; a2 += v2; a3 += v3;
-      }
-      for (; sp < splits; sp += sl) a0 += base[(long long)sp * sstride];
+  float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if (kk < ktot) {
+    const int chunk = kk >> 6, n_t = chunk / nb, col = (chunk - n_t * nb) * 64 + (kk & 63);
+    const float* base = partial + ((((long long)n_t * m_tiles + m_t) * splits) * kBlockM + r) * ncols + col;
+    int sp = sj;
+    for (; sp + 7 * sl < splits; sp += 8 * sl) {
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __ldcs(base + (long long)(sp + j * sl) * sstride);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] += v[j];
     }
-    s_lane[sj * KT + kl] = (a0 + a1) + (a2 + a3);
-    __syncthreads();
-    if (sj == 0 && kk < ktot) {
-      float acc = 0.f;
-      for (int j = 0; j < sl; ++j) acc += s_lane[j * KT + kl];
-      if (rs == 1) { if (kk < cin_real) dw[obase + kk] = mask[obase + kk] * acc; }
-      else s_row[kk] = acc;
-    }
-    __syncthreads();
+    for (; sp < splits; sp += sl) a[0] += __ldcs(base + (long long)sp * sstride);
   }
-  if (rs > 1) {
-    const int nout = cin_real * rs;
-    for (int o = threadIdx.x; o < nout; o += blockDim.x) {
-      const int ci = o / rs, tap = o - ci * rs;
-      dw[obase + o] = mask[obase + o] * s_row[tap * cin_p + ci];
+  s_lane[sj * KT + kl] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+  __syncthreads();
+  if (sj == 0 && kk < ktot) {
+    float acc = 0.f;
+    for (int j = 0; j < sl; ++j) acc += s_lane[j * KT + kl];
+    const int tap = kk / cin_p, ci = kk - tap * cin_p;
+    if (ci < cin_real) {
+      const long long o = ((long long)co * cin_real + ci) * rs + tap;
+      dw[o] = mask[o] * acc;
     }
   }
 }
@@ -661,8 +681,8 @@ static int pick_block_n(long long m_tiles, int n) {
 
 template <int BN, int CL>
 static int launch_fwd(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const FwdParams& p, cudaStream_t st) {
-  constexpr int kStages = (BN == 256) ? 4 : (BN == 128 ? 6 : 8);
-  constexpr int smem = kStages * (kBlockM * kBlockK * 2 + BN * kBlockK * 2) + 8 * 32 * 128 + 1024 + 256;
+  constexpr int kStages = fwd_stages(BN, CL);
+  constexpr int smem = kStages * (kBlockM * kBlockK * 2 + (BN / CL) * kBlockK * 2) + 8 * 32 * 128 + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
     TP_CUDA_CHECK(cudaFuncSetAttribute(k_igemm_fwd<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
@@ -711,13 +731,14 @@ static int run_fwd(const CUtensorMap& a, const CUtensorMap& b, FwdParams& p, cud
 
 // Cluster size for a problem: pairs of M tiles share the weight tile (multicast) whenever there are enough tiles.
 static int pick_cluster(long long m_tiles) {
-  static int forced = -1;
-  if (forced < 0) { const char* e = getenv("TP_IGEMM_CLUSTER"); forced = e ? atoi(e) : 0; }
+  const char* e = getenv("TP_IGEMM_CLUSTER");        // read every call: the parity tests flip it
+  const int forced = e ? atoi(e) : 0;
   if (forced == 1 || forced == 2) return forced;
+  // Measured on B200 (profiles/r01_notes.md, tools/conv_bench.py): the cta_group::2 pair kernel is bit-identical but
+  // not faster — 0.92-0.96x on the layer4 GEMMs, 1.05-1.4x SLOWER on the HBM-bound layers (both CTAs' epilogues and
+  // loads gate every accumulator hand-off through cluster-remote arrivals).  The mainloop is not L2-bandwidth bound,
+  // the per-tile epilogue is.  Pairs stay selectable with TP_IGEMM_CLUSTER=2 (parity-tested).
   (void)m_tiles;
-  // Measured on B200 (profiles/r01_notes.md): multicast halves the L2->SM weight traffic but does not move the
-  // step time — the mainloop is bound by bytes-in-flight (4 x 48 KB stages vs ~1.5 us load latency), not by L2
-  // bandwidth.  Kept behind TP_IGEMM_CLUSTER=2 (parity-tested) as the stepping stone to cta_group::2 tiles.
   return 1;
 }
 
@@ -918,18 +939,16 @@ int tp_conv_wgrad(const tp_conv_desc* d, const void* x, const void* dy, const vo
   static bool attr_set = false;
   if (!attr_set) {
     TP_CUDA_CHECK(cudaFuncSetAttribute(k_igemm_wgrad, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    TP_CUDA_CHECK(cudaFuncSetAttribute(k_wgrad_finalize, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     attr_set = true;
   }
   const int items = p.m_tiles * p.n_tiles * splits;
   k_igemm_wgrad<<<items < sms ? items : sms, kThreads, smem, st>>>(ta, tb, p);
   TP_LAUNCH_CHECK();
-  const size_t fin_smem = 256 * sizeof(float) + (rs > 1 ? (size_t)rs * d->cin * sizeof(float) : 0);
-  if (fin_smem > 64 * 1024) return TP_ERR_UNSUPPORTED;
   // split lanes only pay when there are many splits (skinny layers); wide-K layers keep all 256 threads on K
   const int sl = splits >= 64 ? 8 : (splits >= 32 ? 4 : (splits >= 16 ? 2 : 1));
-  k_wgrad_finalize<<<d->cout, 256, fin_smem, st>>>(p.partial, (const float*)mask, (float*)dw, d->cout, cin_real, d->cin, rs,
-                                                    p.nb, p.m_tiles, p.n_tiles, splits, sl);
+  const int fin_kt = 256 / sl;
+  k_wgrad_finalize<<<dim3(d->cout, (rs * d->cin + fin_kt - 1) / fin_kt), 256, 0, st>>>(
+      p.partial, (const float*)mask, (float*)dw, d->cout, cin_real, d->cin, rs, p.nb, p.m_tiles, p.n_tiles, splits, sl);
   TP_LAUNCH_CHECK();
   if (db) {
     k_colsum<<<(d->cout + 31) / 32, 256, 0, st>>>((const __nv_bfloat16*)dy, (long long)p.Kpix, d->cout, d->cout, (float*)db);

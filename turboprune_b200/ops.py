@@ -364,7 +364,8 @@ class MaskedConv2dFn(torch.autograd.Function):
         m32 = mask.detach().contiguous()
         small_c = (cin % 8 != 0) or (r * s > 1 and cin % 64 != 0)
         desc = make_desc(n, h, w, cin, cout, r, s, stride, padding)
-        cout_p = _round_up(cout, 8)
+        # the backward GEMMs contract over Cout: filters larger than 1x1 walk it in 64-channel blocks per tap
+        cout_p = _round_up(cout, 64 if (r * s > 1 and not small_c) else 8)    # (the stem path is a plain GEMM over im2col)
         if small_c:
             if cin > 8:
                 raise NotImplementedError(f"masked conv with Cin={cin} (not a multiple of 64) and a {r}x{s} filter")
