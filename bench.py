@@ -207,9 +207,13 @@ def main():
 
     from turboprune_b200.grad_exchange import GradArena
     arena = reducer if reducer is not None else GradArena(list(model.parameters()))
+    from turboprune_b200 import ops as _ops
+    from turboprune_b200.utils.mask_layers import MASKED_LAYER_TYPES
+    stager = _ops.WeightStager([m for m in model.modules() if isinstance(m, MASKED_LAYER_TYPES)])
 
     def step_body(x, t):
         arena.zero()                           # one memset; grads live in persistent slots (stable pointers)
+        stager.stage()                         # bf16(mask*w) operands of all 54 layers: one launch
         with torch.autocast("cuda", dtype=torch.bfloat16):
             out = model(x)
             loss = torch.nn.functional.cross_entropy(out, t)

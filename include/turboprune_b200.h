@@ -86,6 +86,19 @@ int tp_count_zeros(const void* const* m, const int64_t* numel, int n_seg,
 int tp_stage_weights(const void* w, const void* mask, int cout, int cin, int r, int s,
                      void* wf, int cin_p, void* wd, int cout_p, int cin_p2, void* stream);
 
+/* The same staging for MANY layers in one launch (the bf16 "weight shadow" refreshed once per optimizer step —
+ * SURVEY.md §8(f) row 2; replaces the per-layer mul + cast launches K1/K2 of mask_layers.py:25-34).
+ * wf / wd are persistent buffers owned by the caller, zero-initialised once (channel padding is never rewritten);
+ * wd may be NULL (layer without an input gradient).  table_cached != 0: `ws` still holds the table uploaded by an
+ * earlier call with identical items — no host->device copy, so the call can be captured into a CUDA graph. */
+typedef struct tp_stage_item {
+  const void* w; const void* mask;   /* fp32 OIHW [cout][cin][r][s] */
+  void* wf; void* wd;                /* bf16 [cout][r*s*cin_p], bf16 [cin][r*s*cout_p] or NULL */
+  int32_t cout, cin, r, s, cin_p, cout_p;
+} tp_stage_item;
+size_t tp_stage_batched_workspace_bytes(int n_items);
+int tp_stage_weights_batched(const tp_stage_item* items, int n_items, int table_cached, void* ws, size_t ws_bytes, void* stream);
+
 /* NCHW/NHWC fp32 or bf16 activation -> NHWC bf16 with channels padded to c_pad (zero fill).
  * src_dtype: 0 = fp32, 1 = bf16.  Strides in elements. */
 int tp_to_nhwc_bf16(const void* src, int src_dtype, int64_t sn, int64_t sc, int64_t sh, int64_t sw,

@@ -488,6 +488,63 @@ def test_cuda_graph_step_is_bit_identical_to_eager(dev):
             assert torch.equal(b1, b2), n1
 
 
+def test_batched_weight_staging_matches_per_layer(dev):
+    """WeightStager: one launch writes the bf16(mask*w) fprop / dgrad operands of every layer (stem conv with 3
+    channels, 3x3 and 1x1 convs, the fc) — bit-identical to the per-layer staging kernel; the pairs are consumed
+    exactly once; a train step with the stager gives bit-identical weights to one without."""
+    import copy
+    import refshim
+    from turboprune_b200 import ops
+    from turboprune_b200.optim import FusedSGD
+    from turboprune_b200.utils import custom_models as cm, pruning_utils as pu
+    from turboprune_b200.utils.mask_layers import MASKED_LAYER_TYPES
+    torch.manual_seed(0)
+    base = cm.TorchVisionModel(refshim.make_cfg("resnet18", "cifar10"))
+    torch.manual_seed(1)
+    pu.prune_er_erk(base, 0.3)
+    model = copy.deepcopy(base).to(dev).train()
+    layers = [m for m in model.modules() if isinstance(m, MASKED_LAYER_TYPES)]
+    stager = ops.WeightStager(layers)
+    stager.stage()
+    for l in layers:
+        w = l.weight.detach(); m = l.mask
+        if w.dim() != 4:
+            w = w.reshape(w.shape[0], w.shape[1], 1, 1); m = m.reshape(w.shape)
+        cout, cin, r, s = w.shape
+        cin_p, cout_p, has_wd = ops._operand_plan(cout, cin, r, s)
+        wf, wd = ops.stage_weights(w.contiguous(), m.contiguous(), cin_p, has_wd, cout_p)
+        got = ops.take_staged(l)
+        assert got is not None and ops.take_staged(l) is None            # consumed exactly once
+        assert torch.equal(got[0], wf)
+        if has_wd:
+            assert torch.equal(got[1][:, :wd.shape[1]], wd)
+    # pruning replaces mask tensors: the table follows
+    pu.prune_mag(model, 0.5)
+    stager.stage()
+    l = layers[3]
+    wf, _ = ops.stage_weights(l.weight.detach(), l.mask, l.weight.shape[1], False)
+    assert torch.equal(ops.take_staged(l)[0], wf)
+    for l in layers:
+        ops.take_staged(l)
+    # same step with / without the stager
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn(32, 3, 32, 32, generator=g).to(dev); t = torch.randint(0, 10, (32,), generator=g).to(dev)
+    res = []
+    for use in (False, True):
+        m2 = copy.deepcopy(base).to(dev).train()
+        opt = FusedSGD(m2.parameters(), lr=0.05, momentum=0.9, weight_decay=5e-4)
+        st = ops.WeightStager([q for q in m2.modules() if isinstance(q, MASKED_LAYER_TYPES)])
+        for _ in range(2):
+            opt.zero_grad()
+            if use:
+                st.stage()
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                torch.nn.functional.cross_entropy(m2(x), t).backward()
+            opt.step()
+        res.append([p.detach().clone() for p in m2.parameters()])
+    assert all(torch.equal(a, b) for a, b in zip(*res))
+
+
 def test_arena_direct_gradient_writes_equal_autograd_accumulation(dev):
     """With a GradArena attached, wgrad / BN backward write dW, db, dgamma, dbeta straight into the slots (no
     AccumulateGrad kernel); the values must be the ones autograd would have accumulated into a fresh .grad, and a

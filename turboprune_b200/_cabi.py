@@ -21,6 +21,11 @@ class ConvDesc(ctypes.Structure):
                 ("n", "h", "w", "cin", "cout", "r", "s", "stride_h", "stride_w", "pad_h", "pad_w", "p", "q")]
 
 
+class StageItem(ctypes.Structure):
+    _fields_ = [("w", c_void_p), ("mask", c_void_p), ("wf", c_void_p), ("wd", c_void_p)] + \
+               [(n, c_int32) for n in ("cout", "cin", "r", "s", "cin_p", "cout_p")]
+
+
 # name -> (restype, argtypes); every symbol the header declares
 SIGNATURES = {
     "tp_strerror": (c_char_p, [c_int]),
@@ -36,6 +41,8 @@ SIGNATURES = {
     "tp_count_zeros": (c_int, [POINTER(c_void_p), POINTER(c_int64), c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tp_stage_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int,
                                  c_int, c_void_p]),
+    "tp_stage_batched_workspace_bytes": (c_size_t, [c_int]),
+    "tp_stage_weights_batched": (c_int, [POINTER(StageItem), c_int, c_int, c_void_p, c_size_t, c_void_p]),
     "tp_to_nhwc_bf16": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int,
                                 c_void_p, c_int, c_void_p]),
     "tp_im2col_c8": (c_int, [c_void_p] + [c_int] * 11 + [c_void_p, c_int, c_void_p]),

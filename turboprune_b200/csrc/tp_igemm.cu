@@ -658,6 +658,30 @@ static int make_im2col_map(CUtensorMap* m, const void* ptr, int n, int h, int w,
   return TP_OK;
 }
 
+// Split-K factor of the wgrad GEMM.  Every (tile, split) item costs its share of the K loop plus a fixed 128 x 256
+// fp32 partial tile (written once, read once by the finalize pass), so the cheapest choice is the SMALLEST split
+// count that reaches the minimal makespan over the persistent CTAs — not "as many as fit in two waves": at a per-GPU
+// batch of 64 the partial tiles were most of the wgrad traffic (54 layers x ~300 items x 128 KB, twice).
+static int pick_wgrad_splits(int tiles, int kblocks, int nb) {
+  const int sms = sm_count();
+  int smax = (2 * sms) / tiles;
+  if (smax > kblocks) smax = kblocks;
+  if (smax < 1) smax = 1;
+  const double c_kb = 0.30;                         // us per 64-pixel K block (48 KB of operands, one 128x256x64 MMA group)
+  const double c_part = 0.33 * nb;                  // us to drain one partial tile from TMEM to global
+  const double c_fin = 0.013 * nb;                  // us of finalize traffic per partial tile (read once at ~5 TB/s)
+  int best = 1; double best_cost = 1e30;
+  for (int s = 1; s <= smax; ++s) {
+    const int kb = (kblocks + s - 1) / s;
+    const int s_eff = (kblocks + kb - 1) / kb;      // no empty splits
+    const long long items = (long long)tiles * s_eff;
+    const long long waves = (items + sms - 1) / sms;
+    const double cost = (double)waves * (kb * c_kb + c_part) + (double)items * c_fin;
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = s_eff; }
+  }
+  return best;
+}
+
 static bool is_plain_gemm(const tp_conv_desc* d) {
   return d->r == 1 && d->s == 1 && d->stride_h == 1 && d->stride_w == 1 && d->pad_h == 0 && d->pad_w == 0;
 }
@@ -761,7 +785,7 @@ size_t tp_conv_workspace_bytes(const tp_conv_desc* d, int op) {
   const long long kpix = (long long)d->n * d->p * d->q;
   const int kblocks = (int)((kpix + 63) / 64);
   const int sms = sm_count();
-  int splits = (2 * sms) / (m_tiles * n_tiles);          // fill two waves of CTAs, never spill into a third
+  int splits = (2 * sms) / (m_tiles * n_tiles);          // upper bound of pick_wgrad_splits()
   if (splits > kblocks) splits = kblocks;
   if (splits < 1) splits = 1;
   return (size_t)m_tiles * n_tiles * splits * kBlockM * nb * 64 * sizeof(float) + 1024;
@@ -911,9 +935,7 @@ int tp_conv_wgrad(const tp_conv_desc* d, const void* x, const void* dy, const vo
   p.n_tiles = (p.chunks + p.nb - 1) / p.nb;
   p.kblocks = (p.Kpix + 63) / 64;
   const int sms = sm_count();
-  int splits = (2 * sms) / (p.m_tiles * p.n_tiles);      // fill two waves of CTAs, never spill into a third
-  if (splits > p.kblocks) splits = p.kblocks;
-  if (splits < 1) splits = 1;
+  int splits = pick_wgrad_splits(p.m_tiles * p.n_tiles, p.kblocks, p.nb);
   p.kb_per_split = (p.kblocks + splits - 1) / splits;
   splits = (p.kblocks + p.kb_per_split - 1) / p.kb_per_split;     // no empty splits
   p.splits = splits;

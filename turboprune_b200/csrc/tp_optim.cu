@@ -1,6 +1,7 @@
 // Weight staging (mask*w -> bf16 tensor-core layouts), activation layout conversion and
 // the fused SGD step.  All HBM-bound streaming kernels.
 #include "tp_common.cuh"
+#include <vector>
 
 namespace tp {
 
@@ -9,20 +10,11 @@ namespace tp {
 //   wd[ci][R-1-r][S-1-s][co]            (K-major B operand of dgrad, K = (r',s',co))
 // OIHW -> O(RS)I is a small transpose per output channel: stage the [Cin][RS] slab of one
 // output channel through shared memory so both the read and the wf write are coalesced.
-__global__ void __launch_bounds__(256) k_stage_weights(const float* __restrict__ w, const float* __restrict__ mask,
-                                                       int cout, int cin, int rs,
-                                                       __nv_bfloat16* __restrict__ wf, int cin_p,
-                                                       __nv_bfloat16* __restrict__ wd, int cout_p, int cin_p2) {
-  extern __shared__ float s_slab[];       // [cin_chunk][rs] fp32, cin_chunk <= 1024/rs... sized by host
-  const int co = blockIdx.x;
-  const int chunk = blockDim.y;           // unused (1)
-  (void)chunk;
+__device__ __forceinline__ void stage_slab(const float* __restrict__ w, const float* __restrict__ mask, int co, int c0, int c1,
+                                           int cin, int rs, __nv_bfloat16* __restrict__ wf, int cin_p,
+                                           __nv_bfloat16* __restrict__ wd, int cout_p, bool zero_pad, float* s_slab) {
   const int t = threadIdx.x;
   const long long base = (long long)co * cin * rs;
-  // process channels in chunks of CC so the slab fits in smem
-  const int CC = gridDim.y > 0 ? (cin + gridDim.y - 1) / gridDim.y : cin;
-  const int c0 = blockIdx.y * CC;
-  const int c1 = min(cin, c0 + CC);
   const int nel = (c1 - c0) * rs;
   for (int i = t; i < nel; i += blockDim.x) {
     long long gi = base + (long long)c0 * rs + i;
@@ -42,14 +34,51 @@ __global__ void __launch_bounds__(256) k_stage_weights(const float* __restrict__
       wd[((long long)(c0 + c) * rs + (rs - 1 - tap)) * cout_p + co] = __float2bfloat16_rn(v);
     }
   }
-  // zero the channel padding of wf (cin..cin_p) — done by the y==0 slice
-  if (blockIdx.y == 0 && cin_p > cin) {
+  // zero the channel padding of wf (cin..cin_p) — done by the first channel slice
+  if (zero_pad && c0 == 0 && cin_p > cin) {
     int padn = (cin_p - cin) * rs;
     for (int i = t; i < padn; i += blockDim.x) {
       int tap = i / (cin_p - cin), c = i % (cin_p - cin);
       wf[((long long)co * rs + tap) * cin_p + cin + c] = __float2bfloat16_rn(0.f);
     }
   }
+}
+
+__global__ void __launch_bounds__(256) k_stage_weights(const float* __restrict__ w, const float* __restrict__ mask,
+                                                       int cout, int cin, int rs,
+                                                       __nv_bfloat16* __restrict__ wf, int cin_p,
+                                                       __nv_bfloat16* __restrict__ wd, int cout_p, int cin_p2) {
+  extern __shared__ float s_slab[];       // [cin_chunk][rs] fp32, sized by the host
+  (void)cout; (void)cin_p2;
+  // process channels in chunks of CC so the slab fits in smem
+  const int CC = (cin + gridDim.y - 1) / gridDim.y;
+  const int c0 = blockIdx.y * CC;
+  const int c1 = min(cin, c0 + CC);
+  stage_slab(w, mask, blockIdx.x, c0, c1, cin, rs, wf, cin_p, wd, cout_p, true, s_slab);
+}
+
+// All masked layers of a model in ONE launch (54 launches of ~10 us each were 5 % of the per-GPU-batch-64 step).
+// The operand buffers are persistent and zero-initialised by the host, so channel padding is never rewritten.
+struct StageItem {
+  const float* w; const float* mask; __nv_bfloat16* wf; __nv_bfloat16* wd;
+  int cout, cin, rs, cin_p, cout_p, ysplit, cc, pad_;
+  long long cta0;                         // first CTA of this layer; CTAs = cout * ysplit
+};
+
+__global__ void __launch_bounds__(256) k_stage_weights_batched(const StageItem* __restrict__ items, int n_items) {
+  extern __shared__ float s_slab[];
+  int lo = 0, hi = n_items - 1;
+  const long long b = blockIdx.x;
+  while (lo < hi) {                       // last item with cta0 <= b
+    const int mid = (lo + hi + 1) >> 1;
+    if (items[mid].cta0 <= b) lo = mid; else hi = mid - 1;
+  }
+  const StageItem it = items[lo];
+  const int local = (int)(b - it.cta0);
+  const int co = local / it.ysplit, y = local - co * it.ysplit;
+  const int c0 = y * it.cc, c1 = min(it.cin, c0 + it.cc);
+  if (co >= it.cout || c0 >= c1) return;
+  stage_slab(it.w, it.mask, co, c0, c1, it.cin, it.rs, it.wf, it.cin_p, it.wd, it.cout_p, false, s_slab);
 }
 
 __global__ void k_zero_bf16(__nv_bfloat16* p, long long n) {
@@ -206,6 +235,42 @@ int tp_stage_weights(const void* w, const void* mask, int cout, int cin, int r, 
   dim3 grid(cout, ysplit);
   k_stage_weights<<<grid, 256, smem, st>>>((const float*)w, (const float*)mask, cout, cin, rs,
                                            (__nv_bfloat16*)wf, cin_p, (__nv_bfloat16*)wd, cout_p, cin_p2);
+  TP_LAUNCH_CHECK();
+  return TP_OK;
+}
+
+size_t tp_stage_batched_workspace_bytes(int n_items) {
+  return n_items > 0 ? (size_t)n_items * sizeof(StageItem) + 512 : 0;
+}
+
+int tp_stage_weights_batched(const tp_stage_item* items, int n_items, int table_cached, void* ws, size_t ws_bytes, void* stream) {
+  if (!items || n_items <= 0 || !ws) return TP_ERR_INVALID;
+  cudaStream_t st = (cudaStream_t)stream;
+  Arena ar(ws, ws_bytes);
+  StageItem* d_items = (StageItem*)ar.take(sizeof(StageItem) * n_items);
+  if (!d_items) return TP_ERR_WORKSPACE;
+  std::vector<StageItem> h(n_items);
+  long long cta = 0; size_t smem = 0;
+  for (int i = 0; i < n_items; ++i) {
+    const tp_stage_item& q = items[i];
+    if (!q.w || !q.mask || !q.wf || q.cout <= 0 || q.cin <= 0 || q.r <= 0 || q.s <= 0 || q.cin_p < q.cin) return TP_ERR_INVALID;
+    if (q.wd && q.cout_p < q.cout) return TP_ERR_INVALID;
+    const int rs = q.r * q.s;
+    int max_c = 8192 / rs; if (max_c < 1) return TP_ERR_UNSUPPORTED;      // slab of at most 8192 floats (32 KB) per CTA
+    const int ysplit = (q.cin + max_c - 1) / max_c;
+    const int cc = (q.cin + ysplit - 1) / ysplit;
+    StageItem& t = h[i];
+    t.w = (const float*)q.w; t.mask = (const float*)q.mask; t.wf = (__nv_bfloat16*)q.wf; t.wd = (__nv_bfloat16*)q.wd;
+    t.cout = q.cout; t.cin = q.cin; t.rs = rs; t.cin_p = q.cin_p; t.cout_p = q.cout_p; t.ysplit = ysplit; t.cc = cc; t.pad_ = 0;
+    t.cta0 = cta;
+    cta += (long long)q.cout * ysplit;
+    const size_t need = (size_t)cc * rs * sizeof(float);
+    if (need > smem) smem = need;
+  }
+  if (cta > 0x7fffffffll) return TP_ERR_UNSUPPORTED;
+  if (!table_cached)   // pageable source: staged by the runtime before returning (not capturable: cache the table first)
+    TP_CUDA_CHECK(cudaMemcpyAsync(d_items, h.data(), sizeof(StageItem) * n_items, cudaMemcpyHostToDevice, st));
+  k_stage_weights_batched<<<(unsigned)cta, 256, smem, st>>>(d_items, n_items);
   TP_LAUNCH_CHECK();
   return TP_OK;
 }

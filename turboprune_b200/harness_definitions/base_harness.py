@@ -56,6 +56,8 @@ class BaseHarness:
         self.train_loader, self.val_loader = self._setup_dataloaders()
         self.precision, self.use_amp = self._get_dtype_amp()
         self.reducer = None
+        self._arena = None
+        self._stager = None
 
     # the reference wraps in DDP here (base_harness.py:74-82); we keep the bare module and reduce explicitly
     def _setup_model(self, model):
@@ -78,12 +80,34 @@ class BaseHarness:
             from ..grad_exchange import P2PGradReducer
             self.reducer = P2PGradReducer(list(self.model.parameters()))
 
+    def _grad_store(self):
+        if self.distributed:
+            self._ensure_reducer()
+            return self.reducer
+        if self._arena is None:
+            from ..grad_exchange import GradArena
+            self._arena = GradArena(list(self.model.parameters()))
+        return self._arena
+
+    def _weight_stager(self):
+        if self._stager is None:
+            from .. import ops
+            from ..utils.mask_layers import MASKED_LAYER_TYPES
+            self._stager = ops.WeightStager([m for m in self.model.modules() if isinstance(m, MASKED_LAYER_TYPES)])
+        return self._stager
+
     def train_step(self, batch):
         """zero_grad -> autocast forward -> CE -> backward (+ P2P gradient mean) -> SGD (reference :115-134).
         Returns the loss as a 0-dim device tensor (no host sync)."""
         inputs, targets = batch
         inputs, targets = inputs.to(self.device, non_blocking=True), targets.to(self.device, non_blocking=True)
-        self.optimizer.zero_grad(set_to_none=True)
+        if inputs.is_cuda:
+            # zero_grad: one memset of the persistent gradient storage (param.grad views its slot, the masked layers
+            # and fused BN write their gradients straight into it); bf16 weight shadow of all layers: one launch
+            self._grad_store().zero()
+            self._weight_stager().stage()
+        else:
+            self.optimizer.zero_grad(set_to_none=True)
         with autocast(device_type="cuda", dtype=self.precision, enabled=self.use_amp):
             outputs = self.model(inputs)
             loss = self.criterion(outputs, targets)

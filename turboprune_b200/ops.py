@@ -240,6 +240,93 @@ def stage_weights(weight4d, mask4d, cin_p, need_dgrad, cout_p=None):
     return wf, wd
 
 
+def _operand_plan(cout, cin, r, s):
+    """(cin_p, cout_p, has_wd) of the bf16 operand layouts a masked layer consumes, or None when the shape is unsupported."""
+    small_c = (cin % 8 != 0) or (r * s > 1 and cin % 64 != 0)
+    if small_c:
+        return (8, cout, False) if cin <= 8 else None        # stem: explicit im2col over 8 padded channels, no dgrad
+    return cin, _round_up(cout, 64 if r * s > 1 else 8), True
+
+
+class WeightStager:
+    """bf16 "weight shadow" of a whole model, refreshed by ONE launch per optimizer step.
+
+    ``stage()`` writes bf16(mask * w) of every masked layer into persistent fprop / dgrad operand buffers and hands
+    them to the layers; each layer consumes its pair in its next forward (exactly once) instead of launching its own
+    staging kernel — the reference's per-layer ``mask * weight`` + autocast cast (mask_layers.py:25-34) become one
+    kernel per step.  Call it right before the training forward; a forward without a preceding ``stage()`` (eval,
+    pruning scores) stages per layer as before.  Pointers are re-checked every call (pruning replaces mask tensors),
+    the device table is only re-uploaded when they changed, so the call is CUDA-graph capturable after a warm-up step."""
+
+    def __init__(self, layers):
+        self.layers = [l for l in layers]
+        self._key = None
+        self._bufs = None
+        self._items = None
+        self._ws = None
+
+    @staticmethod
+    def _shape4(layer):
+        w = layer.weight
+        if w.dim() == 4:
+            return tuple(w.shape)
+        return (w.shape[0], w.shape[1], 1, 1)                 # Linear [out, in] / Conv1d(k=1) [out, in, 1]
+
+    def _rebuild(self, key):
+        dev = self.layers[0].weight.device
+        if self._bufs is None:
+            self._bufs = []
+            for l in self.layers:
+                cout, cin, r, s = self._shape4(l)
+                plan = _operand_plan(cout, cin, r, s)
+                if plan is None or not l.weight.is_cuda or l.weight.dtype != torch.float32 or not l.weight.is_contiguous():
+                    self._bufs.append(None)
+                    continue
+                cin_p, cout_p, has_wd = plan
+                wf = torch.zeros(cout, r * s * cin_p, dtype=torch.bfloat16, device=dev)
+                wd = torch.zeros(cin, r * s * cout_p, dtype=torch.bfloat16, device=dev) if has_wd else None
+                self._bufs.append((wf, wd, cin_p, cout_p))
+        live = [(l, b) for l, b in zip(self.layers, self._bufs) if b is not None]
+        items = (_cabi.StageItem * len(live))()
+        for it, (l, (wf, wd, cin_p, cout_p)) in zip(items, live):
+            cout, cin, r, s = self._shape4(l)
+            it.w = l.weight.data_ptr(); it.mask = l.mask.data_ptr()
+            it.wf = wf.data_ptr(); it.wd = wd.data_ptr() if wd is not None else None
+            it.cout, it.cin, it.r, it.s, it.cin_p, it.cout_p = cout, cin, r, s, cin_p, cout_p
+        self._items, self._live, self._key = items, live, key
+        if self._ws is None:
+            lib = _cabi.load()
+            self._ws = torch.empty(max(int(lib.tp_stage_batched_workspace_bytes(len(self.layers))), 256), dtype=torch.uint8, device=dev)
+
+    def stage(self):
+        lib = _cabi.load()
+        for l in self.layers:                                  # masks created on the host move with the first use
+            if l.mask.device != l.weight.device or l.mask.dtype != torch.float32 or not l.mask.is_contiguous():
+                l.mask = l.mask.to(device=l.weight.device, dtype=torch.float32).contiguous()
+        key = tuple((l.weight.data_ptr(), l.mask.data_ptr()) for l in self.layers)
+        cached = key == self._key
+        if not cached:
+            self._rebuild(key)
+        if not len(self._live):
+            return
+        dev = self.layers[0].weight.device
+        with torch.cuda.device(dev):
+            rc = lib.tp_stage_weights_batched(self._items, len(self._live), int(cached), c_void_p(self._ws.data_ptr()),
+                                              self._ws.numel(), _cabi.stream_ptr(dev))
+        _cabi.check(rc, "tp_stage_weights_batched")
+        _count()
+        for l, (wf, wd, _, _) in self._live:
+            l.__dict__["_tp_staged"] = (wf, wd)
+
+
+def take_staged(layer):
+    """The (wf, wd) pair a ``WeightStager`` left for this layer's next forward, or None; consumed exactly once."""
+    st = layer.__dict__.get("_tp_staged")
+    if st is not None:
+        layer.__dict__["_tp_staged"] = None
+    return st
+
+
 def to_nhwc_bf16(x, c_pad):
     """[N, C, H, W] (any strides; fp32 or bf16) -> contiguous NHWC bf16 [N, H, W, c_pad]."""
     lib = _cabi.load()
@@ -350,7 +437,7 @@ class MaskedConv2dFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, weight, mask, bias, stride, padding, want_skip=False, grad_slots=None):
+    def forward(ctx, x, weight, mask, bias, stride, padding, want_skip=False, grad_slots=None, staged=None):
         _require_cuda(x, weight, mask)
         ctx.set_materialize_grads(False)
         ctx.want_skip = want_skip
@@ -375,7 +462,10 @@ class MaskedConv2dFn(torch.autograd.Function):
             kp = r * s * 8
             xg = im2col_stem(x, desc, kp)
             gdesc = _cabi.ConvDesc(n * desc.p * desc.q, 1, 1, kp, cout, 1, 1, 1, 1, 0, 0, 1, 1)
-            wf, wd = stage_weights(w32, m32, 8, False)
+            if staged is not None and staged[0].shape == (cout, kp):
+                wf, wd = staged
+            else:
+                wf, wd = stage_weights(w32, m32, 8, False)
             y = empty_cl(n, cout, desc.p, desc.q, x.device)
             conv_fprop(gdesc, xg, wf, bias, out=y)
             ctx.mode = "stem"
@@ -383,7 +473,11 @@ class MaskedConv2dFn(torch.autograd.Function):
             ctx.save_for_backward(xg, m32)
         else:
             xn = to_nhwc_bf16(x, cin)
-            wf, wd = stage_weights(w32, m32, cin, need_dx, cout_p)
+            if (staged is not None and staged[0].shape == (cout, r * s * cin)
+                    and (not need_dx or (staged[1] is not None and staged[1].shape == (cin, r * s * cout_p)))):
+                wf, wd = staged              # refreshed by WeightStager.stage() for this step (one launch for all layers)
+            else:
+                wf, wd = stage_weights(w32, m32, cin, need_dx, cout_p)
             y = empty_cl(n, cout, desc.p, desc.q, x.device)
             conv_fprop(desc, xn, wf, bias, out=y)
             ctx.mode = "conv"
@@ -403,7 +497,7 @@ class MaskedConv2dFn(torch.autograd.Function):
     def backward(ctx, dy, dskip=None):
         desc = ctx.desc
         if dy is None:          # only the skip output was used downstream
-            return dskip, None, None, None, None, None, None, None
+            return dskip, None, None, None, None, None, None, None, None
         cout = desc.cout
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         need_db = ctx.has_bias and ctx.needs_input_grad[3]
@@ -453,17 +547,17 @@ class MaskedConv2dFn(torch.autograd.Function):
             db = dy.float().sum(dim=(0, 2, 3))
         if dskip is not None and dx is None and need_dx is False:
             dx = None
-        return dx, dw, None, db, None, None, None, None
+        return dx, dw, None, db, None, None, None, None, None
 
 
-def masked_conv2d(x, weight, mask, bias=None, stride=(1, 1), padding=(0, 0), want_skip=False, grad_slots=None):
-    return MaskedConv2dFn.apply(x, weight, mask, bias, tuple(stride), tuple(padding), want_skip, grad_slots)
+def masked_conv2d(x, weight, mask, bias=None, stride=(1, 1), padding=(0, 0), want_skip=False, grad_slots=None, staged=None):
+    return MaskedConv2dFn.apply(x, weight, mask, bias, tuple(stride), tuple(padding), want_skip, grad_slots, staged)
 
 
-def masked_linear(x, weight2d, mask2d, bias=None, grad_slots=None):
+def masked_linear(x, weight2d, mask2d, bias=None, grad_slots=None, staged=None):
     """y = x @ (mask*w)^T + b for x [..., in]; runs as a 1x1 convolution over a [rows,1,1,in] image."""
     shp = x.shape
     x2 = x.reshape(-1, shp[-1])
     y = MaskedConv2dFn.apply(x2.view(x2.shape[0], x2.shape[1], 1, 1), weight2d.view(*weight2d.shape, 1, 1),
-                             mask2d.view(*mask2d.shape, 1, 1), bias, (1, 1), (0, 0), False, grad_slots)
+                             mask2d.view(*mask2d.shape, 1, 1), bias, (1, 1), (0, 0), False, grad_slots, staged)
     return y.reshape(*shp[:-1], weight2d.shape[0])

@@ -68,7 +68,7 @@ class ConvMask(_MaskMixin, nn.Conv2d):
         self._check_plain()
         if isinstance(self.padding, str):
             raise NotImplementedError("string padding modes")
-        return ops.masked_conv2d(x, self.weight, self.mask, self.bias, _pair(self.stride), _pair(self.padding), want_skip, _slots(self))
+        return ops.masked_conv2d(x, self.weight, self.mask, self.bias, _pair(self.stride), _pair(self.padding), want_skip, _slots(self), ops.take_staged(self))
 
 
 class LinearMask(_MaskMixin, nn.Linear):
@@ -77,7 +77,7 @@ class LinearMask(_MaskMixin, nn.Linear):
         self._init_mask()
 
     def forward(self, x):
-        return ops.masked_linear(x, self.weight, self.mask, self.bias, _slots(self))
+        return ops.masked_linear(x, self.weight, self.mask, self.bias, _slots(self), ops.take_staged(self))
 
 
 class Conv1dMask(_MaskMixin, nn.Conv1d):
@@ -89,7 +89,7 @@ class Conv1dMask(_MaskMixin, nn.Conv1d):
 
     def forward(self, x):
         w = self.weight
-        return ops.masked_linear(x, w.view(w.shape[0], w.shape[1]), self.mask.view(w.shape[0], w.shape[1]), self.bias, _slots(self))
+        return ops.masked_linear(x, w.view(w.shape[0], w.shape[1]), self.mask.view(w.shape[0], w.shape[1]), self.bias, _slots(self), ops.take_staged(self))
 
 
 MASKED_LAYER_TYPES = (ConvMask, Conv1dMask, LinearMask)
