@@ -136,6 +136,13 @@ size_t tp_conv_workspace_bytes(const tp_conv_desc* d, int op);   /* op: 0 fprop,
 /* y[n,p,q,cout] (bf16) = conv(x[n,h,w,cin] (bf16), wf (bf16, tp_stage_weights layout)) + bias */
 int tp_conv_fprop(const tp_conv_desc* d, const void* x, const void* wf, const void* bias_f32,
                   void* y, void* ws, size_t ws_bytes, void* stream);
+/* Same, and the epilogue also writes BatchNorm batch statistics of the bf16 outputs it stores: for every group of 32
+ * output pixels one row [2][cout] fp32 = (sum, sum of squares) per channel; stats holds tp_conv_stats_rows(d) rows
+ * (rows past the last pixel are written as zeros).  Consumed by tp_bn_forward_ext — the BatchNorm2d that follows
+ * the convolution (torchvision graph built at utils/custom_models.py:184) then needs no statistics pass. */
+size_t tp_conv_stats_rows(const tp_conv_desc* d);
+int tp_conv_fprop_stats(const tp_conv_desc* d, const void* x, const void* wf, const void* bias_f32,
+                        void* y, void* stats, void* ws, size_t ws_bytes, void* stream);
 /* dx[n,h,w,cin] (bf16) = conv_dgrad(dy[n,p,q,cout] (bf16), wd (bf16, rotated layout)) [+ addend[n,h,w,cin]]
  * addend (optional, bf16, same layout as dx): the gradient arriving over a skip connection, accumulated in the
  * epilogue instead of by a separate elementwise add (autograd's grad accumulation at a ResNet block input). */
@@ -144,6 +151,15 @@ int tp_conv_dgrad(const tp_conv_desc* d, const void* dy, const void* wd, const v
 /* dw[cout][cin_real][r][s] (fp32, OIHW) = mask * conv_wgrad(x, dy); db[cout] = sum dy (optional) */
 int tp_conv_wgrad(const tp_conv_desc* d, const void* x, const void* dy, const void* mask,
                   int cin_real, void* dw, void* db, void* ws, size_t ws_bytes, void* stream);
+
+/* tp_bn_forward with the batch statistics supplied by the producing convolution (tp_conv_fprop_stats):
+ * ext_stats [ext_rows][2][C] fp32 un-shifted sums; training must be non-zero.  ext_stats == NULL: identical to
+ * tp_bn_forward. */
+int tp_bn_forward_ext(const void* y, const void* residual, void* z, int64_t M, int C,
+                      const void* weight, const void* bias, void* running_mean, void* running_var,
+                      void* num_batches_tracked, float momentum, float eps, int training, int relu,
+                      void* save_mean, void* save_invstd, const void* ext_stats, int64_t ext_rows,
+                      void* ws, size_t ws_bytes, void* stream);
 
 /* ---- fused BatchNorm (+ residual add) (+ ReLU) on NHWC bf16 activations ------------------
  * the unmasked torchvision BatchNorm2d / ReLU / `out += identity` ops between

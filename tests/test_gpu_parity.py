@@ -426,6 +426,54 @@ def test_fused_batchnorm_vs_torch(dev, case):
         assert _rel(bn(x, relu=relu), torch.relu(ref(x.float())) if relu else ref(x.float())) < 1e-2
 
 
+@pytest.mark.parametrize("case", [(6, 64, 128, 3, 1, 1, 19, True), (5, 128, 256, 1, 1, 0, 14, False), (4, 64, 64, 3, 2, 1, 30, False),
+                                  (3, 3, 64, 7, 2, 3, 40, False)])
+def test_conv_epilogue_batchnorm_statistics(dev, case):
+    """The conv epilogue's per-channel (sum, sum of squares) of the bf16 outputs equal a direct reduction of the
+    stored activation, and conv -> BatchNorm with the statistics handed over through the epilogue matches the
+    two-pass path (outputs, running statistics, all gradients)."""
+    import copy
+    from turboprune_b200 import fused_norm as fn
+    from turboprune_b200.utils import mask_layers as ml
+    b, cin, cout, k, s, p, hw, bias = case
+    g = torch.Generator(device=dev).manual_seed(sum(case[:7]))
+    conv = ml.ConvMask(in_channels=cin, out_channels=cout, kernel_size=k, stride=s, padding=p, bias=bias).to(dev)
+    with torch.no_grad():
+        conv.mask.copy_((torch.rand(conv.weight.shape, device=dev, generator=g) < 0.4).float())
+        if bias:
+            conv.bias.copy_(torch.randn(cout, device=dev, generator=g) * 3)         # |mean| >> std for some channels
+    bn = fn.BatchNorm2dB200(cout).to(dev).train()
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(cout, device=dev, generator=g) + 0.5); bn.bias.copy_(torch.randn(cout, device=dev, generator=g))
+    x = torch.randn(b, cin, hw, hw, device=dev, generator=g).to(torch.bfloat16 if cin >= 8 else torch.float32)
+    x = x.contiguous(memory_format=torch.channels_last)
+    y, stats = conv(x, want_stats=True)
+    yf = y.detach().float()
+    ref1 = yf.sum(dim=(0, 2, 3)); ref2 = (yf * yf).sum(dim=(0, 2, 3))
+    got = stats.sum(dim=0)
+    assert float((got[0] - ref1).abs().max()) <= 1e-4 * float(ref2.sqrt().max()) * (y.numel() / cout) ** 0.5 + 1e-3
+    assert _rel(got[1], ref2) < 1e-5
+    res = []
+    for fused in (False, True):
+        c2, b2 = copy.deepcopy(conv), copy.deepcopy(bn)
+        xx = x.clone().requires_grad_(cin >= 8)
+        if fused:
+            z, _ = fn._conv_bn(c2, b2, xx, relu=True)
+        else:
+            z = b2(c2(xx), relu=True)
+        gz = torch.Generator(device=dev).manual_seed(11)
+        z.backward(torch.randn(z.shape, device=dev, generator=gz).to(z.dtype).contiguous(memory_format=torch.channels_last))
+        res.append((z.detach().float(), b2.running_mean.clone(), b2.running_var.clone(), c2.weight.grad.clone(),
+                    b2.weight.grad.clone(), b2.bias.grad.clone(), xx.grad.float() if cin >= 8 else None))
+    a_, b_ = res
+    assert _rel(b_[0], a_[0]) < 1e-2                                    # bf16 outputs: a last-bit flip of scale/shift at most
+    assert _rel(b_[1], a_[1]) < 1e-5 and _rel(b_[2], a_[2]) < 1e-4
+    for i in (3, 4, 5):
+        assert _rel(b_[i], a_[i]) < 2e-2
+    if a_[6] is not None:
+        assert _rel(b_[6], a_[6]) < 2e-2
+
+
 def test_maxpool_vs_torch(dev):
     from turboprune_b200.fused_norm import MaxPool2dB200
     g = torch.Generator().manual_seed(3)

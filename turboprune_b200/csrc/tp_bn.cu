@@ -151,11 +151,19 @@ __global__ void __launch_bounds__(kFinC * kFinP) k_bn_finalize_stats(const float
   if (threadIdx.y != 0) return;
   if (c == 0 && nbt) *nbt += 1;
   if (c >= C) return;
-  const float sh = __bfloat162float(y[c]);
-  const float inv_m = 1.f / (float)M;
-  const float dm = s1 * inv_m;
-  const float mean = sh + dm;
-  float var = fmaf(-dm, dm, s2 * inv_m);
+  float mean, var;
+  if (y) {
+    const float sh = __bfloat162float(y[c]);
+    const float inv_m = 1.f / (float)M;
+    const float dm = s1 * inv_m;
+    mean = sh + dm;
+    var = fmaf(-dm, dm, s2 * inv_m);
+  } else {
+    // un-shifted sums from the conv epilogue: E[x^2] - E[x]^2 combined in double (one thread per channel)
+    const double dmean = (double)s1 / (double)M;
+    mean = (float)dmean;
+    var = (float)((double)s2 / (double)M - dmean * dmean);
+  }
   var = fmaxf(var, 0.f);
   const float invstd = rsqrtf(var + eps);
   save_mean[c] = mean; save_invstd[c] = invstd;
@@ -165,6 +173,37 @@ __global__ void __launch_bounds__(kFinC * kFinP) k_bn_finalize_stats(const float
     running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
     const float unbiased = M > 1 ? var * ((float)M / (float)(M - 1)) : var;
     running_var[c] = (1.f - momentum) * running_var[c] + momentum * unbiased;
+  }
+}
+
+// First fold level for statistics produced by the conv epilogue: ext[rows][2][C] (one row per 32 output pixels) ->
+// partial[g][2][C], 1024 rows per CTA in a fixed order; k_bn_finalize_stats then folds the (few) g rows.
+__global__ void __launch_bounds__(kFinC * kFinP) k_bn_fold_ext(const float* __restrict__ ext, long long rows, int C,
+                                                               float* __restrict__ partial) {
+  __shared__ float sm[2][kFinP][kFinC];
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  const int c = blockIdx.x * kFinC + tx;
+  const long long r0 = (long long)blockIdx.y * 1024, r1 = min(rows, r0 + 1024);
+  float a1 = 0.f, a2 = 0.f;
+  if (c < C) {
+    long long j = r0 + ty;
+    for (; j + 3 * kFinP < r1; j += 4 * kFinP) {
+      float v1[4], v2[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { v1[u] = ext[(size_t)(j + u * kFinP) * 2 * C + c]; v2[u] = ext[(size_t)(j + u * kFinP) * 2 * C + C + c]; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { a1 += v1[u]; a2 += v2[u]; }
+    }
+    for (; j < r1; j += kFinP) { a1 += ext[(size_t)j * 2 * C + c]; a2 += ext[(size_t)j * 2 * C + C + c]; }
+  }
+  sm[0][ty][tx] = a1; sm[1][ty][tx] = a2;
+  __syncthreads();
+  if (ty == 0 && c < C) {
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int k = 0; k < kFinP; ++k) { s1 += sm[0][k][tx]; s2 += sm[1][k][tx]; }
+    partial[(size_t)blockIdx.y * 2 * C + c] = s1;
+    partial[(size_t)blockIdx.y * 2 * C + C + c] = s2;
   }
 }
 
@@ -405,7 +444,17 @@ int tp_bn_forward(const void* y, const void* residual, void* z, int64_t M, int C
                   const void* weight, const void* bias, void* running_mean, void* running_var,
                   void* num_batches_tracked, float momentum, float eps, int training, int relu,
                   void* save_mean, void* save_invstd, void* ws, size_t ws_bytes, void* stream) {
+  return tp_bn_forward_ext(y, residual, z, M, C, weight, bias, running_mean, running_var, num_batches_tracked, momentum,
+                           eps, training, relu, save_mean, save_invstd, nullptr, 0, ws, ws_bytes, stream);
+}
+
+int tp_bn_forward_ext(const void* y, const void* residual, void* z, int64_t M, int C,
+                      const void* weight, const void* bias, void* running_mean, void* running_var,
+                      void* num_batches_tracked, float momentum, float eps, int training, int relu,
+                      void* save_mean, void* save_invstd, const void* ext_stats, int64_t ext_rows,
+                      void* ws, size_t ws_bytes, void* stream) {
   if (!y || !z || M <= 0 || C <= 0 || C % 8 != 0 || !ws) return TP_ERR_INVALID;
+  if (ext_stats && (!training || ext_rows <= 0)) return TP_ERR_INVALID;
   if (training && (!save_mean || !save_invstd)) return TP_ERR_INVALID;
   if (!training && (!running_mean || !running_var)) return TP_ERR_INVALID;
   if (ws_bytes < tp_bn_workspace_bytes(M, C)) return TP_ERR_WORKSPACE;
@@ -416,7 +465,16 @@ int tp_bn_forward(const void* y, const void* residual, void* z, int64_t M, int C
   float* scale = partial + (size_t)g.grid_x * 2 * C;
   float* shift = scale + C;
   dim3 block(g.tx, g.ty), grid(g.grid_x, g.ctiles);
-  if (training) {
+  if (training && ext_stats) {
+    // statistics came out of the producing convolution's epilogue: two small folds, no pass over the activation
+    const long long groups = (ext_rows + 1023) / 1024;
+    if (groups > g.grid_x) return TP_ERR_WORKSPACE;
+    k_bn_fold_ext<<<dim3((C + kFinC - 1) / kFinC, (unsigned)groups), dim3(kFinC, kFinP), 0, st>>>((const float*)ext_stats, ext_rows, C, partial);
+    k_bn_finalize_stats<<<(C + kFinC - 1) / kFinC, dim3(kFinC, kFinP), 0, st>>>(partial, (int)groups, nullptr, M, C,
+                                                          (const float*)weight, (const float*)bias, (float*)running_mean,
+                                                          (float*)running_var, (long long*)num_batches_tracked, momentum, eps,
+                                                          (float*)save_mean, (float*)save_invstd, scale, shift);
+  } else if (training) {
     k_bn_stats<<<grid, block, 0, st>>>((const __nv_bfloat16*)y, M, C, partial);
     k_bn_finalize_stats<<<(C + kFinC - 1) / kFinC, dim3(kFinC, kFinP), 0, st>>>(partial, g.grid_x, (const __nv_bfloat16*)y, M, C,
                                                           (const float*)weight, (const float*)bias, (float*)running_mean,

@@ -54,6 +54,9 @@ struct FwdParams {
   __nv_bfloat16* out;
   const float* bias;
   const __nv_bfloat16* addend;   // optional: out = acc (+ bias) + addend[pixel][channel] (same layout as out)
+  float* stats;                  // optional (linear output only): per-channel sum / sum of squares of the bf16 outputs
+                                 // of every 32-row group, [ceil(M/128)*4][2][N] fp32 — BatchNorm statistics without
+                                 // another pass over the activation
   TapEntry taps[kMaxTaps];
 };
 
@@ -245,6 +248,7 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         __nv_bfloat16* gout = p.out + (wrow0 + r_in) * ldc + c16 * 8;           // + i*4*ldc + n0
         const __nv_bfloat16* gadd = p.addend ? p.addend + (wrow0 + r_in) * ldc + c16 * 8 : nullptr;
         const float* bias = p.bias;
+        float* stats = p.stats ? p.stats + (long long)(m_t * 4 + quarter) * 2 * N + c16 * 8 : nullptr;
         const uint32_t wr_base = buf + lane * 128;                              // my row (TMEM lane) in the staging tile
         const uint32_t wr_sw = (uint32_t)(lane & 7);
         const uint32_t rd_even = buf + r_in * 128 + ((uint32_t)(c16 ^ r_in) << 4);          // rows r_in + 8j
@@ -318,6 +322,36 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             if (i * 4 + r_in < rows_left && col_ok) *reinterpret_cast<uint4*>(gout + (long long)(i * 4) * ldc + n0) = o[i];
+          if (stats) {
+            // BatchNorm batch statistics of exactly the values just stored (bf16-rounded): this thread owns 8 channels
+            // of rows r_in, r_in+4, ...; a fixed-order xor tree over the 4 row groups finishes the 32 rows
+            float s1[8], s2[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { s1[q] = 0.f; s2[q] = 0.f; }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (i * 4 + r_in < rows_left) {
+                const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&o[i]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float2 t2 = __bfloat1622float2(h2[q]);
+                  s1[2 * q] += t2.x; s2[2 * q] = fmaf(t2.x, t2.x, s2[2 * q]);
+                  s1[2 * q + 1] += t2.y; s2[2 * q + 1] = fmaf(t2.y, t2.y, s2[2 * q + 1]);
+                }
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], 8);  s2[q] += __shfl_xor_sync(0xffffffffu, s2[q], 8);
+              s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], 16); s2[q] += __shfl_xor_sync(0xffffffffu, s2[q], 16);
+            }
+            if (r_in == 0 && col_ok) {
+              float4* d1 = reinterpret_cast<float4*>(stats + n0);
+              float4* d2 = reinterpret_cast<float4*>(stats + N + n0);
+              d1[0] = make_float4(s1[0], s1[1], s1[2], s1[3]); d1[1] = make_float4(s1[4], s1[5], s1[6], s1[7]);
+              d2[0] = make_float4(s2[0], s2[1], s2[2], s2[3]); d2[1] = make_float4(s2[4], s2[5], s2[6], s2[7]);
+            }
+          }
           __syncwarp();
         }
       } else {
@@ -689,6 +723,10 @@ static bool is_plain_gemm(const tp_conv_desc* d) {
 static int pick_block_n(long long m_tiles, int n) {
   // favour wide tiles (fewer re-reads of the activation tile), but keep the last wave full
   const int sms = sm_count();
+  if (const char* e = getenv("TP_IGEMM_BN")) {        // experiments only: force the tile width
+    const int f = atoi(e);
+    if ((f == 64 || f == 128 || f == 256) && (f == 64 || n > f / 2)) return f;
+  }
   int best = 64; double best_score = -1;
   const int cands[3] = {256, 128, 64};
   const double weight[3] = {1.0, 0.92, 0.75};
@@ -742,6 +780,7 @@ static int run_fwd(const CUtensorMap& a, const CUtensorMap& b, FwdParams& p, cud
     int rc = make_out_map(&c, p.out, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldc); if (rc) return rc;
     p.tma_store = 1;
   }
+  if (p.stats && !p.tma_store) return TP_ERR_UNSUPPORTED;
   const int bn = pick_block_n((p.M + kBlockM - 1) / kBlockM, p.N);
   if (p.cluster == 2) {
     if (bn == 256) return launch_fwd<256, 2>(a, b, c, p, st);
@@ -791,10 +830,22 @@ size_t tp_conv_workspace_bytes(const tp_conv_desc* d, int op) {
   return (size_t)m_tiles * n_tiles * splits * kBlockM * nb * 64 * sizeof(float) + 1024;
 }
 
+size_t tp_conv_stats_rows(const tp_conv_desc* d) {
+  if (!d) return 0;
+  const long long M = (long long)d->n * d->p * d->q;
+  return (size_t)((M + kBlockM - 1) / kBlockM) * 4;
+}
+
 int tp_conv_fprop(const tp_conv_desc* d, const void* x, const void* wf, const void* bias_f32,
                   void* y, void* ws, size_t ws_bytes, void* stream) {
+  return tp_conv_fprop_stats(d, x, wf, bias_f32, y, nullptr, ws, ws_bytes, stream);
+}
+
+int tp_conv_fprop_stats(const tp_conv_desc* d, const void* x, const void* wf, const void* bias_f32,
+                        void* y, void* stats, void* ws, size_t ws_bytes, void* stream) {
   (void)ws; (void)ws_bytes;
   if (!d || !x || !wf || !y) return TP_ERR_INVALID;
+  if (stats && (d->cout % 8 != 0 || (((uintptr_t)y) & 15) != 0 || (((uintptr_t)stats) & 15) != 0)) return TP_ERR_UNSUPPORTED;
   if (d->cin % 8 != 0 || d->r * d->s > kMaxTaps) return TP_ERR_UNSUPPORTED;
   if (d->r * d->s > 1 && d->cin % 64 != 0) return TP_ERR_UNSUPPORTED;
   int rc = load_driver_fns(); if (rc) return rc;
@@ -807,6 +858,7 @@ int tp_conv_fprop(const tp_conv_desc* d, const void* x, const void* wf, const vo
   p.out_img_pix = (long long)d->p * d->q; p.out_row_pix = d->q;
   p.osh = 1; p.oah = 0; p.osw = 1; p.oaw = 0;
   p.ldc = d->cout; p.out = (__nv_bfloat16*)y; p.bias = (const float*)bias_f32;
+  p.stats = (float*)stats;
   for (int r = 0; r < d->r; ++r) for (int s = 0; s < d->s; ++s) {
     TapEntry& t = p.taps[r * d->s + s];
     t.off_w = (uint16_t)s; t.off_h = (uint16_t)r; t.kofs = (r * d->s + s) * d->cin;

@@ -22,7 +22,7 @@ def _ptr(t):
 
 class _BNFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, residual, weight, bias, running_mean, running_var, nbt, momentum, eps, training, relu, grad_slots=None):
+    def forward(ctx, x, residual, weight, bias, running_mean, running_var, nbt, momentum, eps, training, relu, grad_slots=None, ext_stats=None):
         lib = _cabi.load()
         ctx.set_materialize_grads(False)
         ctx.grad_slots = grad_slots
@@ -36,9 +36,11 @@ class _BNFn(torch.autograd.Function):
         save_invstd = torch.empty(c, dtype=torch.float32, device=dev) if training else None
         wsb = ops._workspace(lib.tp_bn_workspace_bytes(m, c), dev, "bn")
         with torch.cuda.device(dev):
-            rc = lib.tp_bn_forward(_ptr(xn), _ptr(rn), _ptr(z), m, c, _ptr(weight), _ptr(bias), _ptr(running_mean),
-                                   _ptr(running_var), _ptr(nbt), float(momentum), float(eps), int(training), int(relu),
-                                   _ptr(save_mean), _ptr(save_invstd), _ptr(wsb), wsb.numel(), _cabi.stream_ptr(dev))
+            use_ext = ext_stats is not None and training
+            rc = lib.tp_bn_forward_ext(_ptr(xn), _ptr(rn), _ptr(z), m, c, _ptr(weight), _ptr(bias), _ptr(running_mean),
+                                       _ptr(running_var), _ptr(nbt), float(momentum), float(eps), int(training), int(relu),
+                                       _ptr(save_mean), _ptr(save_invstd), _ptr(ext_stats) if use_ext else None,
+                                       ext_stats.shape[0] if use_ext else 0, _ptr(wsb), wsb.numel(), _cabi.stream_ptr(dev))
         _cabi.check(rc, "tp_bn_forward")
         ops._count(3 if training else 2)
         if training:
@@ -79,13 +81,14 @@ class _BNFn(torch.autograd.Function):
             gr = gr.to(ctx.res_dtype)
         if direct:
             dweight = dbias = None
-        return gx, gr, dweight, dbias, None, None, None, None, None, None, None, None
+        return gx, gr, dweight, dbias, None, None, None, None, None, None, None, None, None
 
 
 class BatchNorm2dB200(nn.BatchNorm2d):
     """nn.BatchNorm2d whose CUDA path is the fused sm_100a kernel; ``forward(x, residual=None, relu=False)``."""
 
-    def forward(self, x, residual=None, relu=False):
+    def forward(self, x, residual=None, relu=False, ext_stats=None):
+        """``ext_stats``: batch statistics of ``x`` already computed by the producing convolution's epilogue."""
         training = self.training or not self.track_running_stats
         # eval-mode BN inside an autograd graph is not on the hot path: leave it to torch
         if not x.is_cuda or x.shape[1] % 8 != 0 or (not training and torch.is_grad_enabled() and x.requires_grad):
@@ -97,7 +100,7 @@ class BatchNorm2dB200(nn.BatchNorm2d):
         slots = grad_slots(self.weight, self.bias)
         return _BNFn.apply(x, residual, self.weight, self.bias, self.running_mean, self.running_var,
                            self.num_batches_tracked if (training and self.track_running_stats) else None,
-                           momentum, self.eps, training, relu, slots)
+                           momentum, self.eps, training, relu, slots, ext_stats)
 
 
 class _MaxPoolFn(torch.autograd.Function):
@@ -146,35 +149,59 @@ class MaxPool2dB200(nn.MaxPool2d):
 
 
 # ---- fused forwards for the torchvision graphs the reference instantiates ------------------------------
-def _conv_with_skip(conv, x):
-    """(conv(x), x') where x' aliases x and routes its gradient into conv's dgrad epilogue (no separate add kernel)."""
+def _stats_ok(conv, bn, x):
+    """conv -> bn can hand the batch statistics over through the conv epilogue (training-mode fused BN on CUDA)."""
     from .utils.mask_layers import ConvMask
-    if isinstance(conv, ConvMask) and x.requires_grad and x.shape[1] % 64 == 0:
-        return conv(x, want_skip=True)
-    return conv(x), x
+    return (isinstance(conv, ConvMask) and isinstance(bn, BatchNorm2dB200) and x.is_cuda and conv.out_channels % 8 == 0
+            and (bn.training or not bn.track_running_stats) and not isinstance(conv.padding, str))
+
+
+def _conv_bn(conv, bn, x, residual=None, relu=False, skip=False):
+    """bn(conv(x)) [+ residual] [relu] with the statistics taken from the conv epilogue when possible.
+    ``skip=True`` also returns the aliased input whose gradient lands in conv's dgrad epilogue."""
+    fuse = _stats_ok(conv, bn, x)
+    xs = x
+    if skip:
+        from .utils.mask_layers import ConvMask
+        skip = isinstance(conv, ConvMask) and x.requires_grad and x.shape[1] % 64 == 0
+    if fuse:
+        outs = conv(x, want_skip=skip, want_stats=True)
+        y, stats = outs[0], outs[-1]
+        if skip:
+            xs = outs[1]
+        z = bn(y, residual=residual, relu=relu, ext_stats=stats)
+    else:
+        if skip:
+            y, xs = conv(x, want_skip=True)
+        else:
+            y = conv(x)
+        z = bn(y, residual=residual, relu=relu)
+    return z, xs
+
+
+def _downsample(ds, identity):
+    if isinstance(ds, nn.Sequential) and len(ds) == 2:
+        return _conv_bn(ds[0], ds[1], identity)[0]
+    return ds(identity)
 
 
 def _basic_block_forward(self, x):
-    out, identity = _conv_with_skip(self.conv1, x)
-    out = self.bn1(out, relu=True)
-    out = self.conv2(out)
+    out, identity = _conv_bn(self.conv1, self.bn1, x, relu=True, skip=True)
     if self.downsample is not None:
-        identity = self.downsample(identity)
-    return self.bn2(out, residual=identity, relu=True)
+        identity = _downsample(self.downsample, identity)
+    return _conv_bn(self.conv2, self.bn2, out, residual=identity, relu=True)[0]
 
 
 def _bottleneck_forward(self, x):
-    out, identity = _conv_with_skip(self.conv1, x)
-    out = self.bn1(out, relu=True)
-    out = self.bn2(self.conv2(out), relu=True)
-    out = self.conv3(out)
+    out, identity = _conv_bn(self.conv1, self.bn1, x, relu=True, skip=True)
+    out = _conv_bn(self.conv2, self.bn2, out, relu=True)[0]
     if self.downsample is not None:
-        identity = self.downsample(identity)
-    return self.bn3(out, residual=identity, relu=True)
+        identity = _downsample(self.downsample, identity)
+    return _conv_bn(self.conv3, self.bn3, out, residual=identity, relu=True)[0]
 
 
 def _resnet_forward_impl(self, x):
-    x = self.bn1(self.conv1(x), relu=True)
+    x = _conv_bn(self.conv1, self.bn1, x, relu=True)[0]
     x = self.maxpool(x)
     x = self.layer4(self.layer3(self.layer2(self.layer1(x))))
     x = torch.flatten(self.avgpool(x), 1)
@@ -189,7 +216,10 @@ class _FusedSeq(nn.Sequential):
         i = 0
         while i < len(mods):
             m = mods[i]
-            if isinstance(m, BatchNorm2dB200) and i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU):
+            if i + 1 < len(mods) and _stats_ok(m, mods[i + 1], x):          # conv -> BN [-> ReLU]
+                relu = i + 2 < len(mods) and isinstance(mods[i + 2], nn.ReLU)
+                x = _conv_bn(m, mods[i + 1], x, relu=relu)[0]; i += 3 if relu else 2
+            elif isinstance(m, BatchNorm2dB200) and i + 1 < len(mods) and isinstance(mods[i + 1], nn.ReLU):
                 x = m(x, relu=True); i += 2
             else:
                 x = m(x); i += 1

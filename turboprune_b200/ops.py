@@ -381,17 +381,23 @@ def im2col_stem(x, desc, kp):
     return out
 
 
-def conv_fprop(desc, x_nhwc, wf, bias=None, out=None):
+def conv_fprop(desc, x_nhwc, wf, bias=None, out=None, want_stats=False):
+    """``want_stats``: also return the BatchNorm batch statistics of the output, written by the conv epilogue
+    ([rows, 2, cout] fp32: per 32-pixel group and channel the sum and the sum of squares of the bf16 outputs)."""
     lib = _cabi.load()
     dev = x_nhwc.device
     y = out if out is not None else torch.empty(desc.n, desc.p, desc.q, desc.cout, dtype=torch.bfloat16, device=dev)
+    stats = None
+    if want_stats:
+        stats = torch.empty(int(lib.tp_conv_stats_rows(ctypes.byref(desc))), 2, desc.cout, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev), _Timed("fprop", desc):
-        rc = lib.tp_conv_fprop(ctypes.byref(desc), c_void_p(x_nhwc.data_ptr()), c_void_p(wf.data_ptr()),
-                               c_void_p(bias.data_ptr()) if bias is not None else None, c_void_p(y.data_ptr()),
-                               None, 0, _cabi.stream_ptr(dev))
+        rc = lib.tp_conv_fprop_stats(ctypes.byref(desc), c_void_p(x_nhwc.data_ptr()), c_void_p(wf.data_ptr()),
+                                     c_void_p(bias.data_ptr()) if bias is not None else None, c_void_p(y.data_ptr()),
+                                     c_void_p(stats.data_ptr()) if stats is not None else None,
+                                     None, 0, _cabi.stream_ptr(dev))
     _cabi.check(rc, "tp_conv_fprop")
     _count()
-    return y
+    return (y, stats) if want_stats else y
 
 
 def conv_dgrad(desc, dy_nhwc, wd, addend=None):
@@ -437,10 +443,12 @@ class MaskedConv2dFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, weight, mask, bias, stride, padding, want_skip=False, grad_slots=None, staged=None):
+    def forward(ctx, x, weight, mask, bias, stride, padding, want_skip=False, grad_slots=None, staged=None, want_stats=False):
         _require_cuda(x, weight, mask)
         ctx.set_materialize_grads(False)
         ctx.want_skip = want_skip
+        ctx.want_stats = want_stats
+        stats = None
         # (w_slot, b_slot): persistent arena slots; when given, backward writes dW / db there and returns None for
         # them (no AccumulateGrad add kernel; the slot IS param.grad)
         ctx.grad_slots = grad_slots
@@ -467,7 +475,10 @@ class MaskedConv2dFn(torch.autograd.Function):
             else:
                 wf, wd = stage_weights(w32, m32, 8, False)
             y = empty_cl(n, cout, desc.p, desc.q, x.device)
-            conv_fprop(gdesc, xg, wf, bias, out=y)
+            if want_stats:
+                _, stats = conv_fprop(gdesc, xg, wf, bias, out=y, want_stats=True)
+            else:
+                conv_fprop(gdesc, xg, wf, bias, out=y)
             ctx.mode = "stem"
             ctx.gdesc = gdesc
             ctx.save_for_backward(xg, m32)
@@ -479,7 +490,10 @@ class MaskedConv2dFn(torch.autograd.Function):
             else:
                 wf, wd = stage_weights(w32, m32, cin, need_dx, cout_p)
             y = empty_cl(n, cout, desc.p, desc.q, x.device)
-            conv_fprop(desc, xn, wf, bias, out=y)
+            if want_stats:
+                _, stats = conv_fprop(desc, xn, wf, bias, out=y, want_stats=True)
+            else:
+                conv_fprop(desc, xn, wf, bias, out=y)
             ctx.mode = "conv"
             ctx.save_for_backward(xn, m32, wd)
         ctx.desc = desc
@@ -490,14 +504,22 @@ class MaskedConv2dFn(torch.autograd.Function):
             # second output = the input itself: whatever gradient reaches it (the identity path of a residual
             # block, or a downsample branch) comes back to backward() as ``dskip`` and is accumulated inside
             # the dgrad epilogue instead of by autograd's separate elementwise add
+            if want_stats:
+                ctx.mark_non_differentiable(stats)
+                return y, x, stats
             return y, x
+        if want_stats:
+            ctx.mark_non_differentiable(stats)
+            return y, stats
         return y
 
     @staticmethod
-    def backward(ctx, dy, dskip=None):
+    def backward(ctx, dy, *rest):
+        # outputs were (y [, x_skip] [, stats]); the statistics output is non-differentiable
+        dskip = rest[0] if ctx.want_skip and rest else None
         desc = ctx.desc
         if dy is None:          # only the skip output was used downstream
-            return dskip, None, None, None, None, None, None, None, None
+            return dskip, None, None, None, None, None, None, None, None, None
         cout = desc.cout
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         need_db = ctx.has_bias and ctx.needs_input_grad[3]
@@ -547,11 +569,13 @@ class MaskedConv2dFn(torch.autograd.Function):
             db = dy.float().sum(dim=(0, 2, 3))
         if dskip is not None and dx is None and need_dx is False:
             dx = None
-        return dx, dw, None, db, None, None, None, None, None
+        return dx, dw, None, db, None, None, None, None, None, None
 
 
-def masked_conv2d(x, weight, mask, bias=None, stride=(1, 1), padding=(0, 0), want_skip=False, grad_slots=None, staged=None):
-    return MaskedConv2dFn.apply(x, weight, mask, bias, tuple(stride), tuple(padding), want_skip, grad_slots, staged)
+def masked_conv2d(x, weight, mask, bias=None, stride=(1, 1), padding=(0, 0), want_skip=False, grad_slots=None, staged=None,
+                  want_stats=False):
+    """Returns y, or (y, x_skip) with ``want_skip``, with the BatchNorm statistics tensor appended for ``want_stats``."""
+    return MaskedConv2dFn.apply(x, weight, mask, bias, tuple(stride), tuple(padding), want_skip, grad_slots, staged, want_stats)
 
 
 def masked_linear(x, weight2d, mask2d, bias=None, grad_slots=None, staged=None):

@@ -62,13 +62,15 @@ class ConvMask(_MaskMixin, nn.Conv2d):
         super().__init__(**kwargs)
         self._init_mask()
 
-    def forward(self, x, want_skip=False):
+    def forward(self, x, want_skip=False, want_stats=False):
         """``want_skip=True`` additionally returns ``x`` as a second output whose gradient is accumulated inside
-        this layer's dgrad kernel (used by the fused ResNet block forwards for the identity / downsample paths)."""
+        this layer's dgrad kernel (used by the fused ResNet block forwards for the identity / downsample paths).
+        ``want_stats=True`` appends the BatchNorm batch statistics of the output, computed in the conv epilogue
+        (consumed by the BatchNorm2dB200 that follows: no separate statistics pass over the activation)."""
         self._check_plain()
         if isinstance(self.padding, str):
             raise NotImplementedError("string padding modes")
-        return ops.masked_conv2d(x, self.weight, self.mask, self.bias, _pair(self.stride), _pair(self.padding), want_skip, _slots(self), ops.take_staged(self))
+        return ops.masked_conv2d(x, self.weight, self.mask, self.bias, _pair(self.stride), _pair(self.padding), want_skip, _slots(self), ops.take_staged(self), want_stats)
 
 
 class LinearMask(_MaskMixin, nn.Linear):
