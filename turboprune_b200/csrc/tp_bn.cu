@@ -469,8 +469,13 @@ int tp_bn_forward_ext(const void* y, const void* residual, void* z, int64_t M, i
     // statistics came out of the producing convolution's epilogue: two small folds, no pass over the activation
     const long long groups = (ext_rows + 1023) / 1024;
     if (groups > g.grid_x) return TP_ERR_WORKSPACE;
-    k_bn_fold_ext<<<dim3((C + kFinC - 1) / kFinC, (unsigned)groups), dim3(kFinC, kFinP), 0, st>>>((const float*)ext_stats, ext_rows, C, partial);
-    k_bn_finalize_stats<<<(C + kFinC - 1) / kFinC, dim3(kFinC, kFinP), 0, st>>>(partial, (int)groups, nullptr, M, C,
+    const float* fold_src = (const float*)ext_stats;       // <= 1024 rows: the finalize kernel folds them directly
+    long long fold_rows = ext_rows;
+    if (groups > 1) {
+      k_bn_fold_ext<<<dim3((C + kFinC - 1) / kFinC, (unsigned)groups), dim3(kFinC, kFinP), 0, st>>>((const float*)ext_stats, ext_rows, C, partial);
+      fold_src = partial; fold_rows = groups;
+    }
+    k_bn_finalize_stats<<<(C + kFinC - 1) / kFinC, dim3(kFinC, kFinP), 0, st>>>(fold_src, (int)fold_rows, nullptr, M, C,
                                                           (const float*)weight, (const float*)bias, (float*)running_mean,
                                                           (float*)running_var, (long long*)num_batches_tracked, momentum, eps,
                                                           (float*)save_mean, (float*)save_invstd, scale, shift);
