@@ -84,7 +84,9 @@ int tp_count_zeros(const void* const* m, const int64_t* numel, int n_seg,
  * w, mask: fp32 OIHW [Cout][Cin][R][S].  Cin_p / Cout_p: channel counts padded (zero filled).
  */
 int tp_stage_weights(const void* w, const void* mask, int cout, int cin, int r, int s,
-                     void* wf, int cin_p, void* wd, int cout_p, int cin_p2, void* stream);
+                     void* wf, int cin_p, int wf_ld, void* wd, int cout_p, int cin_p2, void* stream);
+/* wf_ld: elements between consecutive rows of wf (0 = dense, R*S*cin_p); columns past R*S*cin_p are the caller's
+ * zero padding (the 7x7x4 stem GEMM runs with K = 200 for 196 real columns). */
 
 /* The same staging for MANY layers in one launch (the bf16 "weight shadow" refreshed once per optimizer step —
  * SURVEY.md §8(f) row 2; replaces the per-layer mul + cast launches K1/K2 of mask_layers.py:25-34).
@@ -94,7 +96,7 @@ int tp_stage_weights(const void* w, const void* mask, int cout, int cin, int r, 
 typedef struct tp_stage_item {
   const void* w; const void* mask;   /* fp32 OIHW [cout][cin][r][s] */
   void* wf; void* wd;                /* bf16 [cout][r*s*cin_p], bf16 [cin][r*s*cout_p] or NULL */
-  int32_t cout, cin, r, s, cin_p, cout_p;
+  int32_t cout, cin, r, s, cin_p, cout_p, wf_ld;   /* wf_ld: 0 = dense */
 } tp_stage_item;
 size_t tp_stage_batched_workspace_bytes(int n_items);
 int tp_stage_weights_batched(const tp_stage_item* items, int n_items, int table_cached, void* ws, size_t ws_bytes, void* stream);
@@ -112,7 +114,9 @@ int tp_im2col_c8(const void* x, int n, int h, int w, int r, int s, int stride_h,
                  int pad_h, int pad_w, int p, int q, void* xcol, int kp, void* stream);
 
 /* Same expansion straight from the framework's input tensor (src_dtype 0 = fp32, 1 = bf16; element strides; c <= 8):
- * the precision/layout conversion is fused in, the NHWC8 intermediate never exists. */
+ * the precision/layout conversion is fused in, the NHWC8 intermediate never exists.  kp >= r*s*8: 8 channels per tap
+ * (column (r*S+s)*8 + c); r*s*4 <= kp < r*s*8 with c <= 4: 4 channels per tap (column (r*S+s)*4 + c) — half the
+ * matrix for RGB stems. */
 int tp_im2col_stem(const void* src, int src_dtype, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
                    int n, int c, int h, int w, int r, int s, int stride_h, int stride_w, int pad_h, int pad_w,
                    int p, int q, void* xcol, int kp, void* stream);

@@ -559,8 +559,8 @@ def test_batched_weight_staging_matches_per_layer(dev):
         if w.dim() != 4:
             w = w.reshape(w.shape[0], w.shape[1], 1, 1); m = m.reshape(w.shape)
         cout, cin, r, s = w.shape
-        cin_p, cout_p, has_wd = ops._operand_plan(cout, cin, r, s)
-        wf, wd = ops.stage_weights(w.contiguous(), m.contiguous(), cin_p, has_wd, cout_p)
+        cin_p, cout_p, has_wd, wf_ld = ops._operand_plan(cout, cin, r, s)
+        wf, wd = ops.stage_weights(w.contiguous(), m.contiguous(), cin_p, has_wd, cout_p, wf_ld=wf_ld)
         got = ops.take_staged(l)
         assert got is not None and ops.take_staged(l) is None            # consumed exactly once
         assert torch.equal(got[0], wf)

@@ -23,7 +23,7 @@ class ConvDesc(ctypes.Structure):
 
 class StageItem(ctypes.Structure):
     _fields_ = [("w", c_void_p), ("mask", c_void_p), ("wf", c_void_p), ("wd", c_void_p)] + \
-               [(n, c_int32) for n in ("cout", "cin", "r", "s", "cin_p", "cout_p")]
+               [(n, c_int32) for n in ("cout", "cin", "r", "s", "cin_p", "cout_p", "wf_ld")]
 
 
 # name -> (restype, argtypes); every symbol the header declares
@@ -39,7 +39,7 @@ SIGNATURES = {
     "tp_apply_threshold": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                    POINTER(c_int64), c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tp_count_zeros": (c_int, [POINTER(c_void_p), POINTER(c_int64), c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "tp_stage_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_int,
+    "tp_stage_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int,
                                  c_int, c_void_p]),
     "tp_stage_batched_workspace_bytes": (c_size_t, [c_int]),
     "tp_stage_weights_batched": (c_int, [POINTER(StageItem), c_int, c_int, c_void_p, c_size_t, c_void_p]),

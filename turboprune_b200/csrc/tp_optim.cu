@@ -11,7 +11,7 @@ namespace tp {
 // OIHW -> O(RS)I is a small transpose per output channel: stage the [Cin][RS] slab of one
 // output channel through shared memory so both the read and the wf write are coalesced.
 __device__ __forceinline__ void stage_slab(const float* __restrict__ w, const float* __restrict__ mask, int co, int c0, int c1,
-                                           int cin, int rs, __nv_bfloat16* __restrict__ wf, int cin_p,
+                                           int cin, int rs, __nv_bfloat16* __restrict__ wf, int cin_p, int wf_ld,
                                            __nv_bfloat16* __restrict__ wd, int cout_p, bool zero_pad, float* s_slab) {
   const int t = threadIdx.x;
   const long long base = (long long)co * cin * rs;
@@ -25,7 +25,7 @@ __device__ __forceinline__ void stage_slab(const float* __restrict__ w, const fl
   for (int i = t; i < nel; i += blockDim.x) {
     int tap = i / (c1 - c0), c = i % (c1 - c0);
     float v = s_slab[c * rs + tap];
-    wf[((long long)co * rs + tap) * cin_p + c0 + c] = __float2bfloat16_rn(v);
+    wf[(long long)co * wf_ld + tap * cin_p + c0 + c] = __float2bfloat16_rn(v);
   }
   if (wd) {
     for (int i = t; i < nel; i += blockDim.x) {
@@ -39,7 +39,7 @@ __device__ __forceinline__ void stage_slab(const float* __restrict__ w, const fl
     int padn = (cin_p - cin) * rs;
     for (int i = t; i < padn; i += blockDim.x) {
       int tap = i / (cin_p - cin), c = i % (cin_p - cin);
-      wf[((long long)co * rs + tap) * cin_p + cin + c] = __float2bfloat16_rn(0.f);
+      wf[(long long)co * wf_ld + tap * cin_p + cin + c] = __float2bfloat16_rn(0.f);
     }
   }
 }
@@ -47,21 +47,21 @@ __device__ __forceinline__ void stage_slab(const float* __restrict__ w, const fl
 __global__ void __launch_bounds__(256) k_stage_weights(const float* __restrict__ w, const float* __restrict__ mask,
                                                        int cout, int cin, int rs,
                                                        __nv_bfloat16* __restrict__ wf, int cin_p,
-                                                       __nv_bfloat16* __restrict__ wd, int cout_p, int cin_p2) {
+                                                       __nv_bfloat16* __restrict__ wd, int cout_p, int wf_ld) {
   extern __shared__ float s_slab[];       // [cin_chunk][rs] fp32, sized by the host
-  (void)cout; (void)cin_p2;
+  (void)cout;
   // process channels in chunks of CC so the slab fits in smem
   const int CC = (cin + gridDim.y - 1) / gridDim.y;
   const int c0 = blockIdx.y * CC;
   const int c1 = min(cin, c0 + CC);
-  stage_slab(w, mask, blockIdx.x, c0, c1, cin, rs, wf, cin_p, wd, cout_p, true, s_slab);
+  stage_slab(w, mask, blockIdx.x, c0, c1, cin, rs, wf, cin_p, wf_ld, wd, cout_p, true, s_slab);
 }
 
 // All masked layers of a model in ONE launch (54 launches of ~10 us each were 5 % of the per-GPU-batch-64 step).
 // The operand buffers are persistent and zero-initialised by the host, so channel padding is never rewritten.
 struct StageItem {
   const float* w; const float* mask; __nv_bfloat16* wf; __nv_bfloat16* wd;
-  int cout, cin, rs, cin_p, cout_p, ysplit, cc, pad_;
+  int cout, cin, rs, cin_p, cout_p, ysplit, cc, wf_ld;
   long long cta0;                         // first CTA of this layer; CTAs = cout * ysplit
 };
 
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) k_stage_weights_batched(const StageItem* 
   const int co = local / it.ysplit, y = local - co * it.ysplit;
   const int c0 = y * it.cc, c1 = min(it.cin, c0 + it.cc);
   if (co >= it.cout || c0 >= c1) return;
-  stage_slab(it.w, it.mask, co, c0, c1, it.cin, it.rs, it.wf, it.cin_p, it.wd, it.cout_p, false, s_slab);
+  stage_slab(it.w, it.mask, co, c0, c1, it.cin, it.rs, it.wf, it.cin_p, it.wf_ld, it.wd, it.cout_p, false, s_slab);
 }
 
 __global__ void k_zero_bf16(__nv_bfloat16* p, long long n) {
@@ -135,32 +135,41 @@ __global__ void __launch_bounds__(256) k_im2col_c8(const uint4* __restrict__ x, 
 // Stem im2col straight from the framework's input tensor (fp32 or bf16, any strides, c <= 8 channels): fuses the
 // layout/precision conversion (k_to_nhwc) into the expansion, so the 3-channel image is read once and the
 // intermediate NHWC8 copy never exists.  Column (r*S + s)*8 + ch, channels >= c are zero.
-template <typename T>
+template <typename T, int CG>
 __global__ void __launch_bounds__(256) k_im2col_stem(const T* __restrict__ src, long long sn, long long sc, long long sh, long long sw,
                                                      int n, int c, int h, int w, int R, int S, int stride_h, int stride_w,
                                                      int pad_h, int pad_w, int P, int Q, uint4* __restrict__ xcol, int kp8) {
+  // one thread = one 16-byte cell of the matrix = 8 / CG taps of CG channels (CG = 4 when the image has <= 4 channels:
+  // the 7x7 stem matrix is then 200 instead of 392 columns — half the bytes written here and read by the two GEMMs)
+  constexpr int TPC = 8 / CG;
   const long long total = (long long)n * P * Q * kp8;
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long step = (long long)gridDim.x * blockDim.x;
   for (; i < total; i += step) {
     const int cell = (int)(i % kp8);
     const long long pix = i / kp8;
-    uint4 v = make_uint4(0u, 0u, 0u, 0u);
-    if (cell < R * S) {
-      const int r = cell / S, s = cell - r * S;
-      const int q = (int)(pix % Q); const long long t2 = pix / Q;
-      const int pp = (int)(t2 % P); const int ni = (int)(t2 / P);
-      const int hi = pp * stride_h - pad_h + r, wi = q * stride_w - pad_w + s;
-      if (hi >= 0 && hi < h && wi >= 0 && wi < w) {
-        const T* sp = src + ni * sn + hi * sh + wi * sw;
-        float f[8];
+    const int q = (int)(pix % Q); const long long t2 = pix / Q;
+    const int pp = (int)(t2 % P); const int ni = (int)(t2 / P);
+    float f[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) f[j] = j < c ? (float)sp[j * sc] : 0.f;
-        __nv_bfloat162* hv = reinterpret_cast<__nv_bfloat162*>(&v);
+    for (int j = 0; j < 8; ++j) f[j] = 0.f;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) hv[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+    for (int t = 0; t < TPC; ++t) {
+      const int tap = cell * TPC + t;
+      if (tap < R * S) {
+        const int r = tap / S, s_ = tap - r * S;
+        const int hi = pp * stride_h - pad_h + r, wi = q * stride_w - pad_w + s_;
+        if (hi >= 0 && hi < h && wi >= 0 && wi < w) {
+          const T* sp = src + ni * sn + hi * sh + wi * sw;
+#pragma unroll
+          for (int j = 0; j < CG; ++j) if (j < c) f[t * CG + j] = (float)sp[j * sc];
+        }
       }
     }
+    uint4 v;
+    __nv_bfloat162* hv = reinterpret_cast<__nv_bfloat162*>(&v);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) hv[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
     xcol[i] = v;
   }
 }
@@ -216,9 +225,11 @@ using namespace tp;
 extern "C" {
 
 int tp_stage_weights(const void* w, const void* mask, int cout, int cin, int r, int s,
-                     void* wf, int cin_p, void* wd, int cout_p, int cin_p2, void* stream) {
+                     void* wf, int cin_p, int wf_ld, void* wd, int cout_p, int cin_p2, void* stream) {
   if (!w || !mask || !wf || cout <= 0 || cin <= 0 || r <= 0 || s <= 0 || cin_p < cin) return TP_ERR_INVALID;
   if (wd && (cout_p < cout || cin_p2 < cin)) return TP_ERR_INVALID;
+  if (wf_ld <= 0) wf_ld = r * s * cin_p;
+  if (wf_ld < r * s * cin_p) return TP_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   const int rs = r * s;
   // slab of at most 8192 floats (32 KB) per CTA
@@ -234,7 +245,7 @@ int tp_stage_weights(const void* w, const void* mask, int cout, int cin, int r, 
   }
   dim3 grid(cout, ysplit);
   k_stage_weights<<<grid, 256, smem, st>>>((const float*)w, (const float*)mask, cout, cin, rs,
-                                           (__nv_bfloat16*)wf, cin_p, (__nv_bfloat16*)wd, cout_p, cin_p2);
+                                           (__nv_bfloat16*)wf, cin_p, (__nv_bfloat16*)wd, cout_p, wf_ld);
   TP_LAUNCH_CHECK();
   return TP_OK;
 }
@@ -261,7 +272,9 @@ int tp_stage_weights_batched(const tp_stage_item* items, int n_items, int table_
     const int cc = (q.cin + ysplit - 1) / ysplit;
     StageItem& t = h[i];
     t.w = (const float*)q.w; t.mask = (const float*)q.mask; t.wf = (__nv_bfloat16*)q.wf; t.wd = (__nv_bfloat16*)q.wd;
-    t.cout = q.cout; t.cin = q.cin; t.rs = rs; t.cin_p = q.cin_p; t.cout_p = q.cout_p; t.ysplit = ysplit; t.cc = cc; t.pad_ = 0;
+    t.cout = q.cout; t.cin = q.cin; t.rs = rs; t.cin_p = q.cin_p; t.cout_p = q.cout_p; t.ysplit = ysplit; t.cc = cc;
+    t.wf_ld = q.wf_ld > 0 ? q.wf_ld : rs * q.cin_p;
+    if (t.wf_ld < rs * q.cin_p) return TP_ERR_INVALID;
     t.cta0 = cta;
     cta += (long long)q.cout * ysplit;
     const size_t need = (size_t)cc * rs * sizeof(float);
@@ -302,13 +315,18 @@ int tp_im2col_c8(const void* x, int n, int h, int w, int r, int s, int stride_h,
 int tp_im2col_stem(const void* src, int src_dtype, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
                    int n, int c, int h, int w, int r, int s, int stride_h, int stride_w, int pad_h, int pad_w,
                    int p, int q, void* xcol, int kp, void* stream) {
-  if (!src || !xcol || n <= 0 || c <= 0 || c > 8 || kp % 8 != 0 || kp < r * s * 8) return TP_ERR_INVALID;
+  if (!src || !xcol || n <= 0 || c <= 0 || c > 8 || kp % 8 != 0) return TP_ERR_INVALID;
+  // channels per tap: 8, or 4 when the caller sized the matrix for 4-channel taps (kp < r*s*8) and c <= 4
+  int cg = 8;
+  if (kp < r * s * 8) { if (c > 4 || kp < r * s * 4) return TP_ERR_INVALID; cg = 4; }
   cudaStream_t st = (cudaStream_t)stream;
   const long long total = (long long)n * p * q * (kp / 8);
   unsigned grid = (unsigned)min((total + 255) / 256, (long long)sm_count() * 32);
-  if (src_dtype == 0) k_im2col_stem<float><<<grid, 256, 0, st>>>((const float*)src, sn, sc, sh, sw, n, c, h, w, r, s, stride_h, stride_w, pad_h, pad_w, p, q, (uint4*)xcol, kp / 8);
-  else if (src_dtype == 1) k_im2col_stem<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, sn, sc, sh, sw, n, c, h, w, r, s, stride_h, stride_w, pad_h, pad_w, p, q, (uint4*)xcol, kp / 8);
+#define TP_STEM_LAUNCH(T, CG) k_im2col_stem<T, CG><<<grid, 256, 0, st>>>((const T*)src, sn, sc, sh, sw, n, c, h, w, r, s, stride_h, stride_w, pad_h, pad_w, p, q, (uint4*)xcol, kp / 8)
+  if (src_dtype == 0) { if (cg == 8) TP_STEM_LAUNCH(float, 8); else TP_STEM_LAUNCH(float, 4); }
+  else if (src_dtype == 1) { if (cg == 8) TP_STEM_LAUNCH(__nv_bfloat16, 8); else TP_STEM_LAUNCH(__nv_bfloat16, 4); }
   else return TP_ERR_INVALID;
+#undef TP_STEM_LAUNCH
   TP_LAUNCH_CHECK();
   return TP_OK;
 }

@@ -221,19 +221,29 @@ def make_desc(n, h, w, cin, cout, r, s, stride, padding):
     return _cabi.ConvDesc(n, h, w, cin, cout, r, s, sh, sw, ph, pw, p, q)
 
 
-def stage_weights(weight4d, mask4d, cin_p, need_dgrad, cout_p=None):
-    """(mask*w) -> bf16 operand layouts wf [Cout, R*S*cin_p] and (optionally) wd [cin, R*S*cout_p]."""
+def stem_geometry(cin, r, s):
+    """(channels per tap, K of the stem GEMM): taps of 4 channels for images with <= 4 channels, else 8; K padded to 8."""
+    cg = 4 if cin <= 4 else 8
+    return cg, _round_up(r * s * cg, 8)
+
+
+def stage_weights(weight4d, mask4d, cin_p, need_dgrad, cout_p=None, wf_ld=0):
+    """(mask*w) -> bf16 operand layouts wf [Cout, R*S*cin_p] (row stride ``wf_ld`` when given, zero tail) and
+    (optionally) wd [cin, R*S*cout_p]."""
     lib = _cabi.load()
     cout, cin, r, s = weight4d.shape
     dev = weight4d.device
-    wf = torch.empty(cout, r * s * cin_p, dtype=torch.bfloat16, device=dev)
+    if wf_ld and wf_ld > r * s * cin_p:
+        wf = torch.zeros(cout, wf_ld, dtype=torch.bfloat16, device=dev)
+    else:
+        wf = torch.empty(cout, r * s * cin_p, dtype=torch.bfloat16, device=dev)
     wd = None
     cout_p = cout if cout_p is None else cout_p
     if need_dgrad:
         wd = torch.empty(cin, r * s * cout_p, dtype=torch.bfloat16, device=dev)
     with torch.cuda.device(dev):
         rc = lib.tp_stage_weights(c_void_p(weight4d.data_ptr()), c_void_p(mask4d.data_ptr()), cout, cin, r, s,
-                                  c_void_p(wf.data_ptr()), cin_p, c_void_p(wd.data_ptr()) if wd is not None else None,
+                                  c_void_p(wf.data_ptr()), cin_p, int(wf_ld), c_void_p(wd.data_ptr()) if wd is not None else None,
                                   cout_p, cin, _cabi.stream_ptr(dev))
     _cabi.check(rc, "tp_stage_weights")
     _count()
@@ -241,11 +251,15 @@ def stage_weights(weight4d, mask4d, cin_p, need_dgrad, cout_p=None):
 
 
 def _operand_plan(cout, cin, r, s):
-    """(cin_p, cout_p, has_wd) of the bf16 operand layouts a masked layer consumes, or None when the shape is unsupported."""
+    """(cin_p, cout_p, has_wd, wf_ld) of the bf16 operand layouts a masked layer consumes, or None when the shape is
+    unsupported."""
     small_c = (cin % 8 != 0) or (r * s > 1 and cin % 64 != 0)
     if small_c:
-        return (8, cout, False) if cin <= 8 else None        # stem: explicit im2col over 8 padded channels, no dgrad
-    return cin, _round_up(cout, 64 if r * s > 1 else 8), True
+        if cin > 8:
+            return None
+        cg, kp = stem_geometry(cin, r, s)                    # stem: explicit im2col over padded channel groups, no dgrad
+        return cg, cout, False, kp
+    return cin, _round_up(cout, 64 if r * s > 1 else 8), True, r * s * cin
 
 
 class WeightStager:
@@ -282,8 +296,8 @@ class WeightStager:
                 if plan is None or not l.weight.is_cuda or l.weight.dtype != torch.float32 or not l.weight.is_contiguous():
                     self._bufs.append(None)
                     continue
-                cin_p, cout_p, has_wd = plan
-                wf = torch.zeros(cout, r * s * cin_p, dtype=torch.bfloat16, device=dev)
+                cin_p, cout_p, has_wd, wf_ld = plan
+                wf = torch.zeros(cout, wf_ld, dtype=torch.bfloat16, device=dev)
                 wd = torch.zeros(cin, r * s * cout_p, dtype=torch.bfloat16, device=dev) if has_wd else None
                 self._bufs.append((wf, wd, cin_p, cout_p))
         live = [(l, b) for l, b in zip(self.layers, self._bufs) if b is not None]
@@ -292,7 +306,7 @@ class WeightStager:
             cout, cin, r, s = self._shape4(l)
             it.w = l.weight.data_ptr(); it.mask = l.mask.data_ptr()
             it.wf = wf.data_ptr(); it.wd = wd.data_ptr() if wd is not None else None
-            it.cout, it.cin, it.r, it.s, it.cin_p, it.cout_p = cout, cin, r, s, cin_p, cout_p
+            it.cout, it.cin, it.r, it.s, it.cin_p, it.cout_p, it.wf_ld = cout, cin, r, s, cin_p, cout_p, wf.shape[1]
         self._items, self._live, self._key = items, live, key
         if self._ws is None:
             lib = _cabi.load()
@@ -466,14 +480,14 @@ class MaskedConv2dFn(torch.autograd.Function):
                 raise NotImplementedError(f"masked conv with Cin={cin} (not a multiple of 64) and a {r}x{s} filter")
             if need_dx:
                 raise NotImplementedError("input gradient of a small-channel stem convolution")
-            # stem conv: pad channels to 8, explicit im2col, then a plain GEMM
-            kp = r * s * 8
+            # stem conv: pad channels to a group of 4 or 8 per tap, explicit im2col, then a plain GEMM
+            cg, kp = stem_geometry(cin, r, s)
             xg = im2col_stem(x, desc, kp)
             gdesc = _cabi.ConvDesc(n * desc.p * desc.q, 1, 1, kp, cout, 1, 1, 1, 1, 0, 0, 1, 1)
             if staged is not None and staged[0].shape == (cout, kp):
                 wf, wd = staged
             else:
-                wf, wd = stage_weights(w32, m32, 8, False)
+                wf, wd = stage_weights(w32, m32, cg, False, wf_ld=kp)
             y = empty_cl(n, cout, desc.p, desc.q, x.device)
             if want_stats:
                 _, stats = conv_fprop(gdesc, xg, wf, bias, out=y, want_stats=True)
@@ -533,8 +547,9 @@ class MaskedConv2dFn(torch.autograd.Function):
                 ones = torch.ones(cout, xg.shape[1], dtype=torch.float32, device=xg.device)
                 gd = ctx.gdesc
                 dwm, db = conv_wgrad(gd, xg, dyn.view(-1, cout), ones.view(cout, -1, 1, 1), xg.shape[1], need_db)
-                # columns are (tap, c8): back to OIHW and apply the mask (9.4 k elements)
-                dw = dwm.view(cout, r * s, 8)[:, :, :cin].permute(0, 2, 1).reshape(cout, cin, r, s) * m32
+                # columns are (tap, channel group): back to OIHW and apply the mask (9.4 k elements)
+                cg = stem_geometry(cin, r, s)[0]
+                dw = dwm[:, :r * s * cg].reshape(cout, r * s, cg)[:, :, :cin].permute(0, 2, 1).reshape(cout, cin, r, s) * m32
         else:
             xn, m32, wd = ctx.saved_tensors
             ddesc = desc
