@@ -86,7 +86,7 @@ int tp_count_zeros(const void* const* m, const int64_t* numel, int n_seg,
 int tp_stage_weights(const void* w, const void* mask, int cout, int cin, int r, int s,
                      void* wf, int cin_p, int wf_ld, void* wd, int cout_p, int cin_p2, void* stream);
 /* wf_ld: elements between consecutive rows of wf (0 = dense, R*S*cin_p); columns past R*S*cin_p are the caller's
- * zero padding (the 7x7x4 stem GEMM runs with K = 200 for 196 real columns). */
+ * zero padding (the 7x7x3 stem GEMM runs with K = 152 for 147 real columns). */
 
 /* The same staging for MANY layers in one launch (the bf16 "weight shadow" refreshed once per optimizer step —
  * SURVEY.md §8(f) row 2; replaces the per-layer mul + cast launches K1/K2 of mask_layers.py:25-34).
@@ -113,12 +113,12 @@ int tp_to_nhwc_bf16(const void* src, int src_dtype, int64_t sn, int64_t sc, int6
 int tp_im2col_c8(const void* x, int n, int h, int w, int r, int s, int stride_h, int stride_w,
                  int pad_h, int pad_w, int p, int q, void* xcol, int kp, void* stream);
 
-/* Same expansion straight from the framework's input tensor (src_dtype 0 = fp32, 1 = bf16; element strides; c <= 8):
- * the precision/layout conversion is fused in, the NHWC8 intermediate never exists.  kp >= r*s*8: 8 channels per tap
- * (column (r*S+s)*8 + c); r*s*4 <= kp < r*s*8 with c <= 4: 4 channels per tap (column (r*S+s)*4 + c) — half the
- * matrix for RGB stems. */
+/* The expansion straight from the framework's input tensor (src_dtype 0 = fp32, 1 = bf16; element strides; c <= 8):
+ * the precision/layout conversion is fused in, no NHWC intermediate exists.  cg (c <= cg <= 8) = channels per tap:
+ * column (r*S+s)*cg + ch, zero for ch >= c and for columns >= r*s*cg; kp % 8 == 0, kp >= r*s*cg.  The RGB stem uses
+ * cg = 3: K = 152 instead of 392 columns. */
 int tp_im2col_stem(const void* src, int src_dtype, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
-                   int n, int c, int h, int w, int r, int s, int stride_h, int stride_w, int pad_h, int pad_w,
+                   int n, int c, int h, int w, int r, int s, int cg, int stride_h, int stride_w, int pad_h, int pad_w,
                    int p, int q, void* xcol, int kp, void* stream);
 
 /* ---- masked implicit-GEMM convolution / linear on tcgen05 tensor cores -----------------

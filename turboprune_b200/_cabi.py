@@ -46,7 +46,7 @@ SIGNATURES = {
     "tp_to_nhwc_bf16": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int,
                                 c_void_p, c_int, c_void_p]),
     "tp_im2col_c8": (c_int, [c_void_p] + [c_int] * 11 + [c_void_p, c_int, c_void_p]),
-    "tp_im2col_stem": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64] + [c_int] * 12 + [c_void_p, c_int, c_void_p]),
+    "tp_im2col_stem": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64] + [c_int] * 13 + [c_void_p, c_int, c_void_p]),
     "tp_conv_workspace_bytes": (c_size_t, [POINTER(ConvDesc), c_int]),
     "tp_conv_fprop": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tp_conv_stats_rows": (c_size_t, [POINTER(ConvDesc)]),

@@ -135,13 +135,23 @@ __global__ void __launch_bounds__(256) k_im2col_c8(const uint4* __restrict__ x, 
 // Stem im2col straight from the framework's input tensor (fp32 or bf16, any strides, c <= 8 channels): fuses the
 // layout/precision conversion (k_to_nhwc) into the expansion, so the 3-channel image is read once and the
 // intermediate NHWC8 copy never exists.  Column (r*S + s)*8 + ch, channels >= c are zero.
-template <typename T, int CG>
+template <typename T>
 __global__ void __launch_bounds__(256) k_im2col_stem(const T* __restrict__ src, long long sn, long long sc, long long sh, long long sw,
-                                                     int n, int c, int h, int w, int R, int S, int stride_h, int stride_w,
+                                                     int n, int c, int h, int w, int R, int S, int cg, int stride_h, int stride_w,
                                                      int pad_h, int pad_w, int P, int Q, uint4* __restrict__ xcol, int kp8) {
-  // one thread = one 16-byte cell of the matrix = 8 / CG taps of CG channels (CG = 4 when the image has <= 4 channels:
-  // the 7x7 stem matrix is then 200 instead of 392 columns — half the bytes written here and read by the two GEMMs)
-  constexpr int TPC = 8 / CG;
+  // one thread = one 16-byte cell (8 consecutive columns) of the matrix; column e = tap * cg + channel.  The
+  // (row offset, column offset, channel) of every column is decoded once per CTA into shared memory, so the inner
+  // loop has no divisions.  cg = channels per tap: the RGB stem uses cg = 3 (K = 152 for 147 real columns) instead
+  // of padding every tap to 8 channels (K = 392) — the matrix written here and read by two GEMMs shrinks 2.6x.
+  extern __shared__ uint32_t s_col[];                  // [kp8 * 8]: dh << 16 | dw << 8 | ch, or ~0u for padding columns
+  const int kp = kp8 * 8;
+  for (int e = threadIdx.x; e < kp; e += blockDim.x) {
+    uint32_t v = 0xFFFFFFFFu;
+    const int tap = e / cg, ch = e - tap * cg;
+    if (tap < R * S && ch < c) { const int r = tap / S, s_ = tap - r * S; v = ((uint32_t)r << 16) | ((uint32_t)s_ << 8) | (uint32_t)ch; }
+    s_col[e] = v;
+  }
+  __syncthreads();
   const long long total = (long long)n * P * Q * kp8;
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long step = (long long)gridDim.x * blockDim.x;
@@ -150,21 +160,15 @@ __global__ void __launch_bounds__(256) k_im2col_stem(const T* __restrict__ src, 
     const long long pix = i / kp8;
     const int q = (int)(pix % Q); const long long t2 = pix / Q;
     const int pp = (int)(t2 % P); const int ni = (int)(t2 / P);
+    const int h0 = pp * stride_h - pad_h, w0 = q * stride_w - pad_w;
+    const T* base = src + ni * sn;
     float f[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) f[j] = 0.f;
-#pragma unroll
-    for (int t = 0; t < TPC; ++t) {
-      const int tap = cell * TPC + t;
-      if (tap < R * S) {
-        const int r = tap / S, s_ = tap - r * S;
-        const int hi = pp * stride_h - pad_h + r, wi = q * stride_w - pad_w + s_;
-        if (hi >= 0 && hi < h && wi >= 0 && wi < w) {
-          const T* sp = src + ni * sn + hi * sh + wi * sw;
-#pragma unroll
-          for (int j = 0; j < CG; ++j) if (j < c) f[t * CG + j] = (float)sp[j * sc];
-        }
-      }
+    for (int j = 0; j < 8; ++j) {
+      const uint32_t cd = s_col[cell * 8 + j];
+      const int hi = h0 + (int)(cd >> 16), wi = w0 + (int)((cd >> 8) & 0xFF);
+      f[j] = 0.f;
+      if (cd != 0xFFFFFFFFu && hi >= 0 && hi < h && wi >= 0 && wi < w) f[j] = (float)base[hi * sh + wi * sw + (long long)(cd & 0xFF) * sc];
     }
     uint4 v;
     __nv_bfloat162* hv = reinterpret_cast<__nv_bfloat162*>(&v);
@@ -313,20 +317,19 @@ int tp_im2col_c8(const void* x, int n, int h, int w, int r, int s, int stride_h,
 }
 
 int tp_im2col_stem(const void* src, int src_dtype, int64_t sn, int64_t sc, int64_t sh, int64_t sw,
-                   int n, int c, int h, int w, int r, int s, int stride_h, int stride_w, int pad_h, int pad_w,
+                   int n, int c, int h, int w, int r, int s, int cg, int stride_h, int stride_w, int pad_h, int pad_w,
                    int p, int q, void* xcol, int kp, void* stream) {
-  if (!src || !xcol || n <= 0 || c <= 0 || c > 8 || kp % 8 != 0) return TP_ERR_INVALID;
-  // channels per tap: 8, or 4 when the caller sized the matrix for 4-channel taps (kp < r*s*8) and c <= 4
-  int cg = 8;
-  if (kp < r * s * 8) { if (c > 4 || kp < r * s * 4) return TP_ERR_INVALID; cg = 4; }
+  if (!src || !xcol || n <= 0 || c <= 0 || c > 8 || cg < c || cg > 8 || kp % 8 != 0 || kp < r * s * cg) return TP_ERR_INVALID;
+  if (r > 255 || s > 255 || kp > 8192) return TP_ERR_UNSUPPORTED;
   cudaStream_t st = (cudaStream_t)stream;
   const long long total = (long long)n * p * q * (kp / 8);
   unsigned grid = (unsigned)min((total + 255) / 256, (long long)sm_count() * 32);
-#define TP_STEM_LAUNCH(T, CG) k_im2col_stem<T, CG><<<grid, 256, 0, st>>>((const T*)src, sn, sc, sh, sw, n, c, h, w, r, s, stride_h, stride_w, pad_h, pad_w, p, q, (uint4*)xcol, kp / 8)
-  if (src_dtype == 0) { if (cg == 8) TP_STEM_LAUNCH(float, 8); else TP_STEM_LAUNCH(float, 4); }
-  else if (src_dtype == 1) { if (cg == 8) TP_STEM_LAUNCH(__nv_bfloat16, 8); else TP_STEM_LAUNCH(__nv_bfloat16, 4); }
+  const size_t smem = (size_t)kp * sizeof(uint32_t);
+  if (src_dtype == 0)
+    k_im2col_stem<float><<<grid, 256, smem, st>>>((const float*)src, sn, sc, sh, sw, n, c, h, w, r, s, cg, stride_h, stride_w, pad_h, pad_w, p, q, (uint4*)xcol, kp / 8);
+  else if (src_dtype == 1)
+    k_im2col_stem<__nv_bfloat16><<<grid, 256, smem, st>>>((const __nv_bfloat16*)src, sn, sc, sh, sw, n, c, h, w, r, s, cg, stride_h, stride_w, pad_h, pad_w, p, q, (uint4*)xcol, kp / 8);
   else return TP_ERR_INVALID;
-#undef TP_STEM_LAUNCH
   TP_LAUNCH_CHECK();
   return TP_OK;
 }

@@ -222,8 +222,9 @@ def make_desc(n, h, w, cin, cout, r, s, stride, padding):
 
 
 def stem_geometry(cin, r, s):
-    """(channels per tap, K of the stem GEMM): taps of 4 channels for images with <= 4 channels, else 8; K padded to 8."""
-    cg = 4 if cin <= 4 else 8
+    """(channels per tap, K of the stem GEMM): no channel padding inside a tap (cg = cin); K padded to a multiple of 8
+    (the RGB 7x7 stem: 147 -> 152 columns)."""
+    cg = cin
     return cg, _round_up(r * s * cg, 8)
 
 
@@ -378,8 +379,8 @@ def empty_cl(n, c, h, w, device):
     return torch.empty((n, c, h, w), dtype=torch.bfloat16, device=device, memory_format=torch.channels_last)
 
 
-def im2col_stem(x, desc, kp):
-    """[N, C<=8, H, W] fp32/bf16 (any strides) -> [N*P*Q, kp] bf16 im2col matrix, conversion fused in."""
+def im2col_stem(x, desc, kp, cg):
+    """[N, C<=8, H, W] fp32/bf16 (any strides) -> [N*P*Q, kp] bf16 im2col matrix (column tap*cg + channel), conversion fused in."""
     lib = _cabi.load()
     n, c, h, w = x.shape
     if x.dtype not in (torch.float32, torch.bfloat16):
@@ -388,7 +389,7 @@ def im2col_stem(x, desc, kp):
     sn, sc, sh, sw = x.stride()
     with torch.cuda.device(x.device):
         rc = lib.tp_im2col_stem(c_void_p(x.data_ptr()), 0 if x.dtype == torch.float32 else 1, sn, sc, sh, sw, n, c, h, w,
-                                desc.r, desc.s, desc.stride_h, desc.stride_w, desc.pad_h, desc.pad_w, desc.p, desc.q,
+                                desc.r, desc.s, cg, desc.stride_h, desc.stride_w, desc.pad_h, desc.pad_w, desc.p, desc.q,
                                 c_void_p(out.data_ptr()), kp, _cabi.stream_ptr(x.device))
     _cabi.check(rc, "tp_im2col_stem")
     _count()
@@ -482,7 +483,7 @@ class MaskedConv2dFn(torch.autograd.Function):
                 raise NotImplementedError("input gradient of a small-channel stem convolution")
             # stem conv: pad channels to a group of 4 or 8 per tap, explicit im2col, then a plain GEMM
             cg, kp = stem_geometry(cin, r, s)
-            xg = im2col_stem(x, desc, kp)
+            xg = im2col_stem(x, desc, kp, cg)
             gdesc = _cabi.ConvDesc(n * desc.p * desc.q, 1, 1, kp, cout, 1, 1, 1, 1, 0, 0, 1, 1)
             if staged is not None and staged[0].shape == (cout, kp):
                 wf, wd = staged
