@@ -5,7 +5,9 @@ Capture (one GPU, never a timing run):
 sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,lts__throughput.avg.pct_of_peak_sustained_elapsed \
       --clock-control none -k regex:k_igemm --csv --log-file gpurun_out/igemm_metrics.csv \
       python bench.py --steps 1 --warmup 1 --no-graph --no-cpu-baseline --no-e2e --no-topk
-usage: python tools/igemm_traffic.py gpurun_out/igemm_metrics.csv profiles/r01_igemm_traffic.json [launches_per_step=170]
+usage: python tools/igemm_traffic.py gpurun_out/igemm_metrics.csv profiles/r01_igemm_traffic.json [launches_per_step=170] [skip_tail=54]
+(skip_tail: bench.py ends with one batch-2 eval forward that only measures tensor shapes — 54 tiny fprop launches after
+the last train step)
 """
 import collections, csv, json, re, sys
 
@@ -16,6 +18,7 @@ UNIT = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us":
 def main():
     src, dst = sys.argv[1], sys.argv[2]
     per_step = int(sys.argv[3]) if len(sys.argv) > 3 else 170
+    skip_tail = int(sys.argv[4]) if len(sys.argv) > 4 else 54
     lines = [l for l in open(src, newline="") if not l.startswith("==")]
     launches = collections.OrderedDict()
     for r in csv.DictReader(lines):
@@ -23,7 +26,8 @@ def main():
             continue
         d = launches.setdefault(int(r["ID"]), {"name": re.sub(r"\(.*", "", r["Kernel Name"]).replace("tp::", "").strip()})
         d[r["Metric Name"]] = float(r["Metric Value"].replace(",", "")) * UNIT.get(r["Metric Unit"], 1.0)
-    last = list(launches.values())[-per_step:]
+    allv = list(launches.values())
+    last = allv[len(allv) - skip_tail - per_step: len(allv) - skip_tail]
     agg = collections.OrderedDict()
     for d in last:
         a = agg.setdefault(d["name"], collections.defaultdict(float))
