@@ -49,8 +49,32 @@ class ClockSampler:
         self.index = index
         self.proc = None
         self.lines = []
+        self.nv = []            # in-process NVML samples (sm MHz, max MHz, reasons bitmask): every 10 ms, so even a
+        self._stop = False      # 0.2 s timed region (8 GPUs x batch 64) is sampled; nvidia-smi -lms stays as the fallback
+
+    def _nvml_loop(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            try:
+                import torch
+                uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+                h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:
+                h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            mx = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self._stop:
+                self.nv.append((pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM), mx,
+                                int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))))
+                time.sleep(0.01)
+        except Exception:
+            pass
 
     def start(self):
+        try:
+            self.tn = threading.Thread(target=self._nvml_loop, daemon=True); self.tn.start()
+        except Exception:
+            pass
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -63,13 +87,25 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        self._stop = True
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                self.proc.kill()
+        if self.nv:
+            # NVML throttle-reason bits: 0x4 sw_power_cap, 0x8 hw_slowdown, 0x20 sw_thermal_slowdown, 0x40 hw_thermal_slowdown
+            bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+            sm_sorted = sorted(v[0] for v in self.nv)
+            loaded = sm_sorted[len(sm_sorted) // 3:] or sm_sorted
+            allbits = 0
+            for v in self.nv:
+                allbits |= v[2]
+            return {"sm_mhz": float(statistics.median(loaded)), "sm_max_mhz": float(self.nv[0][1]),
+                    "reasons": sorted(n for b, n in bits.items() if allbits & b), "samples": len(self.nv), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except Exception:
-            self.proc.kill()
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
