@@ -134,3 +134,17 @@ def test_config_composer_and_densities():
         assert c.dataset_params.total_batch_size == 512 and generate_densities(c, 0.0) == [1 - 0.8]
         c = C.compose("imagenet_er_balanced", ["pruning_params=iterative_wr", "pruning_params.target_sparsity=0.988"], ref_conf)
         assert len(generate_densities(c, 0.0)) == 21
+
+
+def test_operand_planning_of_the_weight_shadow():
+    """Host-side layout decisions shared by the per-layer staging and the one-launch WeightStager."""
+    from turboprune_b200 import ops
+    assert ops.stem_geometry(3, 7, 7) == (3, 152)            # RGB 7x7 stem: 147 real columns, K padded to 8
+    assert ops.stem_geometry(3, 3, 3) == (3, 32)             # CIFAR stem
+    assert ops.stem_geometry(8, 3, 3) == (8, 72)
+    assert ops._operand_plan(64, 3, 7, 7) == (3, 64, False, 152)          # stem: no dgrad operand
+    assert ops._operand_plan(64, 64, 3, 3) == (64, 64, True, 576)
+    assert ops._operand_plan(96, 64, 3, 3) == (64, 128, True, 576)        # multi-tap backward walks Cout in 64-blocks
+    assert ops._operand_plan(1000, 2048, 1, 1) == (2048, 1000, True, 2048)
+    assert ops._operand_plan(10, 512, 1, 1) == (512, 16, True, 512)
+    assert ops._operand_plan(32, 12, 3, 3) is None                        # 9..63 channels with k > 1: unsupported layout
