@@ -148,3 +148,42 @@ def test_operand_planning_of_the_weight_shadow():
     assert ops._operand_plan(1000, 2048, 1, 1) == (2048, 1000, True, 2048)
     assert ops._operand_plan(10, 512, 1, 1) == (512, 16, True, 512)
     assert ops._operand_plan(32, 12, 3, 3) is None                        # 9..63 channels with k > 1: unsupported layout
+
+
+def test_device_resident_checkpoint_cache(tmp_path, monkeypatch):
+    """save_model keeps a clone of what it wrote; load_model / reset_weights are served from it while the file on
+    disk is still the one written (format on disk unchanged), and fall back to torch.load otherwise."""
+    import refshim
+    from turboprune_b200.utils import custom_models as cm, harness_utils as hu
+    torch.manual_seed(0)
+    model = cm.TorchVisionModel(refshim.make_cfg("resnet18", "cifar10"))
+    ck = tmp_path / "checkpoints"; ck.mkdir()
+    path = str(ck / "model_init.pt")
+    hu.save_model(model, path)
+    on_disk = torch.load(path)
+    want = {k: v.clone() for k, v in model.model.state_dict().items()}
+    assert set(on_disk) == set(want) and all(torch.equal(on_disk[k], want[k]) for k in want)      # same file format / content
+    with torch.no_grad():
+        for p_ in model.parameters():
+            p_.add_(1.0)
+    calls = []
+    real_load = torch.load
+    monkeypatch.setattr(torch, "load", lambda *a, **k: (calls.append(a), real_load(*a, **k))[1])
+    model.load_model(path)
+    assert not calls                                                     # served from the cache
+    assert all(torch.equal(v, want[k]) for k, v in model.model.state_dict().items())
+    cfg = refshim.make_cfg("resnet18", "cifar10"); cfg.pruning_params.training_type = "imp"
+    with torch.no_grad():
+        for p_ in model.parameters():
+            p_.mul_(0.5)
+    model.reset_weights(cfg, str(tmp_path))
+    assert not calls
+    assert all(torch.equal(v, want[k]) for k, v in model.model.state_dict().items() if not k.endswith("mask"))
+    # a file rewritten behind our back is not served from the cache
+    other = {k: torch.zeros_like(v) for k, v in want.items()}
+    real_save = torch.save
+    real_save(other, path)
+    os.utime(path, ns=(1, 1))
+    model.load_model(path)
+    assert len(calls) == 1
+    assert all(float(v.abs().sum()) == 0 for v in model.model.state_dict().values())

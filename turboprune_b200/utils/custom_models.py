@@ -90,7 +90,8 @@ class PruneModel(nn.Module):
 
     # ---- checkpoints -------------------------------------------------------------------------
     def load_model(self, load_path):
-        self.model.load_state_dict(torch.load(load_path))
+        from .harness_utils import load_checkpoint
+        self.model.load_state_dict(load_checkpoint(load_path))
 
     def reset_weights(self, cfg, expt_dir: str) -> None:
         kind = cfg.pruning_params.training_type
@@ -100,7 +101,8 @@ class PruneModel(nn.Module):
             ckpt = "model_rewind.pt"
         else:
             return                                        # LRR / pruning at init: nothing to rewind
-        saved = torch.load(os.path.join(expt_dir, "checkpoints", ckpt))
+        from .harness_utils import load_checkpoint
+        saved = load_checkpoint(os.path.join(expt_dir, "checkpoints", ckpt))
         live = self.model.state_dict()
         for name, tensor in saved.items():
             if name in live and live[name].shape == tensor.shape and not name.endswith("mask"):
@@ -112,7 +114,8 @@ class PruneModel(nn.Module):
             m.mask.fill_(1)
 
     def load_only_masks(self, load_path: str):
-        saved = torch.load(load_path)
+        from .harness_utils import load_checkpoint
+        saved = load_checkpoint(load_path)
         live = self.model.state_dict()
         for name, tensor in saved.items():
             if name in live and live[name].shape == tensor.shape and name.endswith("mask"):

@@ -68,7 +68,45 @@ def unwrap(model):
     return m.model
 
 
+# ---- device-resident checkpoint cache ------------------------------------------------------
+# The level loop re-reads checkpoints it wrote moments earlier: model_level_{L-1}.pt at the start of level L and
+# model_init.pt / model_rewind.pt at every rewind (run_experiment.py:96-105 of the reference: a torch.load + H2D of the
+# whole state dict each time, 20+ levels).  The on-disk files and their format are unchanged; save_model additionally
+# keeps a clone of what it wrote on the model's device, and load_checkpoint serves it as long as the file is still the
+# one that was written (same size and mtime).  A few entries suffice: init / rewind / previous level.
+_CKPT_CACHE = {}
+_CKPT_CACHE_MAX = 4
+
+
+def _file_key(path):
+    st = os.stat(path)
+    return (st.st_size, st.st_mtime_ns)
+
+
+def load_checkpoint(path):
+    """``torch.load(path)`` semantics, served from the device-resident cache when this process wrote the file."""
+    ap = os.path.abspath(path)
+    hit = _CKPT_CACHE.get(ap)
+    if hit is not None:
+        try:
+            if _file_key(ap) == hit[0]:
+                return hit[1]
+        except OSError:
+            pass
+        _CKPT_CACHE.pop(ap, None)
+    return torch.load(path)
+
+
 def save_model(model, save_path, distributed: bool = False) -> None:
     """State dict of the INNER torchvision net: keys ``conv1.weight``, ``conv1.mask`` ... (checkpoint compatible)."""
-    torch.save(unwrap(model).state_dict(), save_path)
+    sd = unwrap(model).state_dict()
+    torch.save(sd, save_path)
+    try:
+        ap = os.path.abspath(save_path)
+        _CKPT_CACHE.pop(ap, None)
+        while len(_CKPT_CACHE) >= _CKPT_CACHE_MAX:
+            _CKPT_CACHE.pop(next(iter(_CKPT_CACHE)))                 # oldest entry
+        _CKPT_CACHE[ap] = (_file_key(ap), {k: v.detach().clone() for k, v in sd.items()})
+    except OSError:
+        pass
     print(f"Model saved to {save_path}")
