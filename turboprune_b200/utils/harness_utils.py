@@ -105,7 +105,9 @@ def save_model(model, save_path, distributed: bool = False) -> None:
         ap = os.path.abspath(save_path)
         _CKPT_CACHE.pop(ap, None)
         while len(_CKPT_CACHE) >= _CKPT_CACHE_MAX:
-            _CKPT_CACHE.pop(next(iter(_CKPT_CACHE)))                 # oldest entry
+            # evict the oldest per-level checkpoint first: model_init.pt / model_rewind.pt are re-read at every level
+            levels = [k for k in _CKPT_CACHE if os.path.basename(k).startswith("model_level_")]
+            _CKPT_CACHE.pop(levels[0] if levels else next(iter(_CKPT_CACHE)))
         _CKPT_CACHE[ap] = (_file_key(ap), {k: v.detach().clone() for k, v in sd.items()})
     except OSError:
         pass
