@@ -5,9 +5,10 @@
     python bench.py --gpus N --steps K --warmup W            (N>1: launched by torchrun, one rank per GPU)
     python bench.py --impl reference ...                      (the reference's CPU path = oracle port, host cores)
 
-One "step" = one pass of the hot path over one batch: H2D (e2e only) -> zero_grad -> autocast forward through
-the sm_100a masked-conv kernels -> CE loss -> backward (dgrad/wgrad kernels, mask fused in wgrad) -> P2P gradient
-mean over NVLink (N>1) -> fused SGD.  Nothing is skipped in the timed region.
+One "step" = one ``PruningHarness.train_step`` call over one batch (the product's own step, not a copy of it):
+H2D (e2e only) -> zero_grad -> autocast forward through the sm_100a masked-conv kernels -> CE loss -> backward
+(dgrad/wgrad kernels, mask fused in wgrad) -> P2P gradient mean over NVLink under the backward pass (N>1) -> fused SGD
+-> LR scheduler step.  Nothing is skipped in the timed region.
 
 Output: ONE JSON line (see the task contract): value = whole-job images/s with inputs resident in HBM,
 e2e = the same through the public API with pinned-host inputs copied every step and the loss read back,
@@ -131,14 +132,20 @@ def triangular_lr(total_steps, warmup_fraction=0.2):
     return np.interp(np.arange(1 + total_steps), [0, int(warmup_fraction * total_steps), total_steps], [0.2, 1, 0])
 
 
+def host_threads():
+    """Thread count of the CPU arm: set explicitly (torchrun exports OMP_NUM_THREADS=1, and torch's default differs
+    between boxes), physical cores = logical CPUs // 2, capped at 64."""
+    n = os.cpu_count() or 2
+    return max(1, min(64, n // 2))
+
+
 def cpu_train_step_rate(batch, steps, warmup, threads=None):
     """The reference's CPU path (oracle port): RN50 ERK-80 train step, bf16 autocast, on host cores."""
     import torch
     import oracle.model as om
     from oracle import prune as OP
     from oracle.train import train_step
-    if threads:
-        torch.set_num_threads(threads)
+    torch.set_num_threads(threads or host_threads())
     torch.manual_seed(0)
     net = om.build("resnet50", "imagenet")
     torch.manual_seed(1)
@@ -161,21 +168,97 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ.pop("OMP_NUM_THREADS", None)          # torchrun sets it to 1 for every rank; the CPU arm owns the box
     batch = 16
     steps = max(1, min(args.steps, 40))
-    rate, s_per_step, threads = cpu_train_step_rate(batch, steps, max(1, min(args.warmup, 2)))
+    warm = max(3, min(args.warmup, 3))
+    rate, s_per_step, threads = cpu_train_step_rate(batch, steps, warm, host_threads())
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": "images/s", "n_gpus": args.gpus,
-        "steps": steps, "warmup": max(1, min(args.warmup, 2)), "ms_per_step": s_per_step * 1e3,
+        "steps": steps, "warmup": warm, "ms_per_step": s_per_step * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": "resnet50 imagenet-shape ERK-80% masked train step (reference CPU path, oracle port)",
-                   "global_batch": batch, "sample": f"batch {batch} per step on host cores"},
+                   "global_batch": batch, "sample": f"batch {batch} per step on host cores", "threads": threads},
         "cpu_baseline": {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
-                         "sample": f"{steps} steps of batch {batch} (torch CPU, bf16 autocast), os.cpu_count()={os.cpu_count()}"},
+                         "sample": f"{steps} steps of batch {batch} after {warm} warm-up steps (torch CPU, bf16 autocast), "
+                                   f"torch.set_num_threads({threads}), os.cpu_count()={os.cpu_count()}"},
         "e2e": {"value": rate, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
     print(json.dumps(line), flush=True)
+
+
+def gpu_eager_reference(dev, B, steps, world):
+    """The kernels to beat: the reference's own GPU execution model — cuDNN convs on mask*w, ATen
+    BatchNorm / ReLU, torch.optim.SGD under bf16 autocast (the oracle's module graph moved to cuda), ATen kthvalue on
+    the concatenated scores (pruning_utils.py:75-79), NCCL all_reduce of the 102 MB gradient (world > 1)."""
+    import torch
+    import torch.distributed as dist
+    from oracle import model as OM, prune as OP
+    out = {}
+    torch.manual_seed(0)
+    ref = OM.build("resnet50", "imagenet")
+    probs = OP.erk_keep_probabilities([tuple(m.weight.shape) for _, m in OM.masked_layers(ref)], 0.2)
+    torch.manual_seed(1)
+    OM.set_er_masks(ref, probs)
+    ref = ref.to(dev).to(memory_format=torch.channels_last).train()
+    opt = torch.optim.SGD(ref.parameters(), lr=0.2, momentum=0.9, weight_decay=1e-4)
+    g = torch.Generator(device=dev).manual_seed(2)
+    x = torch.randn(B, 3, 224, 224, device=dev, generator=g).contiguous(memory_format=torch.channels_last)
+    t = torch.randint(0, 1000, (B,), device=dev, generator=g)
+    prev = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
+
+    def ref_step():
+        opt.zero_grad()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = torch.nn.functional.cross_entropy(ref(x), t)
+        loss.backward()
+        opt.step()
+    for _ in range(3):
+        ref_step()
+    torch.cuda.synchronize(dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        ref_step()
+    b.record(); torch.cuda.synchronize(dev)
+    ms = a.elapsed_time(b) / steps
+    out["cudnn_eager_train_step"] = {"ms_per_step": ms, "images_per_s": B / ms * 1e3, "batch": B,
+                                     "what": "F.conv2d(x, mask*w) on cuDNN + ATen BN/ReLU + torch.optim.SGD, bf16 autocast, channels_last, cudnn.benchmark"}
+    # ATen kthvalue + where on the same 25.5 M scores (reference prune_mag, pruning_utils.py:73-87)
+    layers = [m for _, m in OM.masked_layers(ref)]
+    n = sum(m.weight.numel() for m in layers); k = int((1 - 0.2) * n)
+    ones = [torch.ones_like(m.weight) for m in layers]
+
+    def aten_prune():
+        scores = torch.cat([(mk * m.weight).detach().abs().flatten() for m, mk in zip(layers, ones)])
+        thr, _ = torch.kthvalue(scores, k)
+        return [torch.where((mk * m.weight).detach().abs() <= thr, 0.0, 1.0) for m, mk in zip(layers, ones)]
+    aten_prune(); torch.cuda.synchronize(dev)
+    ts = []
+    for _ in range(3):
+        a.record(); aten_prune(); b.record(); torch.cuda.synchronize(dev)
+        ts.append(a.elapsed_time(b))
+    out["aten_prune_mag"] = {"us": statistics.median(ts) * 1e3, "elements": n,
+                             "GBps_on_12B_per_elem": 12.0 * n / (statistics.median(ts) / 1e3) / 1e9,
+                             "what": "per-layer abs(mask*w), torch.cat, torch.kthvalue, per-layer torch.where"}
+    del ref, opt, layers, ones
+    torch.backends.cudnn.benchmark = prev
+    torch.cuda.empty_cache()
+    if world > 1:
+        buf = torch.randn(25_557_032, device=dev)
+        for _ in range(3):
+            dist.all_reduce(buf)
+        torch.cuda.synchronize(dev); dist.barrier()
+        a.record()
+        for _ in range(10):
+            dist.all_reduce(buf)
+        b.record(); torch.cuda.synchronize(dev)
+        us = torch.tensor([a.elapsed_time(b) / 10 * 1e3], device=dev)
+        dist.all_reduce(us, op=dist.ReduceOp.MAX)
+        out["nccl_allreduce_102MB"] = {"us": float(us.item()), "busbw_GBps": 2 * 25_557_032 * 4 * (world - 1) / world / (float(us.item()) / 1e6) / 1e9}
+    return out
 
 
 def main():
@@ -189,17 +272,20 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-topk", action="store_true")
+    ap.add_argument("--no-gpu-eager", action="store_true", help="skip the cuDNN / ATen / NCCL 'kernels to beat' sub-record")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the train step into a CUDA graph")
+    ap.add_argument("--no-overlap", action="store_true", help="launch the gradient exchange after the backward pass")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
+    import tempfile
     import torch
     import torch.distributed as dist
-    from refshim import make_cfg
     from turboprune_b200 import ops
-    from turboprune_b200.optim import FusedSGD
-    from turboprune_b200.utils import custom_models as cm, pruning_utils as pu
+    from turboprune_b200.harness_definitions.standard_pruning_harness import PruningHarness
+    from turboprune_b200.utils import config as tp_config, custom_models as cm, pruning_utils as pu
+    from turboprune_b200.utils.dataset import DevicePrefetcher, SyntheticLoader
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -208,62 +294,40 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    W = max(1, args.warmup)
+    W = max(3, args.warmup)
     K = max(1, args.steps)
     B = args.per_gpu_batch or max(1, args.global_batch // world)
     scaling = "weak" if args.per_gpu_batch else "strong"
-
-    # ---- model: seed-0 ResNet-50, ERK-80 % Bernoulli masks (identical on every rank by construction) ----
-    torch.manual_seed(0)
-    model = cm.TorchVisionModel(make_cfg("resnet50", "imagenet", precision="bfloat16"))
-    torch.manual_seed(1)
-    pu.prune_er_erk(model, 0.2)
-    model = model.to(dev).train()
-    sparsity = model.get_overall_sparsity()
     use_graph = not args.no_graph
-    opt = FusedSGD(model.parameters(), lr=0.2, momentum=0.9, weight_decay=1e-4, capturable=use_graph)
-    sched_tab = triangular_lr(10 * (W + K) * 3)
-    reducer = None
-    if world > 1:
-        from turboprune_b200.grad_exchange import P2PGradReducer
-        reducer = P2PGradReducer(list(model.parameters()))
 
-    gen = torch.Generator(device=dev).manual_seed(1000 * 0 + rank)
-    pool = [(torch.randn(B, 3, 224, 224, device=dev, generator=gen).contiguous(memory_format=torch.channels_last),
-             torch.randint(0, 1000, (B,), device=dev, generator=gen)) for _ in range(2)]
-    step_idx = [0]
+    # ---- BASELINE.json config 2 through the product surface: the composed config, TorchVisionModel, prune_er_erk,
+    # ---- PruningHarness (its train_step owns gradient arena / weight shadow / P2P reducer / CUDA graph) ----
+    total_steps = 3 * (W + K) + 16
+    cfg = tp_config.compose("synthetic_rn50_erk80", [
+        f"dataset_params.total_batch_size={B * world}", f"dataset_params.synthetic_steps_per_epoch={total_steps}",
+        "+dataset_params.synthetic_fresh=true", "optimizer_params.weight_decay=1e-4",
+        f"experiment_params.distributed={'true' if world > 1 else 'false'}",
+        f"+experiment_params.cuda_graph={'true' if use_graph else 'false'}",
+        f"experiment_params.base_dir={tempfile.gettempdir()}"], os.path.join(ROOT, "conf_b200"))
+    torch.manual_seed(0)
+    model = cm.TorchVisionModel(cfg)             # seed-0 ResNet-50
+    torch.manual_seed(1)
+    pu.prune_er_erk(model, 0.2)                  # ERK-80 % Bernoulli masks (identical on every rank by construction)
+    harness = PruningHarness(cfg=cfg, gpu_id=rank, expt_dir=("bench", tempfile.gettempdir()), model=model)
+    model = harness.model
+    model.train()
+    sparsity = model.get_overall_sparsity()
+    harness._setup_optimizer()
+    harness._setup_scheduler(1)                  # TriangularSchedule over total_steps, stepped per iteration like train_epoch
+    if harness.distributed and args.no_overlap:
+        harness._ensure_reducer(); harness.reducer.overlap = False
     loss_acc = torch.zeros((), device=dev)
+    batches = iter(harness.train_loader)         # fresh Philox batch per step, generated on the device
 
-    def set_lr():
-        for g in opt.param_groups:
-            g["lr"] = 0.2 * float(sched_tab[min(step_idx[0], len(sched_tab) - 1)])
-        step_idx[0] += 1
-        if use_graph:
-            opt.sync_lr()                      # device scalar: the captured step reads it, nothing is baked in
-
-    from turboprune_b200.grad_exchange import GradArena
-    arena = reducer if reducer is not None else GradArena(list(model.parameters()))
-    from turboprune_b200 import ops as _ops
-    from turboprune_b200.utils.mask_layers import MASKED_LAYER_TYPES
-    stager = _ops.WeightStager([m for m in model.modules() if isinstance(m, MASKED_LAYER_TYPES)])
-
-    def step_body(x, t):
-        arena.zero()                           # one memset; grads live in persistent slots (stable pointers)
-        stager.stage()                         # bf16(mask*w) operands of all 54 layers: one launch
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            out = model(x)
-            loss = torch.nn.functional.cross_entropy(out, t)
-        loss.backward()
-        if reducer is not None:
-            reducer.reduce()
-        opt.step()
-        return loss
-
-    def eager_step(x, t):
-        set_lr()
-        return step_body(x, t)
-
-    step = eager_step
+    def step(batch):
+        out = harness.train_step(batch)["loss"]
+        harness.scheduler.step()
+        return out
 
     def barrier():
         if world > 1:
@@ -283,57 +347,35 @@ def main():
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return float(ms.item())
 
-    # ---- warm-up (eager): allocates workspaces, sets kernel attributes, fills momentum buffers ----
-    for i in range(W):
-        step(*pool[i % 2])
-    launches_per_step = 0
-    if True:
-        l0 = ops.launch_count(); step(*pool[0]); launches_per_step = ops.launch_count() - l0
-
-    # ---- capture ONE whole train step (fwd + bwd + P2P reduce + SGD) into a CUDA graph ----
-    graph = None
-    if use_graph:
-        static_x, static_t = torch.empty_like(pool[0][0]), torch.empty_like(pool[0][1])
-        static_x.copy_(pool[0][0]); static_t.copy_(pool[0][1])
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for _ in range(2):
-                eager_step(static_x, static_t)
-        torch.cuda.current_stream(dev).wait_stream(side)
-        barrier()
-        graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, capture_error_mode="thread_local"):
-            static_loss = step_body(static_x, static_t)
-
-        def graph_step(x, t):
-            static_x.copy_(x, non_blocking=True); static_t.copy_(t, non_blocking=True)
-            set_lr()
-            graph.replay()
-            return static_loss
-        step = graph_step
-        for i in range(2):
-            step(*pool[i % 2])
+    # ---- warm-up: W steps through harness.train_step (the third one captures the CUDA graph) ----
+    l0 = ops.launch_count()
+    step(next(batches))
+    launches_per_step = ops.launch_count() - l0  # kernel-launching C-ABI calls of one (eager) step; the graph replays the same kernels
+    for i in range(max(W, 4) - 1):
+        step(next(batches))
+    assert (harness._graph is not None) == use_graph
 
     # ---- device-resident run (value) ----
     clocks = ClockSampler(local_rank); clocks.start()
 
     def dev_step(i):
-        loss_acc.add_(step(*pool[i % 2]).detach())
+        loss_acc.add_(step(next(batches)))
     ms_total = timed(K, dev_step)
     launches = launches_per_step * K
     clk = clocks.stop()
-    if reducer is not None:
-        reducer.check_status()
+    if harness.reducer is not None:
+        harness.reducer.check_status()
     img_s = world * B * K / (ms_total / 1e3)
 
     # ---- per-kernel timing of the masked GEMMs: CUDA events around every C-ABI conv call on the launching stream
-    # (eager steps of the same workload — events cannot be read back from inside a replayed graph) ----
+    # (eager steps of the same workload through the same harness — events cannot be read back from inside a replayed graph) ----
     timer = ops.KernelTimer()
     KT = min(K, 5)
+    cfg.experiment_params["cuda_graph"] = False
     ops.set_timer(timer)
-    ms_eager = timed(KT, lambda i: eager_step(*pool[i % 2]))
+    ms_eager = timed(KT, lambda i: step(next(batches)))
     ops.set_timer(None)
+    cfg.experiment_params["cuda_graph"] = use_graph
     tot = timer.totals()
     gemm_ms = sum(v[0] for v in tot.values()) * (K / KT)
     pk = peaks()
@@ -345,9 +387,10 @@ def main():
     hooks = []
     for name, m in model._masked():
         hooks.append(m.register_forward_hook(lambda mod, inp, out, name=name: io.__setitem__(name, (inp[0].numel(), (out[0] if isinstance(out, tuple) else out).numel()))))
+    probe = torch.randn(2, 3, 224, 224, device=dev).contiguous(memory_format=torch.channels_last)
     model.eval()
     with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
-        model(pool[0][0][:2])
+        model(probe)
     model.train()
     for h in hooks:
         h.remove()
@@ -356,19 +399,21 @@ def main():
     alg_bytes_step = 2.0 * per_img / 2 * B
     achieved_gbs = alg_bytes_step * K / (gemm_ms / 1e3) / 1e9 if gemm_ms > 0 else 0.0
     traffic = None
-    tpath = os.path.join(ROOT, "profiles", "r01_igemm_traffic.json")
+    tpath = os.path.join(ROOT, "profiles", "r02_igemm_traffic.json")
+    if not os.path.isfile(tpath):
+        tpath = os.path.join(ROOT, "profiles", "r01_igemm_traffic.json")
     if os.path.isfile(tpath) and B == 512:
         traffic = json.load(open(tpath))["dram_bytes_per_launch"]
     n_launch = sum(v[2] for v in tot.values()) / KT
     roofline = {"bound": "hbm", "achieved": achieved_gbs, "peak": pk["hbm"], "unit": "GB/s",
                 "frac": achieved_gbs / pk["hbm"], "traffic": traffic,
-                "traffic_note": "dram read+write per igemm kernel launch, ncu over one eager step at B=512 (profiles/r01_igemm_traffic.json)" if traffic else None,
+                "traffic_note": f"dram read+write per igemm kernel launch, ncu over one eager step at B=512 ({os.path.relpath(tpath, ROOT)})" if traffic else None,
                 "peak_source": pk["src"] + " HBM copy bandwidth",
                 "kernel": "k_igemm_fwd (fprop+dgrad) / k_igemm_wgrad — masked implicit GEMM, tcgen05 + TMA",
                 "why_hbm": "sum over the 54 layers: conv I/O bytes / HBM peak (11.4 ms at B=512) exceeds FLOPs / tensor peak (8.5 ms); 30 of 54 layers are HBM-bound",
                 "algorithmic_bytes_per_step": alg_bytes_step, "algorithmic_bytes_per_launch": alg_bytes_step / n_launch,
                 "launches_per_step": n_launch,
-                "timing": f"CUDA events around each masked-GEMM C-ABI call over {KT} eager steps ({ms_eager / KT:.2f} ms/step eager); step rate from CUDA-graph replay" if use_graph else "CUDA events, eager",
+                "timing": f"CUDA events around each masked-GEMM C-ABI call over {KT} eager harness.train_step calls ({ms_eager / KT:.2f} ms/step eager); step rate from the harness's CUDA-graph replay" if use_graph else "CUDA events, eager",
                 "ms_per_step_in_kernel": gemm_ms / K,
                 "by_op_ms_per_step": {k: v[0] / KT for k, v in tot.items()},
                 "share_of_step": gemm_ms / ms_total,
@@ -376,86 +421,100 @@ def main():
                            "flops_per_step": GFLOP_PER_IMG * 1e9 * B, "peak_source": pk["src"] + " sustained bf16"},
                 "frac_of_masked_gemm_roofline_img_s": (img_s / world) / ROOFLINE_IMG_S}
 
-    # ---- end-to-end run: pinned host inputs copied every step, loss read back every step ----
+    # ---- end-to-end run: pinned host batches -> DevicePrefetcher (copy stream, double-buffered) -> harness.train_step,
+    # ---- loss read back every step like the reference's loss.item() (base_harness.py:134) ----
     e2e = None
     if not args.no_e2e:
-        hpool = [(torch.randn(B, 3, 224, 224).pin_memory(), torch.randint(0, 1000, (B,)).pin_memory()) for _ in range(2)]
+        hg = torch.Generator().manual_seed(7 + rank)
+        hpool = [(torch.randn(B, 224, 224, 3, generator=hg).pin_memory().permute(0, 3, 1, 2),
+                  torch.randint(0, 1000, (B,), generator=hg).pin_memory()) for _ in range(2)]
         h2d = hpool[0][0].numel() * 4 + hpool[0][1].numel() * 8
 
-        # double-buffered prefetch: batch i+1 crosses PCIe on a copy stream while step i computes
-        copy_stream = torch.cuda.Stream(dev)
-        stage = [(torch.empty_like(pool[0][0]), torch.empty_like(pool[0][1])) for _ in range(2)]
-        h2d_done = [torch.cuda.Event() for _ in range(2)]
-        consumed = [torch.cuda.Event() for _ in range(2)]
+        class HostLoader:
+            def __init__(self, n): self.n = n
+            def __len__(self): return self.n
+            def __iter__(self):
+                for i in range(self.n):
+                    yield hpool[i % 2]
 
-        def prefetch(i):
-            j = i % 2
-            with torch.cuda.stream(copy_stream):
-                copy_stream.wait_event(consumed[j])
-                stage[j][0].copy_(hpool[j][0], non_blocking=True); stage[j][1].copy_(hpool[j][1], non_blocking=True)
-                h2d_done[j].record(copy_stream)
-
-        for ev in consumed:
-            ev.record(torch.cuda.current_stream(dev))
-
-        def e2e_step(i):
-            j = i % 2
-            if i == 0:
-                prefetch(0)
-            torch.cuda.current_stream(dev).wait_event(h2d_done[j])
-            prefetch(i + 1)                                   # overlaps with this step's compute
-            loss = step(stage[j][0], stage[j][1])
-            consumed[j].record(torch.cuda.current_stream(dev))
-            return float(loss.item())                         # the reference returns loss.item() every step (base_harness.py:134)
-        for i in range(2):
-            e2e_step(i)
+        def run_e2e(n):
+            for batch in DevicePrefetcher(HostLoader(n), dev):
+                float(step(batch).item())
+        run_e2e(2)
         torch.cuda.synchronize(dev)
-        ms_e2e = timed(K, e2e_step)
+        ms_e2e = timed(1, lambda i: run_e2e(K))
         e2e = {"value": world * B * K / (ms_e2e / 1e3), "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-               "ms_per_step": ms_e2e / K}
+               "ms_per_step": ms_e2e / K, "api": "DevicePrefetcher(pinned host batches) -> PruningHarness.train_step -> loss.item()"}
 
-    # ---- mask top-k (second half of the metric): prune_mag over the model's 25.5 M masked weights ----
+    # ---- mask top-k (second half of the metric): prune_mag over the model's 25.5 M masked weights, and the
+    # ---- VGG-16-sized SynFlow select (134.7 M elements, 16 B/elem) ----
     topk = None
     if not args.no_topk and rank == 0:
+        def time_plan(plan, k, reps=10):
+            for _ in range(3):
+                plan.run(k)
+            flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
+            tms, info = [], None
+            for _ in range(reps):
+                flush.zero_()                                  # 256 MiB write: evicts the 126 MB L2
+                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record(); _, _, info = plan.run(k); b.record(); torch.cuda.synchronize(dev)
+                tms.append(a.elapsed_time(b))
+            del flush
+            return statistics.median(tms), info
         layers = [m for _, m in model._masked()]
         ws = [m.weight.detach() for m in layers]; ms_ = [torch.ones_like(m.mask) for m in layers]
         n = sum(w.numel() for w in ws); k = int((1 - 0.2) * n)
-        plan = ops.TopKPlan(ws, ms_)                       # pointer tables marshalled once: the timed call is the C-ABI call
-        for _ in range(3):
-            plan.run(k)
-        reps = 10
-        flush = torch.empty(64 * 1024 * 1024, dtype=torch.float32, device=dev)
-        tms = []
-        for _ in range(reps):
-            flush.zero_()                                  # 256 MiB write: evicts the 126 MB L2
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(); _, _, info = plan.run(k); b.record(); torch.cuda.synchronize(dev)
-            tms.append(a.elapsed_time(b))
-        tmed = statistics.median(tms)
+        tmed, info = time_plan(ops.TopKPlan(ws, ms_), k)      # pointer tables marshalled once: the timed call is the C-ABI call
         gbs = 12.0 * n / (tmed / 1e3) / 1e9
         topk = {"metric": "mask_topk_GBps", "elements": n, "k": k, "algorithmic_bytes": 12 * n, "ms": tmed, "GBps": gbs,
                 "roofline": {"bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"], "traffic": None},
                 "path": info["path"], "candidates": info["candidates"], "l2": "flushed between reps"}
-        del flush
+        del ms_
+        n2, nseg = 134_657_728, 16
+        sizes = [n2 // nseg] * (nseg - 1); sizes.append(n2 - sum(sizes))
+        g2 = torch.Generator(device=dev).manual_seed(11)
+        w2 = [torch.randn(s_, device=dev, generator=g2).abs_() * 0.02 for s_ in sizes]
+        gr2 = [torch.randn(s_, device=dev, generator=g2) * 1e-3 for s_ in sizes]
+        m2 = [torch.ones(s_, device=dev) for s_ in sizes]
+        t2, info2 = time_plan(ops.TopKPlan(w2, m2, gs=gr2, kind=2), int(0.95 * n2), reps=5)
+        gbs2 = 16.0 * n2 / (t2 / 1e3) / 1e9
+        topk["synflow_vgg16_size"] = {"elements": n2, "k": int(0.95 * n2), "algorithmic_bytes": 16 * n2, "ms": t2, "GBps": gbs2,
+                                      "frac_of_hbm_peak": gbs2 / pk["hbm"], "path": info2["path"], "candidates": info2["candidates"]}
+        del w2, gr2, m2
+        torch.cuda.empty_cache()
+
+    gpu_eager = None
+    if not args.no_gpu_eager:
+        try:
+            gpu_eager = gpu_eager_reference(dev, B, min(K, 5), world)
+        except Exception as e:           # the comparison arm must never take the bench line down
+            gpu_eager = {"error": repr(e)[:200]}
+        if gpu_eager and "cudnn_eager_train_step" in gpu_eager:
+            gpu_eager["speedup_vs_cudnn_eager"] = gpu_eager["cudnn_eager_train_step"]["ms_per_step"] / (ms_total / K)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        rate, s_per_step, threads = cpu_train_step_rate(16, 6, 1)
+        rate, s_per_step, threads = cpu_train_step_rate(16, 6, 2, host_threads())
         cpu = {"value": rate, "unit": "images/s", "cores": threads, "kind": "port",
-               "sample": f"6 steps of batch 16 of the same workload (oracle port, torch CPU bf16 autocast, {s_per_step:.2f} s/step), "
-                         f"os.cpu_count()={os.cpu_count()}"}
+               "sample": f"6 steps of batch 16 of the same workload after 2 warm-up steps (oracle port, torch CPU bf16 autocast, {s_per_step:.2f} s/step), "
+                         f"torch.set_num_threads({threads}), os.cpu_count()={os.cpu_count()}"}
 
     if rank == 0:
         line = {
             "metric": METRIC, "value": img_s, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "resnet50 imagenet-shape [B,3,224,224] ERK-80% unstructured masks, SGD(0.9, wd 1e-4), CE loss",
+            "config": {"workload": "resnet50 imagenet-shape [B,3,224,224] ERK-80% unstructured masks, SGD(0.9, wd 1e-4), CE loss, TriangularSchedule",
                        "global_batch": B * world, "per_gpu_batch": B, "parallelism": f"dp{world}",
+                       "api": "PruningHarness.train_step (conf_b200/synthetic_rn50_erk80.yaml)",
+                       "inputs": "fresh Philox batch generated on the device every step (generation inside the timed region)",
                        "sparsity_percent": sparsity, "cuda_graph": bool(use_graph), "l2": "inputs (308 MB/batch at B=512) and activations exceed the 126 MB L2",
-                       "grad_exchange": "none (1 GPU)" if world == 1 else "tp_p2p_allreduce_mask over symmetric memory (NVLink), no NCCL on the data path"},
+                       "grad_exchange": "none (1 GPU)" if world == 1 else
+                       ("tp_p2p_allreduce over symmetric memory (NVLink), per-bucket on a side stream under the backward pass, mask applied in the kernel; no NCCL on the data path"
+                        + ("" if not args.no_overlap else " [overlap disabled]"))},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
-            "topk": topk, "loss_mean": float(loss_acc.item()) / K,
+            "topk": topk, "reference_gpu_eager": gpu_eager, "loss_mean": float(loss_acc.item()) / K,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

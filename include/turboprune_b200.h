@@ -228,8 +228,16 @@ int tp_p2p_allreduce_mask(void* const* peer_bufs, void* const* signal_pads, int 
                           int64_t numel, const void* mask, float scale, void* out,
                           int algo, int timeout_ms, int* status_dev, void* stream);
 
-/* ---- development probes (used by tests/ and tools/, not by the training path) ---------- */
-int tp_probe_run(int which, void* out, size_t out_bytes, void* stream);
+/* NVLS variant of the two-shot schedule: the reduction and the broadcast happen inside the NVSwitch.
+ *   multicast_buf : DEVICE pointer — the multicast mapping of the same symmetric bucket (element 0 of the bucket's
+ *                   data, e.g. torch symmetric memory's `multicast_ptr` + the signal-pad bytes); rank r issues
+ *                   multimem.ld_reduce.add.v4.f32 on shard r, scales / masks, multimem.st's the result to all replicas.
+ * Every replica receives the value rank r computed (replicas stay bit-identical); the switch, not this kernel,
+ * fixes the order of the W-term sum, so against tp_p2p_allreduce_mask the result may differ in the last bit for W > 2.
+ */
+int tp_p2p_allreduce_nvls(void* const* peer_bufs, void* const* signal_pads, void* multicast_buf, int rank, int world,
+                          int64_t numel, const void* mask, float scale, void* out,
+                          int timeout_ms, int* status_dev, void* stream);
 
 #ifdef __cplusplus
 }

@@ -151,12 +151,27 @@ def gen_prune():
         for m in layers:
             m.mask = torch.ones_like(m.weight)
         net.train()
+        # prune_synflow calls model.zero_grad() after scoring (pruning_utils.py:270): wrap THIS instance's method (the
+        # reference source stays untouched) so the gradients and the linearised |w| it scored are captured first
+        captured = {}
+        real_zero_grad = net.zero_grad
+
+        def capturing_zero_grad(*a, **k):
+            if all(m.weight.grad is not None for m in layers):
+                captured["g"] = [m.weight.grad.detach().numpy().copy() for m in layers]
+                captured["w"] = [m.weight.detach().numpy().copy() for m in layers]
+            return real_zero_grad(*a, **k)
+        net.zero_grad = capturing_zero_grad
         with cuda_as_cpu():
             fn(cfg, net, loader, 0.5)
+        del net.zero_grad
         for i, m in enumerate(layers):
-            out[f"{tag}.g{i}"] = (m.weight.grad.numpy().copy() if m.weight.grad is not None else np.zeros(m.weight.shape, np.float32))
+            if tag == "synflow":
+                out[f"{tag}.g{i}"] = captured["g"][i]
+                out[f"{tag}.absw{i}"] = captured["w"][i]          # |w| at scoring time (signs restored afterwards)
+            else:
+                out[f"{tag}.g{i}"] = (m.weight.grad.numpy().copy() if m.weight.grad is not None else np.zeros(m.weight.shape, np.float32))
         snap(tag)
-    # synflow gradient is zeroed by the reference (model.zero_grad) -> regenerate its grads for the fixture
     # random criteria (torch generator stream is part of the contract)
     for tag, fn in [("rand_erk", pu.prune_random_erk), ("rand_bal", pu.prune_random_balanced)]:
         net.load_state_dict(init)

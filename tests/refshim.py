@@ -104,3 +104,15 @@ def make_cfg(model_name="resnet18", dataset="cifar10", mask_layer_type="ConvMask
     for k, v in extra.items():
         cfg[k] = v
     return Cfg(cfg)
+
+
+def make_harness(cfg, model, batch, tmp_dir=None):
+    """A PruningHarness (the product's train-step surface, reference standard_pruning_harness.py:28-50) around a
+    prebuilt wrapper model, with the optimizer of ``cfg.optimizer_params`` — what run_experiment.py builds per level."""
+    import tempfile
+    from turboprune_b200.harness_definitions.standard_pruning_harness import PruningHarness
+    cfg["dataset_params"]["total_batch_size"] = batch
+    cfg["dataset_params"]["synthetic_steps_per_epoch"] = 2
+    h = PruningHarness(cfg=cfg, gpu_id=0, expt_dir=("test", tmp_dir or tempfile.gettempdir()), model=model)
+    h._setup_optimizer()
+    return h

@@ -136,6 +136,30 @@ def test_config_composer_and_densities():
         assert len(generate_densities(c, 0.0)) == 21
 
 
+def test_cli_override_floats_parse_like_hydra():
+    """'5e-4' / '1e-1' on the command line are floats for hydra; PyYAML alone would hand the harness strings."""
+    from turboprune_b200.utils import config as C
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = C.compose("synthetic_rn18_imp", ["optimizer_params.weight_decay=5e-4", "optimizer_params.lr=1e-1",
+                                           "+pruning_params.rewind_epoch=2", "model_params.model_name=resnet50"],
+                    os.path.join(root, "conf_b200"))
+    assert cfg.optimizer_params.weight_decay == 5e-4 and isinstance(cfg.optimizer_params.weight_decay, float)
+    assert cfg.optimizer_params.lr == 0.1 and cfg.pruning_params.rewind_epoch == 2 and cfg.model_params.model_name == "resnet50"
+
+
+def test_mask_epoch_counts_new_mask_tensors():
+    """Captured graphs / pointer tables key on it: assigning a mask bumps it, in-place edits and other attributes do not."""
+    from turboprune_b200.utils import mask_layers as ml
+    m = ml.ConvMask(in_channels=8, out_channels=8, kernel_size=1)
+    e0 = ml.mask_epoch()
+    m.mask.fill_(0.0); m.weight.data.mul_(2); m.foo = 1
+    assert ml.mask_epoch() == e0
+    m.set_er_mask(0.5)
+    assert ml.mask_epoch() == e0 + 1
+    m.mask = torch.ones_like(m.weight)
+    assert ml.mask_epoch() == e0 + 2 and "mask" in dict(m.named_buffers())
+
+
 def test_operand_planning_of_the_weight_shadow():
     """Host-side layout decisions shared by the per-layer staging and the one-launch WeightStager."""
     from turboprune_b200 import ops
@@ -147,7 +171,10 @@ def test_operand_planning_of_the_weight_shadow():
     assert ops._operand_plan(96, 64, 3, 3) == (64, 128, True, 576)        # multi-tap backward walks Cout in 64-blocks
     assert ops._operand_plan(1000, 2048, 1, 1) == (2048, 1000, True, 2048)
     assert ops._operand_plan(10, 512, 1, 1) == (512, 16, True, 512)
-    assert ops._operand_plan(32, 12, 3, 3) is None                        # 9..63 channels with k > 1: unsupported layout
+    assert ops._operand_plan(32, 12, 3, 3) == (64, 64, True, 576)         # 9..63 channels with k > 1: zero-padded to 64
+    assert ops._operand_plan(24, 16, 1, 1) == (16, 24, True, 16)
+    assert ops._operand_plan(10, 10, 1, 1) == (16, 16, True, 16)          # a 1x1 / linear needs 16-byte rows only
+    assert ops.padded_cin(3, 1, 1) == 8 and ops.padded_cin(65, 3, 3) == 128 and ops.padded_cin(256, 3, 3) == 256
 
 
 def test_device_resident_checkpoint_cache(tmp_path, monkeypatch):

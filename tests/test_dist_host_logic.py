@@ -38,6 +38,24 @@ def _worker(rank, world, port, q):
         ddp = mine / world
         dist.all_reduce(ddp, op=dist.ReduceOp.SUM)
         assert np.array_equal(ours, (ddp * mask).numpy())
+        # pruning on every rank + rank-0 broadcast: rank-dependent masks (what SNIP on per-rank batches gives) end up
+        # identical everywhere and equal to rank 0's (the reference prunes on rank 0 and lets DDP broadcast)
+        import torch.nn as nn
+        from turboprune_b200.utils import mask_layers as ml, pruning_utils as pu
+        torch.manual_seed(0)
+        net = nn.Sequential(ml.ConvMask(in_channels=8, out_channels=16, kernel_size=3), ml.Conv1dMask(16, 10, bias=True))
+        torch.manual_seed(10 + rank)
+        for m in net:
+            m.mask = (torch.rand_like(m.weight) < 0.5).float()
+        mine0 = [m.mask.clone() for m in net]
+        pu.sync_masks_from_rank0(net)
+        flat = torch.cat([m.mask.reshape(-1) for m in net])
+        got = [torch.empty_like(flat) for _ in range(world)]
+        dist.all_gather(got, flat)
+        assert all(torch.equal(got[0], t) for t in got)
+        if rank == 0:
+            assert all(torch.equal(a, m.mask) for a, m in zip(mine0, net))
+        assert all(m.mask.shape == m.weight.shape and m.mask.dtype == torch.float32 for m in net)
         q.put((rank, "ok"))
     except Exception as e:      # pragma: no cover
         q.put((rank, repr(e)))

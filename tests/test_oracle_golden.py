@@ -84,9 +84,9 @@ def test_prune_mag_levels_bit_exact(prune_npz):
 @pytest.mark.parametrize("tag,kind", [("snip", P.SCORE_SNIP), ("synflow", P.SCORE_SYNFLOW)])
 def test_prune_grad_scores_bit_exact(prune_npz, tag, kind):
     z = prune_npz
-    if tag == "synflow":
-        pytest.skip("the reference zeroes the gradients (model.zero_grad) before returning; covered live on the GPU")
-    ws = _ws(z)
+    # synflow scores the linearised |w| with the gradients the reference held right before its model.zero_grad()
+    # (pruning_utils.py:263-270); make_golden.py captures both from the running reference
+    ws = [z[f"synflow.absw{i}"] for i in range(4)] if tag == "synflow" else _ws(z)
     gs = [z[f"{tag}.g{i}"] for i in range(4)]
     ms = [np.ones_like(w) for w in ws]
     new, thr, k = P.prune_global(ws, ms, 0.5, gs=gs, kind=kind)

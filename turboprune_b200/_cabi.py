@@ -68,7 +68,8 @@ SIGNATURES = {
                                c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tp_maxpool_forward": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [c_void_p]),
     "tp_maxpool_backward": (c_int, [c_void_p, c_void_p, c_void_p] + [c_int] * 9 + [c_void_p]),
-    "tp_probe_run": (c_int, [c_int, c_void_p, c_size_t, c_void_p]),
+    "tp_p2p_allreduce_nvls": (c_int, [POINTER(c_void_p), POINTER(c_void_p), c_void_p, c_int, c_int, c_int64, c_void_p, c_float,
+                                      c_void_p, c_int, c_void_p, c_void_p]),
 }
 
 

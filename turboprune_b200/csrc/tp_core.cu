@@ -95,7 +95,7 @@ const char* tp_strerror(int code) {
 }
 
 const char* tp_last_cuda_error(void) { return tp::g_last_err; }
-int tp_abi_version(void) { return 6; }
+int tp_abi_version(void) { return 7; }
 int tp_device_sm_count(void) { return tp::sm_count(); }
 
 size_t tp_segtable_workspace_bytes(int n_seg) {

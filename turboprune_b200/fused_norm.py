@@ -81,6 +81,7 @@ class _BNFn(torch.autograd.Function):
             gr = gr.to(ctx.res_dtype)
         if direct:
             dweight = dbias = None
+            ops.grad_ready(ws_, bs_)
         return gx, gr, dweight, dbias, None, None, None, None, None, None, None, None, None
 
 
@@ -91,12 +92,14 @@ class BatchNorm2dB200(nn.BatchNorm2d):
         """``ext_stats``: batch statistics of ``x`` already computed by the producing convolution's epilogue."""
         training = self.training or not self.track_running_stats
         # eval-mode BN inside an autograd graph is not on the hot path: leave it to torch
-        if not x.is_cuda or x.shape[1] % 8 != 0 or (not training and torch.is_grad_enabled() and x.requires_grad):
+        # momentum=None means a cumulative moving average in torch (factor 1/num_batches_tracked): not on the hot path
+        if (not x.is_cuda or x.shape[1] % 8 != 0 or (not training and torch.is_grad_enabled() and x.requires_grad)
+                or (self.momentum is None and training and self.track_running_stats)):
             y = super().forward(x)
             if residual is not None:
                 y = y + residual
             return torch.relu(y) if relu else y
-        momentum = 0.1 if self.momentum is None else self.momentum
+        momentum = 0.0 if self.momentum is None else self.momentum
         slots = grad_slots(self.weight, self.bias)
         return _BNFn.apply(x, residual, self.weight, self.bias, self.running_mean, self.running_var,
                            self.num_batches_tracked if (training and self.track_running_stats) else None,

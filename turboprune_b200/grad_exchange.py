@@ -71,7 +71,25 @@ class GradArena:
 
 
 class P2PGradReducer:
-    def __init__(self, params, bucket_cap_mb=64.0, algo="auto", group=None, masks=None):
+    """Gradient mean over NVLink peer memory, one kernel per bucket, overlapped with the backward pass.
+
+    ``algo``: "one_shot" | "two_shot" | "nvls" | "auto".  "nvls" is the two-shot schedule with the reduction and the
+    broadcast done INSIDE the NVSwitch (``multimem.ld_reduce`` / ``multimem.st`` on the symmetric allocation's
+    multicast address): rank r pulls the switch-reduced shard r, scales / masks it and stores it once to the
+    multicast address.  The switch's summation order is fixed by the fabric, not by us: replicas stay
+    bit-identical (every replica receives the value rank r computed), but against the fixed rank-order sum the result
+    may differ in the last bit for W > 2 (tested with that tolerance); "auto" therefore keeps the plain two-shot
+    kernel unless TP_P2P_NVLS=1.
+
+    Overlap: the masked layers / fused BN (which write their gradients straight into the bucket slots) and autograd's
+    post-accumulate hooks (all other parameters) report every finished gradient through ``notify``; when the last
+    gradient of a bucket is in, that bucket's kernel is launched on a side stream behind an event of the compute
+    stream, so it runs under the rest of the backward pass (the reference's DDP does the same with NCCL,
+    base_harness.py:81,127).  ``reduce()`` after ``loss.backward()`` launches whatever is left and joins the side
+    stream.  Under CUDA-graph capture the same calls become a forked branch of the graph.
+    """
+
+    def __init__(self, params, bucket_cap_mb=25.0, algo="auto", group=None, masks=None, overlap=True):
         import torch.distributed._symmetric_memory as symm_mem
         self.group = group or dist.group.WORLD
         self.world = dist.get_world_size(self.group)
@@ -86,8 +104,8 @@ class P2PGradReducer:
         self.plan = plan_buckets([p.numel() for p in rev], cap)
         self.buckets = [[rev[i] for i in idx] for idx, _, _ in self.plan]
         self._bk = []
-        masks = masks or {}
-        for plist in self.buckets:
+        self._slot_bucket = {}          # slot data_ptr -> bucket index
+        for bi, plist in enumerate(self.buckets):
             offs, total = [], 0
             for p in plist:
                 offs.append(total); total += (p.numel() + 3) // 4 * 4
@@ -97,39 +115,142 @@ class P2PGradReducer:
             ptrs = [int(x) for x in hdl.buffer_ptrs]
             data_ptrs = (c_void_p * self.world)(*[c_void_p(x + PAD_FLOATS * 4) for x in ptrs])
             pad_ptrs = (c_void_p * self.world)(*[c_void_p(x) for x in ptrs])
+            mc = 0
+            try:
+                mc = int(hdl.multicast_ptr or 0)
+            except Exception:
+                mc = 0
             data = buf[PAD_FLOATS:]
             views = [data[o:o + p.numel()].view_as(p) for o, p in zip(offs, plist)]
-            algo = self._algo_for(total)
+            algo_id = self._algo_for(total, mc != 0)
             # one-shot: peers read my bucket while I produce the result, so it needs its own
-            # output buffer; two-shot finishes in place (only rank r ever reads shard r).
-            out = torch.empty(total, dtype=torch.float32, device=dev) if algo == 0 else data
+            # output buffer; two-shot / nvls finish in place (only rank r ever reads shard r).
+            out = torch.empty(total, dtype=torch.float32, device=dev) if algo_id == 0 else data
             out_views = [out[o:o + p.numel()].view_as(p) for o, p in zip(offs, plist)]
-            mask = None
-            if any(id(p) in masks for p in plist):
-                mask = torch.ones(total, dtype=torch.float32, device=dev)
-                for o, p in zip(offs, plist):
-                    if id(p) in masks:
-                        mask[o:o + p.numel()] = masks[id(p)].reshape(-1)
-            self._bk.append(dict(buf=buf, hdl=hdl, data=data, views=views, numel=total, params=plist,
-                                 data_ptrs=data_ptrs, pad_ptrs=pad_ptrs, mask=mask, algo=algo, out=out,
-                                 out_views=out_views))
+            for v in views:
+                self._slot_bucket[v.data_ptr()] = bi
+            self._bk.append(dict(buf=buf, hdl=hdl, data=data, views=views, numel=total, params=plist, offs=offs,
+                                 data_ptrs=data_ptrs, pad_ptrs=pad_ptrs, mask=None, algo=algo_id, out=out,
+                                 out_views=out_views, mc=(mc + PAD_FLOATS * 4) if mc else 0))
         self.status = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.overlap = bool(overlap)
+        self._side = torch.cuda.Stream(dev)
+        self._pending = [set() for _ in self._bk]
+        self._launched = [False] * len(self._bk)
+        self._armed = False
+        self._hooks = []
+        if masks:
+            self.set_masks(masks)
         torch.cuda.synchronize(dev)
         dist.barrier(self.group)
 
-    def _algo_for(self, numel):
+    # -- configuration -----------------------------------------------------------------------------------------
+    def _algo_for(self, numel, has_mc):
         if self.algo == "one_shot":
             return 0
         if self.algo == "two_shot":
             return 1
-        return 0 if numel * 4 <= (1 << 20) else 1
+        if self.algo == "nvls":
+            if not has_mc:
+                raise RuntimeError("P2PGradReducer(algo='nvls'): the symmetric allocation has no multicast address")
+            return 2
+        if numel * 4 <= (1 << 20):
+            return 0
+        import os
+        return 2 if (has_mc and os.environ.get("TP_P2P_NVLS", "0") == "1") else 1
+
+    def set_masks(self, masks):
+        """``masks``: {id(param): mask tensor}.  The kernel multiplies the averaged gradient by it while writing it
+        back ("already-masked gradients", BASELINE.json north_star); parameters without an entry get ones."""
+        for bk in self._bk:
+            if not any(id(p) in masks for p in bk["params"]):
+                bk["mask"] = None
+                continue
+            m = bk["mask"]
+            if m is None:
+                m = torch.ones(bk["numel"], dtype=torch.float32, device=self.device)
+            for o, p in zip(bk["offs"], bk["params"]):
+                if id(p) in masks:
+                    m[o:o + p.numel()] = masks[id(p)].reshape(-1).to(device=self.device, dtype=torch.float32)
+                else:
+                    m[o:o + p.numel()] = 1.0
+            bk["mask"] = m
+
+    def set_model_masks(self, model):
+        """Flat per-bucket copies of every masked layer's mask (call after pruning: once per level)."""
+        from .utils.mask_layers import MASKED_LAYER_TYPES
+        self.set_masks({id(m.weight): m.mask for m in model.modules() if isinstance(m, MASKED_LAYER_TYPES)})
+
+    # -- overlap machinery -------------------------------------------------------------------------------------
+    def _launch_bucket(self, bi, stream):
+        lib = _cabi.load()
+        bk = self._bk[bi]
+        st = c_void_p(stream.cuda_stream)
+        mask = c_void_p(bk["mask"].data_ptr()) if bk["mask"] is not None else None
+        if bk["algo"] == 2:
+            rc = lib.tp_p2p_allreduce_nvls(bk["data_ptrs"], bk["pad_ptrs"], c_void_p(bk["mc"]), self.rank, self.world,
+                                           bk["numel"], mask, 1.0 / self.world, c_void_p(bk["out"].data_ptr()),
+                                           20000, c_void_p(self.status.data_ptr()), st)
+        else:
+            rc = lib.tp_p2p_allreduce_mask(bk["data_ptrs"], bk["pad_ptrs"], self.rank, self.world, bk["numel"], mask,
+                                           1.0 / self.world, c_void_p(bk["out"].data_ptr()), bk["algo"],
+                                           20000, c_void_p(self.status.data_ptr()), st)
+        _cabi.check(rc, "tp_p2p_allreduce")
+        ops._count()
+        self._launched[bi] = True
+
+    def notify(self, slot_ptr):
+        """A gradient living at ``slot_ptr`` (a bucket slot) is complete on the current stream."""
+        if not self._armed:
+            return
+        bi = self._slot_bucket.get(slot_ptr)
+        if bi is None:
+            return
+        seen = self._pending[bi]
+        seen.add(slot_ptr)                           # a set, not a counter: a gradient reported twice counts once
+        if len(seen) == len(self._bk[bi]["params"]) and not self._launched[bi]:
+            cur = torch.cuda.current_stream(self.device)
+            ev = torch.cuda.Event()
+            ev.record(cur)
+            self._side.wait_event(ev)
+            with torch.cuda.device(self.device):
+                self._launch_bucket(bi, self._side)
+
+    def arm(self):
+        """Start counting finished gradients for this step (call after ``zero()``, before the backward pass)."""
+        if not self.overlap:
+            return
+        if not self._hooks:
+            for p in self.params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._post_acc))
+        self._pending = [set() for _ in self._bk]
+        self._launched = [False] * len(self._bk)
+        self._armed = True
+        ops.set_grad_ready_hook(self.notify)
+
+    def _post_acc(self, p):
+        g = p.grad
+        if g is not None:
+            self.notify(g.data_ptr())
+
+    def close(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+        if ops.get_grad_ready_hook() == self.notify:
+            ops.set_grad_ready_hook(None)
 
     @torch.no_grad()
     def reduce(self):
-        """Average gradients across ranks; afterwards every ``param.grad`` views its bucket slot."""
-        lib = _cabi.load()
-        st = _cabi.stream_ptr(self.device)
-        for bk in self._bk:
+        """Average gradients across ranks; afterwards every ``param.grad`` views its bucket slot.  Buckets whose
+        kernel already went out during the backward pass are only joined."""
+        armed, self._armed = self._armed, False
+        cur = torch.cuda.current_stream(self.device)
+        joined = False
+        for bi, bk in enumerate(self._bk):
+            if armed and self._launched[bi]:
+                joined = True
+                continue
             grads = [p.grad for p in bk["params"]]
             live = [(v, g) for v, g in zip(bk["views"], grads) if g is not None and g.data_ptr() != v.data_ptr()]
             if live:
@@ -137,12 +258,17 @@ class P2PGradReducer:
             for v, g in zip(bk["views"], grads):
                 if g is None:
                     v.zero_()
-            rc = lib.tp_p2p_allreduce_mask(bk["data_ptrs"], bk["pad_ptrs"], self.rank, self.world, bk["numel"],
-                                           c_void_p(bk["mask"].data_ptr()) if bk["mask"] is not None else None,
-                                           1.0 / self.world, c_void_p(bk["out"].data_ptr()), bk["algo"],
-                                           20000, c_void_p(self.status.data_ptr()), st)
-            _cabi.check(rc, "tp_p2p_allreduce_mask")
-            ops._count()
+            if joined:
+                # keep the launch order identical on every rank: buckets launched late go to the side stream too
+                ev = torch.cuda.Event(); ev.record(cur); self._side.wait_event(ev)
+                with torch.cuda.device(self.device):
+                    self._launch_bucket(bi, self._side)
+            else:
+                with torch.cuda.device(self.device):
+                    self._launch_bucket(bi, cur)
+        if joined:
+            done = torch.cuda.Event(); done.record(self._side); cur.wait_event(done)
+        for bk in self._bk:
             for p, v in zip(bk["params"], bk["out_views"]):
                 p.grad = v
 
@@ -161,3 +287,20 @@ class P2PGradReducer:
     def check_status(self):
         if int(self.status.item()) != 0:
             raise RuntimeError("tp_p2p_allreduce_mask: peer barrier timed out (a rank did not arrive)")
+
+
+_REDUCERS = {}
+
+
+def get_reducer(params, **kw):
+    """One ``P2PGradReducer`` per (process, parameter set): the level loop builds a new harness around the SAME
+    module every level (run_experiment.py:113-115 of the reference) — its symmetric buckets and rendezvous are
+    reused instead of being allocated again 21 times."""
+    params = [p for p in params if p.requires_grad]
+    key = tuple((p.data_ptr(), p.numel()) for p in params)
+    red = _REDUCERS.get(key)
+    if red is None:
+        for k in list(_REDUCERS):                   # a different model in the same process: drop the old buckets
+            _REDUCERS.pop(k).close()
+        red = _REDUCERS[key] = P2PGradReducer(params, **kw)
+    return red

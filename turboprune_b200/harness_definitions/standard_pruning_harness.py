@@ -51,7 +51,10 @@ class PruningHarness(BaseHarness):
         o = self.cfg.optimizer_params
         if o.scheduler_type == "ScheduleFree":
             raise NotImplementedError("ScheduleFree optimizer (third-party package, off the benchmarked path)")
-        self.optimizer = FusedSGD(self.model.parameters(), lr=o.lr, momentum=o.momentum, weight_decay=o.weight_decay)
+        # capturable: the learning rate is a device scalar refreshed by train_step (sync_lr), so the captured step
+        # follows the per-iteration LR schedule without being re-recorded
+        self.optimizer = FusedSGD(self.model.parameters(), lr=o.lr, momentum=o.momentum, weight_decay=o.weight_decay,
+                                  capturable=True)
 
     def _setup_scheduler(self, epochs_per_level):
         kind = self.cfg.optimizer_params.scheduler_type

@@ -63,6 +63,27 @@ class _Timed:
             _timer.records.append((self.kind, self.flops, self.e0, e1))
 
 
+_grad_ready_hook = None      # set by P2PGradReducer.arm(): called with the data_ptr of every gradient slot a kernel just filled
+
+
+def set_grad_ready_hook(fn):
+    global _grad_ready_hook
+    _grad_ready_hook = fn
+
+
+def get_grad_ready_hook():
+    return _grad_ready_hook
+
+
+def grad_ready(*slots):
+    """Report gradients written straight into their persistent slots (no AccumulateGrad node runs for them, so
+    autograd's own hooks never fire): lets the gradient exchange start a bucket while the backward pass continues."""
+    if _grad_ready_hook is not None:
+        for s in slots:
+            if s is not None:
+                _grad_ready_hook(s.data_ptr())
+
+
 def _require_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:
@@ -251,16 +272,22 @@ def stage_weights(weight4d, mask4d, cin_p, need_dgrad, cout_p=None, wf_ld=0):
     return wf, wd
 
 
+def padded_cin(cin, r, s):
+    """Channel count the TMA layouts need: a multiple of 8 (16-byte rows), and of 64 when the filter has more than one
+    tap (the K loop walks 64-channel blocks per tap).  Inputs in between (the reference wraps ANY nn.Conv2d,
+    custom_models.py:64-107) are zero-padded to it while being laid out as NHWC bf16."""
+    return _round_up(cin, 64 if r * s > 1 else 8)
+
+
 def _operand_plan(cout, cin, r, s):
-    """(cin_p, cout_p, has_wd, wf_ld) of the bf16 operand layouts a masked layer consumes, or None when the shape is
-    unsupported."""
-    small_c = (cin % 8 != 0) or (r * s > 1 and cin % 64 != 0)
-    if small_c:
-        if cin > 8:
-            return None
+    """(cin_p, cout_p, has_wd, wf_ld) of the bf16 operand layouts a masked layer consumes in a train step (the
+    WeightStager's view): the stem layout for <= 8 input channels (explicit im2col, no input gradient), otherwise the
+    TMA layouts with the input channels padded to ``padded_cin``."""
+    if cin <= 8 and (cin % 8 != 0 or r * s > 1):
         cg, kp = stem_geometry(cin, r, s)                    # stem: explicit im2col over padded channel groups, no dgrad
         return cg, cout, False, kp
-    return cin, _round_up(cout, 64 if r * s > 1 else 8), True, r * s * cin
+    cin_p = padded_cin(cin, r, s)
+    return cin_p, _round_up(cout, 64 if r * s > 1 else 8), True, r * s * cin_p
 
 
 class WeightStager:
@@ -472,16 +499,15 @@ class MaskedConv2dFn(torch.autograd.Function):
         need_dx = ctx.needs_input_grad[0]
         w32 = weight.detach().contiguous()
         m32 = mask.detach().contiguous()
-        small_c = (cin % 8 != 0) or (r * s > 1 and cin % 64 != 0)
-        desc = make_desc(n, h, w, cin, cout, r, s, stride, padding)
+        cin_p = padded_cin(cin, r, s)
+        # <= 8 input channels and no input gradient wanted (the RGB stem): explicit im2col + plain GEMM, K = taps * cin.
+        # Everything else goes through the TMA layouts with the channels zero-padded to cin_p.
+        small_c = cin <= 8 and cin_p != cin and not need_dx
+        desc = make_desc(n, h, w, cin_p if not small_c else cin, cout, r, s, stride, padding)
         # the backward GEMMs contract over Cout: filters larger than 1x1 walk it in 64-channel blocks per tap
         cout_p = _round_up(cout, 64 if (r * s > 1 and not small_c) else 8)    # (the stem path is a plain GEMM over im2col)
         if small_c:
-            if cin > 8:
-                raise NotImplementedError(f"masked conv with Cin={cin} (not a multiple of 64) and a {r}x{s} filter")
-            if need_dx:
-                raise NotImplementedError("input gradient of a small-channel stem convolution")
-            # stem conv: pad channels to a group of 4 or 8 per tap, explicit im2col, then a plain GEMM
+            # stem conv: cg = cin channels per tap, explicit im2col, then a plain GEMM
             cg, kp = stem_geometry(cin, r, s)
             xg = im2col_stem(x, desc, kp, cg)
             gdesc = _cabi.ConvDesc(n * desc.p * desc.q, 1, 1, kp, cout, 1, 1, 1, 1, 0, 0, 1, 1)
@@ -498,12 +524,12 @@ class MaskedConv2dFn(torch.autograd.Function):
             ctx.gdesc = gdesc
             ctx.save_for_backward(xg, m32)
         else:
-            xn = to_nhwc_bf16(x, cin)
-            if (staged is not None and staged[0].shape == (cout, r * s * cin)
+            xn = to_nhwc_bf16(x, cin_p)      # channels cin..cin_p are zero (and so are the staged weights there)
+            if (staged is not None and staged[0].shape == (cout, r * s * cin_p)
                     and (not need_dx or (staged[1] is not None and staged[1].shape == (cin, r * s * cout_p)))):
                 wf, wd = staged              # refreshed by WeightStager.stage() for this step (one launch for all layers)
             else:
-                wf, wd = stage_weights(w32, m32, cin, need_dx, cout_p)
+                wf, wd = stage_weights(w32, m32, cin_p, need_dx, cout_p)
             y = empty_cl(n, cout, desc.p, desc.q, x.device)
             if want_stats:
                 _, stats = conv_fprop(desc, xn, wf, bias, out=y, want_stats=True)
@@ -512,6 +538,7 @@ class MaskedConv2dFn(torch.autograd.Function):
             ctx.mode = "conv"
             ctx.save_for_backward(xn, m32, wd)
         ctx.desc = desc
+        ctx.cin = cin
         ctx.has_bias = bias is not None
         ctx.cout_p = cout_p
         ctx.x_dtype = x.dtype
@@ -553,6 +580,7 @@ class MaskedConv2dFn(torch.autograd.Function):
                 dw = dwm[:, :r * s * cg].reshape(cout, r * s, cg)[:, :, :cin].permute(0, 2, 1).reshape(cout, cin, r, s) * m32
         else:
             xn, m32, wd = ctx.saved_tensors
+            cin = ctx.cin                      # real input channels (desc.cin is the padded count the activation carries)
             ddesc = desc
             if ctx.cout_p != cout:
                 ddesc = _cabi.ConvDesc(desc.n, desc.h, desc.w, desc.cin, ctx.cout_p, desc.r, desc.s, desc.stride_h,
@@ -560,27 +588,32 @@ class MaskedConv2dFn(torch.autograd.Function):
             if need_dx:
                 addend = None
                 if dskip is not None:
-                    addend = to_nhwc_bf16(dskip, desc.cin)
-                dx = conv_dgrad(ddesc, dyn, wd, addend).permute(0, 3, 1, 2)
+                    addend = to_nhwc_bf16(dskip, cin)
+                # dX has the REAL channel count: the dgrad GEMM's N axis is cin, its K axis (taps x cout_p)
+                xdesc = ddesc if cin == desc.cin else _cabi.ConvDesc(desc.n, desc.h, desc.w, cin, ctx.cout_p, desc.r, desc.s,
+                                                                      desc.stride_h, desc.stride_w, desc.pad_h, desc.pad_w,
+                                                                      desc.p, desc.q)
+                dx = conv_dgrad(xdesc, dyn, wd, addend).permute(0, 3, 1, 2)
                 if dx.dtype != ctx.x_dtype:
                     dx = dx.to(ctx.x_dtype)
             if need_dw:
                 if ctx.cout_p != cout:
                     m_p = torch.zeros(ctx.cout_p, *m32.shape[1:], dtype=torch.float32, device=m32.device)
                     m_p[:cout] = m32
-                    dwp, dbp = conv_wgrad(ddesc, xn, dyn, m_p, desc.cin, need_db)
+                    dwp, dbp = conv_wgrad(ddesc, xn, dyn, m_p, cin, need_db)
                     dw = dwp[:cout].contiguous()
                     db = dbp[:cout].contiguous() if dbp is not None else None
                 else:
                     ws_, bs_ = ctx.grad_slots if ctx.grad_slots is not None else (None, None)
                     direct_w = ws_ is not None and ws_.is_contiguous() and ws_.numel() == m32.numel()
                     direct_b = need_db and bs_ is not None
-                    dw, db = conv_wgrad(desc, xn, dyn, m32, desc.cin, need_db, dw_out=ws_ if direct_w else None,
+                    dw, db = conv_wgrad(desc, xn, dyn, m32, cin, need_db, dw_out=ws_ if direct_w else None,
                                         db_out=bs_ if direct_b else None)
                     if direct_w:
                         dw = None
                     if direct_b:
                         db = None
+                    grad_ready(ws_ if direct_w else None, bs_ if direct_b else None)
         if need_db and db is None:
             db = dy.float().sum(dim=(0, 2, 3))
         if dskip is not None and dx is None and need_dx is False:

@@ -31,8 +31,6 @@ def _wrap(x):
     return x
 
 
-def _parse_scalar(text):
-    return yaml.safe_load(text) if text != "" else ""
 
 
 def _fix_floats(node):
@@ -47,6 +45,11 @@ def _fix_floats(node):
         except ValueError:
             return node
     return node
+
+
+def _parse_scalar(text):
+    """CLI override value: YAML scalar rules plus hydra's float forms ('5e-4', '1e-1' are floats, not strings)."""
+    return _fix_floats(yaml.safe_load(text)) if text != "" else ""
 
 
 def compose(config_name, overrides=(), conf_dir="conf"):

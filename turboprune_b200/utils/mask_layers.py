@@ -43,9 +43,23 @@ def _slots(layer):
     return grad_slots(layer.weight, layer.bias)
 
 
+_MASK_EPOCH = [0]
+
+
+def mask_epoch() -> int:
+    """Bumped whenever any masked layer gets a NEW mask tensor (pruning assigns ``m.mask = ...`` like the reference,
+    pruning_utils.py:87): captured CUDA graphs and cached pointer tables key on it."""
+    return _MASK_EPOCH[0]
+
+
 class _MaskMixin:
     def _init_mask(self):
         self.register_buffer("mask", torch.ones_like(self.weight))
+
+    def __setattr__(self, name, value):
+        if name == "mask":
+            _MASK_EPOCH[0] += 1
+        super().__setattr__(name, value)
 
     def set_er_mask(self, p) -> None:
         """Bernoulli(p) keep-mask drawn with torch's generator (bit-identical to the reference,

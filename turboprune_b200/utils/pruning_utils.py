@@ -178,6 +178,26 @@ def prune_er_balanced(model: nn.Module, er_sparse_init: float):
     return model
 
 
+def sync_masks_from_rank0(model: nn.Module) -> None:
+    """Make rank 0's masks the masks of every replica (one packed broadcast per pruning step).
+
+    The reference prunes on rank 0 only and lets the next DistributedDataParallel constructor broadcast the buffers
+    (run_experiment.py:85-105,113; base_harness.py:81).  Here every rank runs the pruner, which is replica-identical
+    for the magnitude criteria but NOT for SNIP (each rank scores its own first batch, pruning_utils.py:177-184) nor
+    for the random criteria if the per-device RNG streams ever drift — so rank 0's result is imposed, as upstream."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return
+    layers = _masked(model)
+    flat = torch.cat([m.mask.reshape(-1).to(m.weight.device, torch.float32) for m in layers])
+    dist.broadcast(flat, 0)
+    off = 0
+    for m in layers:
+        n = m.mask.numel()
+        m.mask = flat[off:off + n].view_as(m.weight).clone()
+        off += n
+
+
 def prune_the_model(cfg, harness, target_density: float) -> None:
     """Dispatcher by ``cfg.pruning_params.prune_method`` (reference :23-58)."""
     # the reference unwraps DDP here (:25); our harness keeps the bare module and reduces gradients explicitly
@@ -191,6 +211,8 @@ def prune_the_model(cfg, harness, target_density: float) -> None:
         console.print(f"[bold red]Error: Unknown pruning method '{method}'[/bold red]")
         return
     model = fn(cfg, model, loader, target_density) if loader else fn(model, target_density)
+    if getattr(harness, "distributed", False):
+        sync_masks_from_rank0(model)
     after = model.get_overall_sparsity()
     console.print(f"Initial Sparsity {before:.4f}  ->  Final Sparsity {after:.4f}")
     console.print(f"[bold green]Pruning completed using {method} method![/bold green]")
