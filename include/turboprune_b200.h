@@ -84,7 +84,17 @@ int tp_count_zeros(const void* const* m, const int64_t* numel, int n_seg,
  * w, mask: fp32 OIHW [Cout][Cin][R][S].  Cin_p / Cout_p: channel counts padded (zero filled).
  */
 int tp_stage_weights(const void* w, const void* mask, int cout, int cin, int r, int s,
-                     void* wf, int cin_p, int wf_ld, void* wd, int cout_p, int cin_p2, void* stream);
+                     void* wf, int cin_p, int wf_ld, void* wd, int cout_p, int cin_p2,
+                     void* kmask_f, void* kmask_d, void* stream);
+/* K-block occupancy masks ("skip all-zero tiles", BASELINE.json north_star; the reference multiplies the dense
+ * mask*weight every forward, utils/mask_layers.py:25-34).  For every group of 64 ROWS of a staged operand (wf: output
+ * channels; wd: input channels) a bitmask over its 64-column K blocks: bit b of word (b / 32) is set when the 64 x 64 block
+ * holds a non-zero masked weight.  kmask_f: uint32 [ceil(cout/64)][tp_kblock_mask_words(wf_ld)], kmask_d: uint32
+ * [ceil(cin/64)][tp_kblock_mask_words(r*s*cout_p)]; both optional (NULL = not produced); the staging call zeroes and fills
+ * them.  tp_conv_fprop_stats / tp_conv_dgrad skip a K block (no TMA load, no MMA) when it is empty for every row group
+ * of their output-channel tile; results are bit-identical to the dense walk for finite activations (a skipped block only
+ * ever adds +-0). */
+size_t tp_kblock_mask_words(int64_t columns);
 /* wf_ld: elements between consecutive rows of wf (0 = dense, R*S*cin_p); columns past R*S*cin_p are the caller's
  * zero padding (the 7x7x3 stem GEMM runs with K = 152 for 147 real columns). */
 
@@ -97,9 +107,12 @@ typedef struct tp_stage_item {
   const void* w; const void* mask;   /* fp32 OIHW [cout][cin][r][s] */
   void* wf; void* wd;                /* bf16 [cout][r*s*cin_p], bf16 [cin][r*s*cout_p] or NULL */
   int32_t cout, cin, r, s, cin_p, cout_p, wf_ld;   /* wf_ld: 0 = dense */
+  void* kmask_f; void* kmask_d;      /* K-block occupancy masks of wf / wd (NULL = not produced); inside kmask_all */
 } tp_stage_item;
 size_t tp_stage_batched_workspace_bytes(int n_items);
-int tp_stage_weights_batched(const tp_stage_item* items, int n_items, int table_cached, void* ws, size_t ws_bytes, void* stream);
+/* kmask_all / kmask_bytes: the one buffer all items' occupancy masks live in (zeroed here by a single memset; may be NULL) */
+int tp_stage_weights_batched(const tp_stage_item* items, int n_items, int table_cached, void* kmask_all, size_t kmask_bytes,
+                             void* ws, size_t ws_bytes, void* stream);
 
 /* NCHW/NHWC fp32 or bf16 activation -> NHWC bf16 with channels padded to c_pad (zero fill).
  * src_dtype: 0 = fp32, 1 = bf16.  Strides in elements. */
@@ -145,12 +158,12 @@ int tp_conv_fprop(const tp_conv_desc* d, const void* x, const void* wf, const vo
  * (rows past the last pixel are written as zeros).  Consumed by tp_bn_forward_ext — the BatchNorm2d that follows
  * the convolution (torchvision graph built at utils/custom_models.py:184) then needs no statistics pass. */
 size_t tp_conv_stats_rows(const tp_conv_desc* d);
-int tp_conv_fprop_stats(const tp_conv_desc* d, const void* x, const void* wf, const void* bias_f32,
+int tp_conv_fprop_stats(const tp_conv_desc* d, const void* x, const void* wf, const void* kmask_f, const void* bias_f32,
                         void* y, void* stats, void* ws, size_t ws_bytes, void* stream);
 /* dx[n,h,w,cin] (bf16) = conv_dgrad(dy[n,p,q,cout] (bf16), wd (bf16, rotated layout)) [+ addend[n,h,w,cin]]
  * addend (optional, bf16, same layout as dx): the gradient arriving over a skip connection, accumulated in the
  * epilogue instead of by a separate elementwise add (autograd's grad accumulation at a ResNet block input). */
-int tp_conv_dgrad(const tp_conv_desc* d, const void* dy, const void* wd, const void* addend,
+int tp_conv_dgrad(const tp_conv_desc* d, const void* dy, const void* wd, const void* kmask_d, const void* addend,
                   void* dx, void* ws, size_t ws_bytes, void* stream);
 /* dw[cout][cin_real][r][s] (fp32, OIHW) = mask * conv_wgrad(x, dy); db[cout] = sum dy (optional) */
 int tp_conv_wgrad(const tp_conv_desc* d, const void* x, const void* dy, const void* mask,

@@ -767,3 +767,78 @@ def test_level_loop_two_ranks(dev, tmp_path):
     (summary,) = glob.glob(os.path.join(str(tmp_path), "*", "*_summary.csv"))
     rows = list(csv.DictReader(open(summary)))
     assert [row["Level"] for row in rows] == ["0", "1"] and abs(float(rows[1]["Sparsity"]) - 20.0) < 1e-3
+
+
+# ---------------------------------------------------------------- tile skipping (north_star) ----------------------
+@pytest.mark.parametrize("case", [(2, 14, 256, 192, 3, 1, 1), (3, 12, 512, 320, 1, 1, 0), (2, 15, 128, 128, 3, 2, 1), (2, 9, 192, 64, 3, 1, 1)])
+def test_kblock_skipping_bit_identical_to_dense_walk(dev, case):
+    """Masks with dead filters, dead input-channel blocks and dead taps (what structured sparsity in the IMP tail /
+    SynFlow produces): the staging kernel's occupancy bits equal a direct computation from mask*w, a positive number of
+    64x64 blocks is skipped, and fprop / dgrad / wgrad results are BIT-IDENTICAL to the dense walk over the same
+    operands (a skipped block only ever adds zeros)."""
+    from turboprune_b200 import ops
+    n, hw, cin, cout, k, s_, p_ = case
+    g = torch.Generator(device=dev).manual_seed(sum(case))
+    x = torch.randn(n, cin, hw, hw, device=dev, generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    w = torch.randn(cout, cin, k, k, device=dev, generator=g) / (cin * k * k) ** 0.5
+    m = (torch.rand(cout, cin, k, k, device=dev, generator=g) < 0.3).float()
+    m[:, 64:128] = 0                       # a dead 64-channel input block (every tap)
+    m[64:128] = 0                          # 64 dead filters: a whole row group of the fprop operand
+    m[:, :64, 0, 0] = 0                    # one dead tap for the first channel block
+    if cout > 128:
+        m[128:, :, k - 1, k - 1] = 0
+    # occupancy bits vs a direct computation
+    cout_p = ops._round_up(cout, 64 if k > 1 else 8)
+    wf, wd = ops.stage_weights(w, m, cin, True, cout_p)
+    eff = (m * w).to(torch.bfloat16).float()
+    ref_f = eff.permute(0, 2, 3, 1).reshape(cout, k * k * cin)                       # [co][tap*cin + ci]
+    padr = (-cout) % 64
+    ref_f = torch.nn.functional.pad(ref_f, (0, 0, 0, padr)).reshape((cout + padr) // 64, 64, k * k * cin // 64, 64)
+    occ_f = (ref_f != 0).any(dim=3).any(dim=1).cpu()
+    words = wf.kmask.cpu().to(torch.int64) & 0xFFFFFFFF
+    got_f = torch.tensor([[(int(words[r, b // 32]) >> (b % 32)) & 1 for b in range(occ_f.shape[1])] for r in range(occ_f.shape[0])]).bool()
+    assert torch.equal(got_f, occ_f)
+    empty, total = ops.kblock_occupancy(wf.kmask, wf.shape[1])
+    assert empty > 0 and empty == int((~occ_f).sum())
+    ed, td = ops.kblock_occupancy(wd.kmask, wd.shape[1])
+    assert ed > 0
+    outs = {}
+    for skip in (True, False):
+        ops.set_kblock_skip(skip)
+        try:
+            xx = x.clone().requires_grad_(True); ww = w.clone().requires_grad_(True)
+            y = ops.masked_conv2d(xx, ww, m, None, (s_, s_), (p_, p_))
+            gy = torch.Generator(device=dev).manual_seed(7)
+            dy = torch.randn(y.shape, device=dev, generator=gy).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            y.backward(dy)
+            outs[skip] = (y.detach().clone(), xx.grad.detach().clone(), ww.grad.detach().clone())
+        finally:
+            ops.set_kblock_skip(True)
+    for a, b in zip(outs[True], outs[False]):
+        assert torch.equal(a, b)
+    assert float(outs[True][0][:, 64:128].abs().max()) == 0.0          # dead filters: exactly zero outputs
+
+
+def test_skipped_block_report_on_structured_and_iid_masks(dev):
+    """Honest accounting: iid ERK-80 masks on ResNet-18 leave (almost) no 64x64 block empty; killing filters does."""
+    import refshim
+    from turboprune_b200 import ops
+    from turboprune_b200.utils import custom_models as cm, pruning_utils as pu
+    from turboprune_b200.utils.mask_layers import MASKED_LAYER_TYPES
+    torch.manual_seed(0)
+    model = cm.TorchVisionModel(refshim.make_cfg("resnet18", "cifar10"))
+    torch.manual_seed(1)
+    pu.prune_er_erk(model, 0.2)
+    model = model.to(dev)
+    st = ops.WeightStager([m for m in model.modules() if isinstance(m, MASKED_LAYER_TYPES)])
+    st.stage()
+    rep = ops.skipped_block_report(st)
+    assert rep["total_blocks"] > 1000 and rep["fraction"] < 0.01
+    for _, m in model._masked():
+        if m.weight.dim() == 4 and m.weight.shape[0] >= 128:
+            m.mask[: m.weight.shape[0] // 2] = 0                      # half of the filters dead (in place: same tensors)
+    st.stage()
+    rep2 = ops.skipped_block_report(st)
+    assert rep2["fraction"] > 0.3
+    for l in st.layers:
+        ops.take_staged(l)

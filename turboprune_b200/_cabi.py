@@ -23,7 +23,8 @@ class ConvDesc(ctypes.Structure):
 
 class StageItem(ctypes.Structure):
     _fields_ = [("w", c_void_p), ("mask", c_void_p), ("wf", c_void_p), ("wd", c_void_p)] + \
-               [(n, c_int32) for n in ("cout", "cin", "r", "s", "cin_p", "cout_p", "wf_ld")]
+               [(n, c_int32) for n in ("cout", "cin", "r", "s", "cin_p", "cout_p", "wf_ld")] + \
+               [("kmask_f", c_void_p), ("kmask_d", c_void_p)]
 
 
 # name -> (restype, argtypes); every symbol the header declares
@@ -40,9 +41,10 @@ SIGNATURES = {
                                    POINTER(c_int64), c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tp_count_zeros": (c_int, [POINTER(c_void_p), POINTER(c_int64), c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tp_stage_weights": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_int, c_void_p, c_int,
-                                 c_int, c_void_p]),
+                                 c_int, c_void_p, c_void_p, c_void_p]),
+    "tp_kblock_mask_words": (c_size_t, [c_int64]),
     "tp_stage_batched_workspace_bytes": (c_size_t, [c_int]),
-    "tp_stage_weights_batched": (c_int, [POINTER(StageItem), c_int, c_int, c_void_p, c_size_t, c_void_p]),
+    "tp_stage_weights_batched": (c_int, [POINTER(StageItem), c_int, c_int, c_void_p, c_size_t, c_void_p, c_size_t, c_void_p]),
     "tp_to_nhwc_bf16": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int64, c_int, c_int, c_int, c_int,
                                 c_void_p, c_int, c_void_p]),
     "tp_im2col_c8": (c_int, [c_void_p] + [c_int] * 11 + [c_void_p, c_int, c_void_p]),
@@ -50,8 +52,8 @@ SIGNATURES = {
     "tp_conv_workspace_bytes": (c_size_t, [POINTER(ConvDesc), c_int]),
     "tp_conv_fprop": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tp_conv_stats_rows": (c_size_t, [POINTER(ConvDesc)]),
-    "tp_conv_fprop_stats": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "tp_conv_dgrad": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tp_conv_fprop_stats": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "tp_conv_dgrad": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tp_conv_wgrad": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                               c_size_t, c_void_p]),
     "tp_sgd_momentum": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64), c_int,

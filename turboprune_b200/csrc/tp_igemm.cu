@@ -57,7 +57,30 @@ struct FwdParams {
   float* stats;                  // optional (linear output only): per-channel sum / sum of squares of the bf16 outputs
                                  // of every 32-row group, [ceil(M/128)*4][2][N] fp32 — BatchNorm statistics without
                                  // another pass over the activation
+  const uint32_t* kmask;         // optional K-block occupancy of the weight operand: [ceil(N/64)][kmask_words] bitmasks over
+  int kmask_words;               // 64-column K blocks (tp_stage_weights); empty blocks are neither loaded nor multiplied
   TapEntry taps[kMaxTaps];
+};
+
+// Which K blocks of an output-channel tile hold any non-zero weight: the OR of the occupancy words of the tile's 64-row
+// groups.  Producer and MMA thread walk the K loop with one of these each and must take identical decisions: a block is
+// processed when its bit is set, or when it is the last one and nothing was processed yet (the accumulator must be
+// written at least once).
+struct KSkip {
+  const uint32_t* base; int words, g0, g1; int cur_w; uint32_t bits;
+  __device__ __forceinline__ void begin(const uint32_t* km, int wds, int n0, int block_n, int N) {
+    base = km; words = wds; cur_w = -1; bits = 0u;
+    g0 = n0 >> 6; g1 = min((min(n0 + block_n, N) + 63) >> 6, ((N + 63) >> 6));
+  }
+  __device__ __forceinline__ bool on(int kb) {
+    const int wi = kb >> 5;
+    if (wi != cur_w) {
+      cur_w = wi; bits = 0u;
+      if (wi < words) for (int g = g0; g < g1; ++g) bits |= __ldg(base + (size_t)g * words + wi);
+      else bits = 0xffffffffu;                    // a block outside the mask (never produced by the staging kernels): dense
+    }
+    return (bits >> (kb & 31)) & 1u;
+  }
 };
 
 struct WgParams {
@@ -116,7 +139,6 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   const int cl_id = (int)blockIdx.x / CL, n_cl = (int)gridDim.x / CL;
   const int m_groups = (m_tiles + CL - 1) / CL;
   const int total_tiles = m_groups * n_tiles;
-  const int kiters = p.ntaps * p.cchunks;
   constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
 
   if (warp == 0 && lane == 0) {
@@ -148,11 +170,18 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         int cn = 0, cp = 0, cq = 0;
         if (p.a_mode == 1) decompose_pixel(m0, p.P_it, p.Q_it, cn, cp, cq);
         const int cw = p.base_w + cq * p.step_w, ch = p.base_h + cp * p.step_h;
+        KSkip ks; bool any = false;
+        if (p.kmask) ks.begin(p.kmask, p.kmask_words, n_t * BLOCK_N, BLOCK_N, p.N);
         // nested tap / channel-chunk loops: no integer division on the single producer thread
         // (the first ncu source view showed the producer, not TMA or the tensor pipe, as the limiter)
         for (int tap = 0; tap < p.ntaps; ++tap) {
           const TapEntry te = p.taps[tap];
           for (int cc = 0; cc < p.cchunks; ++cc) {
+            if (p.kmask) {
+              const bool last = tap == p.ntaps - 1 && cc == p.cchunks - 1;
+              if (!ks.on((te.kofs >> 6) + cc) && !(last && !any)) continue;      // all-zero weight block: no load, no MMA
+              any = true;
+            }
             mbar_wait(&empty_bar[stage], phase ^ 1, 1);
             uint8_t* sA = smem + stage * kStageBytes;
             uint8_t* sB = sA + kABytes;
@@ -189,22 +218,32 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-        for (int it = 0; it < kiters; ++it) {
-          mbar_wait(&full_bar[stage], phase, 3);
-          tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
-          const uint32_t b_addr = a_addr + kABytes;
-          const uint64_t adesc = make_smem_desc(a_addr, 16, 1024, kLayoutSW128);
-          const uint64_t bdesc = make_smem_desc(b_addr, 16, 1024, kLayoutSW128);
+        KSkip ks; uint32_t any = 0;
+        if (p.kmask) { const int n_t = tile % n_tiles; ks.begin(p.kmask, p.kmask_words, n_t * BLOCK_N, BLOCK_N, p.N); }
+        for (int tap = 0; tap < p.ntaps; ++tap) {
+          const int kb0 = p.kmask ? (p.taps[tap].kofs >> 6) : 0;
+          for (int cc = 0; cc < p.cchunks; ++cc) {
+            if (p.kmask) {
+              const bool last = tap == p.ntaps - 1 && cc == p.cchunks - 1;
+              if (!ks.on(kb0 + cc) && !(last && !any)) continue;               // same decision as the producer
+            }
+            mbar_wait(&full_bar[stage], phase, 3);
+            tc_fence_after();
+            const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
+            const uint32_t b_addr = a_addr + kABytes;
+            const uint64_t adesc = make_smem_desc(a_addr, 16, 1024, kLayoutSW128);
+            const uint64_t bdesc = make_smem_desc(b_addr, 16, 1024, kLayoutSW128);
 #pragma unroll
-          for (int k = 0; k < kBlockK / 16; ++k) {
-            // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in 16-B units
-            if (CL == 1) umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0);
-            else umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, (it | k) != 0);
+            for (int k = 0; k < kBlockK / 16; ++k) {
+              // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in 16-B units
+              if (CL == 1) umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, any | (uint32_t)k);
+              else umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, any | (uint32_t)k);
+            }
+            any = 1;
+            // frees this smem stage (in both CTAs of a pair) when the MMAs have read it
+            if (CL == 1) umma_commit(&empty_bar[stage]); else umma_commit_pair(&empty_bar[stage], kMask);
+            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
-          // frees this smem stage (in both CTAs of a pair) when the MMAs have read it
-          if (CL == 1) umma_commit(&empty_bar[stage]); else umma_commit_pair(&empty_bar[stage], kMask);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
         }
         // accumulator complete -> epilogue (of both CTAs of a pair)
         if (CL == 1) umma_commit(&tfull_bar[acc]); else umma_commit_pair(&tfull_bar[acc], kMask);
@@ -838,10 +877,10 @@ size_t tp_conv_stats_rows(const tp_conv_desc* d) {
 
 int tp_conv_fprop(const tp_conv_desc* d, const void* x, const void* wf, const void* bias_f32,
                   void* y, void* ws, size_t ws_bytes, void* stream) {
-  return tp_conv_fprop_stats(d, x, wf, bias_f32, y, nullptr, ws, ws_bytes, stream);
+  return tp_conv_fprop_stats(d, x, wf, nullptr, bias_f32, y, nullptr, ws, ws_bytes, stream);
 }
 
-int tp_conv_fprop_stats(const tp_conv_desc* d, const void* x, const void* wf, const void* bias_f32,
+int tp_conv_fprop_stats(const tp_conv_desc* d, const void* x, const void* wf, const void* kmask_f, const void* bias_f32,
                         void* y, void* stats, void* ws, size_t ws_bytes, void* stream) {
   (void)ws; (void)ws_bytes;
   if (!d || !x || !wf || !y) return TP_ERR_INVALID;
@@ -859,6 +898,7 @@ int tp_conv_fprop_stats(const tp_conv_desc* d, const void* x, const void* wf, co
   p.osh = 1; p.oah = 0; p.osw = 1; p.oaw = 0;
   p.ldc = d->cout; p.out = (__nv_bfloat16*)y; p.bias = (const float*)bias_f32;
   p.stats = (float*)stats;
+  p.kmask = (const uint32_t*)kmask_f; p.kmask_words = (int)tp_kblock_mask_words((int64_t)d->r * d->s * d->cin);
   for (int r = 0; r < d->r; ++r) for (int s = 0; s < d->s; ++s) {
     TapEntry& t = p.taps[r * d->s + s];
     t.off_w = (uint16_t)s; t.off_h = (uint16_t)r; t.kofs = (r * d->s + s) * d->cin;
@@ -880,7 +920,7 @@ int tp_conv_fprop_stats(const tp_conv_desc* d, const void* x, const void* wf, co
   return run_fwd(ta, tb, p, st);
 }
 
-int tp_conv_dgrad(const tp_conv_desc* d, const void* dy, const void* wd, const void* addend,
+int tp_conv_dgrad(const tp_conv_desc* d, const void* dy, const void* wd, const void* kmask_d, const void* addend,
                   void* dx, void* ws, size_t ws_bytes, void* stream) {
   (void)ws; (void)ws_bytes;
   if (!d || !dy || !wd || !dx) return TP_ERR_INVALID;
@@ -902,6 +942,7 @@ int tp_conv_dgrad(const tp_conv_desc* d, const void* dy, const void* wd, const v
     p.out_img_pix = (long long)d->h * d->w; p.out_row_pix = d->w;
     p.osh = 1; p.oah = 0; p.osw = 1; p.oaw = 0;
     p.ldc = d->cin; p.out = (__nv_bfloat16*)dx; p.bias = nullptr; p.addend = (const __nv_bfloat16*)addend;
+    p.kmask = (const uint32_t*)kmask_d; p.kmask_words = (int)tp_kblock_mask_words(ktot);
     for (int r = 0; r < R; ++r) for (int s = 0; s < S; ++s) {
       TapEntry& t = p.taps[r * S + s];
       t.off_w = (uint16_t)s; t.off_h = (uint16_t)r; t.kofs = (r * S + s) * cop;
@@ -944,6 +985,7 @@ int tp_conv_dgrad(const tp_conv_desc* d, const void* dy, const void* wd, const v
     p.out_img_pix = (long long)d->h * d->w; p.out_row_pix = d->w;
     p.osh = sh; p.oah = a; p.osw = sw; p.oaw = b;
     p.ldc = d->cin; p.out = (__nv_bfloat16*)dx; p.bias = nullptr; p.addend = (const __nv_bfloat16*)addend;
+    p.kmask = (const uint32_t*)kmask_d; p.kmask_words = (int)tp_kblock_mask_words(ktot);
     for (int r = 0; r < R; ++r) {
       if ((a + d->pad_h - r) % sh != 0) continue;
       for (int s = 0; s < S; ++s) {

@@ -17,9 +17,14 @@ namespace tp {
 constexpr int kCoT = 8;
 constexpr int kSlabFloats = 8192;            // 32 KB
 
+// K-block occupancy (BASELINE.json north_star: skip all-zero tiles): one bit per (64 rows of the staged operand) x (64 K
+// columns), set when the block holds a non-zero masked weight.  kmf: rows = output channels, column = tap*cin_p + ci (wf);
+// kmd: rows = input channels, column = rot_tap*cout_p + co (wd).  Bits are OR-ed into a buffer the host zeroed, so the
+// result does not depend on CTA order.
 __device__ __forceinline__ void stage_slab(const float* __restrict__ w, const float* __restrict__ mask, int co0, int cout,
                                            int c0, int c1, int cin, int rs, __nv_bfloat16* __restrict__ wf, int cin_p, int wf_ld,
-                                           __nv_bfloat16* __restrict__ wd, int cout_p, bool zero_pad, float* s_slab) {
+                                           __nv_bfloat16* __restrict__ wd, int cout_p, bool zero_pad, float* s_slab,
+                                           uint32_t* __restrict__ kmf, int kmf_words, uint32_t* __restrict__ kmd, int kmd_words) {
   const int t = threadIdx.x;
   const int cw = c1 - c0;                    // channels in this slice
   const int per_co = cw * rs;
@@ -55,6 +60,38 @@ __device__ __forceinline__ void stage_slab(const float* __restrict__ w, const fl
       }
     }
   }
+  if (kmf || (kmd && wd)) {
+    const int warp = t >> 5, lane = t & 31, nwarps = blockDim.x >> 5;
+    if (kmf) {
+      for (int tap = 0; tap < rs; ++tap) {
+        const int col0 = tap * cin_p + c0, col1 = tap * cin_p + c1;            // wf columns of this slice for this tap
+        for (int kb = (col0 >> 6) + warp; kb <= ((col1 - 1) >> 6); kb += nwarps) {
+          const int a = max(col0, kb << 6), b = min(col1, (kb + 1) << 6), wdt = b - a;
+          bool nz = false;
+          for (int e = lane; e < nco * wdt; e += 32) {
+            const int cl = e / wdt, c = a + (e - cl * wdt) - tap * cin_p - c0;
+            nz |= s_slab[cl * per_co + c * rs + tap] != 0.f;
+          }
+          if (__any_sync(0xffffffffu, nz) && lane == 0) atomicOr(&kmf[(size_t)(co0 >> 6) * kmf_words + (kb >> 5)], 1u << (kb & 31));
+        }
+      }
+    }
+    if (kmd && wd) {
+      // rows = input channels (64 per group), column block of this CTA's 8 output channels under rotated tap rt
+      const int g0 = c0 >> 6, g1 = (c1 - 1) >> 6;
+      for (int item = warp; item < rs * (g1 - g0 + 1); item += nwarps) {
+        const int tap = item / (g1 - g0 + 1), g = g0 + item % (g1 - g0 + 1);
+        const int a = max(c0, g << 6), b = min(c1, (g + 1) << 6), wdt = b - a;
+        bool nz = false;
+        for (int e = lane; e < nco * wdt; e += 32) {
+          const int cl = e / wdt, c = a + (e - cl * wdt) - c0;
+          nz |= s_slab[cl * per_co + c * rs + tap] != 0.f;
+        }
+        const int kb = ((rs - 1 - tap) * cout_p + co0) >> 6;
+        if (__any_sync(0xffffffffu, nz) && lane == 0) atomicOr(&kmd[(size_t)g * kmd_words + (kb >> 5)], 1u << (kb & 31));
+      }
+    }
+  }
   // zero the channel padding of wf (cin..cin_p) — done by the first channel slice
   if (zero_pad && c0 == 0 && cin_p > cin) {
     const int padw = cin_p - cin;
@@ -69,14 +106,16 @@ __device__ __forceinline__ void stage_slab(const float* __restrict__ w, const fl
 __global__ void __launch_bounds__(256) k_stage_weights(const float* __restrict__ w, const float* __restrict__ mask,
                                                        int cout, int cin, int rs,
                                                        __nv_bfloat16* __restrict__ wf, int cin_p,
-                                                       __nv_bfloat16* __restrict__ wd, int cout_p, int wf_ld) {
+                                                       __nv_bfloat16* __restrict__ wd, int cout_p, int wf_ld,
+                                                       uint32_t* __restrict__ kmf, int kmf_words,
+                                                       uint32_t* __restrict__ kmd, int kmd_words) {
   extern __shared__ float s_slab[];       // [kCoT][cin_chunk][rs] fp32, sized by the host
   // process channels in chunks of CC so the slab fits in smem
   const int CC = (cin + gridDim.y - 1) / gridDim.y;
   const int c0 = blockIdx.y * CC;
   const int c1 = min(cin, c0 + CC);
   if (c0 >= c1) return;
-  stage_slab(w, mask, blockIdx.x * kCoT, cout, c0, c1, cin, rs, wf, cin_p, wf_ld, wd, cout_p, true, s_slab);
+  stage_slab(w, mask, blockIdx.x * kCoT, cout, c0, c1, cin, rs, wf, cin_p, wf_ld, wd, cout_p, true, s_slab, kmf, kmf_words, kmd, kmd_words);
 }
 
 // All masked layers of a model in ONE launch (54 launches of ~10 us each were 5 % of the per-GPU-batch-64 step).
@@ -85,6 +124,8 @@ struct StageItem {
   const float* w; const float* mask; __nv_bfloat16* wf; __nv_bfloat16* wd;
   int cout, cin, rs, cin_p, cout_p, ysplit, cc, wf_ld;
   long long cta0;                         // first CTA of this layer; CTAs = ceil(cout / kCoT) * ysplit
+  uint32_t* kmf; uint32_t* kmd;           // K-block occupancy masks (nullable)
+  int kmf_words, kmd_words;
 };
 
 __global__ void __launch_bounds__(256) k_stage_weights_batched(const StageItem* __restrict__ items, int n_items) {
@@ -100,7 +141,8 @@ __global__ void __launch_bounds__(256) k_stage_weights_batched(const StageItem* 
   const int ct = local / it.ysplit, y = local - ct * it.ysplit;
   const int c0 = y * it.cc, c1 = min(it.cin, c0 + it.cc);
   if (ct * kCoT >= it.cout || c0 >= c1) return;
-  stage_slab(it.w, it.mask, ct * kCoT, it.cout, c0, c1, it.cin, it.rs, it.wf, it.cin_p, it.wf_ld, it.wd, it.cout_p, false, s_slab);
+  stage_slab(it.w, it.mask, ct * kCoT, it.cout, c0, c1, it.cin, it.rs, it.wf, it.cin_p, it.wf_ld, it.wd, it.cout_p, false, s_slab,
+             it.kmf, it.kmf_words, it.kmd, it.kmd_words);
 }
 
 __global__ void k_zero_bf16(__nv_bfloat16* p, long long n) {
@@ -250,8 +292,14 @@ using namespace tp;
 
 extern "C" {
 
+size_t tp_kblock_mask_words(int64_t columns) {
+  if (columns <= 0) return 0;
+  return (size_t)(((columns + 63) / 64 + 31) / 32);
+}
+
 int tp_stage_weights(const void* w, const void* mask, int cout, int cin, int r, int s,
-                     void* wf, int cin_p, int wf_ld, void* wd, int cout_p, int cin_p2, void* stream) {
+                     void* wf, int cin_p, int wf_ld, void* wd, int cout_p, int cin_p2,
+                     void* kmask_f, void* kmask_d, void* stream) {
   if (!w || !mask || !wf || cout <= 0 || cin <= 0 || r <= 0 || s <= 0 || cin_p < cin) return TP_ERR_INVALID;
   if (wd && (cout_p < cout || cin_p2 < cin)) return TP_ERR_INVALID;
   if (wf_ld <= 0) wf_ld = r * s * cin_p;
@@ -269,9 +317,13 @@ int tp_stage_weights(const void* w, const void* mask, int cout, int cin, int r, 
       k_zero_bf16<<<(unsigned)min((nz + 255) / 256, (long long)sm_count() * 16), 256, 0, st>>>((__nv_bfloat16*)wd, nz);
     }
   }
+  const int kmf_words = (int)tp_kblock_mask_words(wf_ld), kmd_words = (int)tp_kblock_mask_words((int64_t)rs * cout_p);
+  if (kmask_f) TP_CUDA_CHECK(cudaMemsetAsync(kmask_f, 0, (size_t)((cout + 63) / 64) * kmf_words * 4, st));
+  if (kmask_d && wd) TP_CUDA_CHECK(cudaMemsetAsync(kmask_d, 0, (size_t)((cin + 63) / 64) * kmd_words * 4, st));
   dim3 grid((cout + kCoT - 1) / kCoT, ysplit);
   k_stage_weights<<<grid, 256, smem, st>>>((const float*)w, (const float*)mask, cout, cin, rs,
-                                           (__nv_bfloat16*)wf, cin_p, (__nv_bfloat16*)wd, cout_p, wf_ld);
+                                           (__nv_bfloat16*)wf, cin_p, (__nv_bfloat16*)wd, cout_p, wf_ld,
+                                           (uint32_t*)kmask_f, kmf_words, (uint32_t*)kmask_d, kmd_words);
   TP_LAUNCH_CHECK();
   return TP_OK;
 }
@@ -280,7 +332,8 @@ size_t tp_stage_batched_workspace_bytes(int n_items) {
   return n_items > 0 ? (size_t)n_items * sizeof(StageItem) + 512 : 0;
 }
 
-int tp_stage_weights_batched(const tp_stage_item* items, int n_items, int table_cached, void* ws, size_t ws_bytes, void* stream) {
+int tp_stage_weights_batched(const tp_stage_item* items, int n_items, int table_cached, void* kmask_all, size_t kmask_bytes,
+                             void* ws, size_t ws_bytes, void* stream) {
   if (!items || n_items <= 0 || !ws) return TP_ERR_INVALID;
   cudaStream_t st = (cudaStream_t)stream;
   Arena ar(ws, ws_bytes);
@@ -302,6 +355,8 @@ int tp_stage_weights_batched(const tp_stage_item* items, int n_items, int table_
     t.wf_ld = q.wf_ld > 0 ? q.wf_ld : rs * q.cin_p;
     if (t.wf_ld < rs * q.cin_p) return TP_ERR_INVALID;
     t.cta0 = cta;
+    t.kmf = (uint32_t*)q.kmask_f; t.kmd = (uint32_t*)q.kmask_d;
+    t.kmf_words = (int)tp_kblock_mask_words(t.wf_ld); t.kmd_words = (int)tp_kblock_mask_words((int64_t)rs * q.cout_p);
     cta += (long long)((q.cout + kCoT - 1) / kCoT) * ysplit;
     const size_t need = (size_t)kCoT * cc * rs * sizeof(float);
     if (need > smem) smem = need;
@@ -309,6 +364,7 @@ int tp_stage_weights_batched(const tp_stage_item* items, int n_items, int table_
   if (cta > 0x7fffffffll) return TP_ERR_UNSUPPORTED;
   if (!table_cached)   // pageable source: staged by the runtime before returning (not capturable: cache the table first)
     TP_CUDA_CHECK(cudaMemcpyAsync(d_items, h.data(), sizeof(StageItem) * n_items, cudaMemcpyHostToDevice, st));
+  if (kmask_all && kmask_bytes) TP_CUDA_CHECK(cudaMemsetAsync(kmask_all, 0, kmask_bytes, st));   // all layers' occupancy masks: one memset node
   k_stage_weights_batched<<<(unsigned)cta, 256, smem, st>>>(d_items, n_items);
   TP_LAUNCH_CHECK();
   return TP_OK;

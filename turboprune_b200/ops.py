@@ -249,9 +249,34 @@ def stem_geometry(cin, r, s):
     return cg, _round_up(r * s * cg, 8)
 
 
-def stage_weights(weight4d, mask4d, cin_p, need_dgrad, cout_p=None, wf_ld=0):
+KBLOCK_SKIP = True      # K-block occupancy masks: all-zero 64x64 weight blocks are neither loaded nor multiplied
+
+
+def set_kblock_skip(on: bool):
+    """Toggle tile skipping (benchmarks / parity tests compare both walks; results are bit-identical)."""
+    global KBLOCK_SKIP
+    KBLOCK_SKIP = bool(on)
+
+
+def kmask_shapes(cout, cin, r, s, wf_ld, cout_p):
+    """([row groups, words] of the fprop mask, [row groups, words] of the dgrad mask) — include/turboprune_b200.h."""
+    words = lambda cols: ((cols + 63) // 64 + 31) // 32
+    return ((cout + 63) // 64, words(wf_ld)), ((cin + 63) // 64, words(r * s * cout_p))
+
+
+def kblock_occupancy(kmask, columns):
+    """(empty, total) 64x64 weight blocks described by an occupancy mask over ``columns`` K columns (host sync)."""
+    kb = (columns + 63) // 64
+    words = kmask.to(torch.int64).cpu() & 0xFFFFFFFF
+    set_bits = sum(bin(int(v)).count("1") for v in words.reshape(-1).tolist())
+    total = kmask.shape[0] * kb
+    return total - set_bits, total
+
+
+def stage_weights(weight4d, mask4d, cin_p, need_dgrad, cout_p=None, wf_ld=0, want_kmask=None):
     """(mask*w) -> bf16 operand layouts wf [Cout, R*S*cin_p] (row stride ``wf_ld`` when given, zero tail) and
-    (optionally) wd [cin, R*S*cout_p]."""
+    (optionally) wd [cin, R*S*cout_p].  With ``want_kmask`` (default: the module switch) the K-block occupancy masks are
+    produced too and ride along as ``wf.kmask`` / ``wd.kmask`` (uint32 tensors consumed by conv_fprop / conv_dgrad)."""
     lib = _cabi.load()
     cout, cin, r, s = weight4d.shape
     dev = weight4d.device
@@ -263,12 +288,21 @@ def stage_weights(weight4d, mask4d, cin_p, need_dgrad, cout_p=None, wf_ld=0):
     cout_p = cout if cout_p is None else cout_p
     if need_dgrad:
         wd = torch.empty(cin, r * s * cout_p, dtype=torch.bfloat16, device=dev)
+    kf = kd = None
+    if KBLOCK_SKIP if want_kmask is None else want_kmask:
+        sf, sd = kmask_shapes(cout, cin, r, s, wf.shape[1], cout_p)
+        kf = torch.empty(sf, dtype=torch.int32, device=dev)
+        kd = torch.empty(sd, dtype=torch.int32, device=dev) if wd is not None else None
     with torch.cuda.device(dev):
         rc = lib.tp_stage_weights(c_void_p(weight4d.data_ptr()), c_void_p(mask4d.data_ptr()), cout, cin, r, s,
                                   c_void_p(wf.data_ptr()), cin_p, int(wf_ld), c_void_p(wd.data_ptr()) if wd is not None else None,
-                                  cout_p, cin, _cabi.stream_ptr(dev))
+                                  cout_p, cin, c_void_p(kf.data_ptr()) if kf is not None else None,
+                                  c_void_p(kd.data_ptr()) if kd is not None else None, _cabi.stream_ptr(dev))
     _cabi.check(rc, "tp_stage_weights")
     _count()
+    wf.kmask = kf
+    if wd is not None:
+        wd.kmask = kd
     return wf, wd
 
 
@@ -328,6 +362,23 @@ class WeightStager:
                 wf = torch.zeros(cout, wf_ld, dtype=torch.bfloat16, device=dev)
                 wd = torch.zeros(cin, r * s * cout_p, dtype=torch.bfloat16, device=dev) if has_wd else None
                 self._bufs.append((wf, wd, cin_p, cout_p))
+            # K-block occupancy masks of all layers in ONE buffer (zeroed by a single memset node per step)
+            shapes = []
+            for l, b in zip(self.layers, self._bufs):
+                if b is None:
+                    shapes.append(None); continue
+                cout, cin, r, s = self._shape4(l)
+                shapes.append(kmask_shapes(cout, cin, r, s, b[0].shape[1], b[3]))
+            total = sum(sf[0] * sf[1] + (sd[0] * sd[1] if b[1] is not None else 0) for (sh, b) in zip(shapes, self._bufs) if sh is not None for sf, sd in [sh])
+            self._kmask_all = torch.zeros(max(total, 1), dtype=torch.int32, device=dev)
+            off = 0
+            for sh, b in zip(shapes, self._bufs):
+                if sh is None:
+                    continue
+                sf, sd = sh
+                b[0].kmask = self._kmask_all[off:off + sf[0] * sf[1]].view(sf); off += sf[0] * sf[1]
+                if b[1] is not None:
+                    b[1].kmask = self._kmask_all[off:off + sd[0] * sd[1]].view(sd); off += sd[0] * sd[1]
         live = [(l, b) for l, b in zip(self.layers, self._bufs) if b is not None]
         items = (_cabi.StageItem * len(live))()
         for it, (l, (wf, wd, cin_p, cout_p)) in zip(items, live):
@@ -335,6 +386,8 @@ class WeightStager:
             it.w = l.weight.data_ptr(); it.mask = l.mask.data_ptr()
             it.wf = wf.data_ptr(); it.wd = wd.data_ptr() if wd is not None else None
             it.cout, it.cin, it.r, it.s, it.cin_p, it.cout_p, it.wf_ld = cout, cin, r, s, cin_p, cout_p, wf.shape[1]
+            it.kmask_f = wf.kmask.data_ptr()
+            it.kmask_d = wd.kmask.data_ptr() if wd is not None else None
         self._items, self._live, self._key = items, live, key
         if self._ws is None:
             lib = _cabi.load()
@@ -353,12 +406,27 @@ class WeightStager:
             return
         dev = self.layers[0].weight.device
         with torch.cuda.device(dev):
-            rc = lib.tp_stage_weights_batched(self._items, len(self._live), int(cached), c_void_p(self._ws.data_ptr()),
+            rc = lib.tp_stage_weights_batched(self._items, len(self._live), int(cached), c_void_p(self._kmask_all.data_ptr()),
+                                              self._kmask_all.numel() * 4, c_void_p(self._ws.data_ptr()),
                                               self._ws.numel(), _cabi.stream_ptr(dev))
         _cabi.check(rc, "tp_stage_weights_batched")
         _count()
         for l, (wf, wd, _, _) in self._live:
             l.__dict__["_tp_staged"] = (wf, wd)
+
+
+def skipped_block_report(stager):
+    """After ``stager.stage()``: per layer and in total, how many 64x64 blocks of the fprop weight operand are empty
+    (never loaded / multiplied).  For iid unstructured masks this is ~0 at any density a 64x64 block survives
+    (SURVEY.md Appendix B); dead filters / dead input channels are what produces skippable blocks."""
+    rows, empty, total = [], 0, 0
+    for l, b in zip(stager.layers, stager._bufs):
+        if b is None or getattr(b[0], "kmask", None) is None:
+            continue
+        e, t = kblock_occupancy(b[0].kmask, b[0].shape[1])
+        rows.append((type(l).__name__, tuple(l.weight.shape), e, t))
+        empty += e; total += t
+    return {"empty_blocks": empty, "total_blocks": total, "fraction": empty / max(total, 1), "layers": rows}
 
 
 def take_staged(layer):
@@ -433,7 +501,9 @@ def conv_fprop(desc, x_nhwc, wf, bias=None, out=None, want_stats=False):
     if want_stats:
         stats = torch.empty(int(lib.tp_conv_stats_rows(ctypes.byref(desc))), 2, desc.cout, dtype=torch.float32, device=dev)
     with torch.cuda.device(dev), _Timed("fprop", desc):
+        km = getattr(wf, "kmask", None) if KBLOCK_SKIP else None
         rc = lib.tp_conv_fprop_stats(ctypes.byref(desc), c_void_p(x_nhwc.data_ptr()), c_void_p(wf.data_ptr()),
+                                     c_void_p(km.data_ptr()) if km is not None else None,
                                      c_void_p(bias.data_ptr()) if bias is not None else None, c_void_p(y.data_ptr()),
                                      c_void_p(stats.data_ptr()) if stats is not None else None,
                                      None, 0, _cabi.stream_ptr(dev))
@@ -442,13 +512,16 @@ def conv_fprop(desc, x_nhwc, wf, bias=None, out=None, want_stats=False):
     return (y, stats) if want_stats else y
 
 
-def conv_dgrad(desc, dy_nhwc, wd, addend=None):
-    """dx = dgrad(dy) [+ addend]: ``addend`` (NHWC bf16, dx's shape) is accumulated in the kernel epilogue."""
+def conv_dgrad(desc, dy_nhwc, wd, addend=None, kmask=None):
+    """dx = dgrad(dy) [+ addend]: ``addend`` (NHWC bf16, dx's shape) is accumulated in the kernel epilogue.
+    ``kmask``: K-block occupancy mask of ``wd`` (defaults to the one riding on the tensor)."""
     lib = _cabi.load()
     dev = dy_nhwc.device
     dx = torch.empty(desc.n, desc.h, desc.w, desc.cin, dtype=torch.bfloat16, device=dev)
     with torch.cuda.device(dev), _Timed("dgrad", desc):
+        km = (kmask if kmask is not None else getattr(wd, "kmask", None)) if KBLOCK_SKIP else None
         rc = lib.tp_conv_dgrad(ctypes.byref(desc), c_void_p(dy_nhwc.data_ptr()), c_void_p(wd.data_ptr()),
+                               c_void_p(km.data_ptr()) if km is not None else None,
                                c_void_p(addend.data_ptr()) if addend is not None else None,
                                c_void_p(dx.data_ptr()), None, 0, _cabi.stream_ptr(dev))
     _cabi.check(rc, "tp_conv_dgrad")
@@ -537,6 +610,7 @@ class MaskedConv2dFn(torch.autograd.Function):
                 conv_fprop(desc, xn, wf, bias, out=y)
             ctx.mode = "conv"
             ctx.save_for_backward(xn, m32, wd)
+            ctx.wd_kmask = getattr(wd, "kmask", None) if wd is not None else None     # attributes do not survive save_for_backward
         ctx.desc = desc
         ctx.cin = cin
         ctx.has_bias = bias is not None
@@ -593,7 +667,7 @@ class MaskedConv2dFn(torch.autograd.Function):
                 xdesc = ddesc if cin == desc.cin else _cabi.ConvDesc(desc.n, desc.h, desc.w, cin, ctx.cout_p, desc.r, desc.s,
                                                                       desc.stride_h, desc.stride_w, desc.pad_h, desc.pad_w,
                                                                       desc.p, desc.q)
-                dx = conv_dgrad(xdesc, dyn, wd, addend).permute(0, 3, 1, 2)
+                dx = conv_dgrad(xdesc, dyn, wd, addend, kmask=ctx.wd_kmask).permute(0, 3, 1, 2)
                 if dx.dtype != ctx.x_dtype:
                     dx = dx.to(ctx.x_dtype)
             if need_dw:
