@@ -816,7 +816,8 @@ def test_kblock_skipping_bit_identical_to_dense_walk(dev, case):
             ops.set_kblock_skip(True)
     for a, b in zip(outs[True], outs[False]):
         assert torch.equal(a, b)
-    assert float(outs[True][0][:, 64:128].abs().max()) == 0.0          # dead filters: exactly zero outputs
+    if cout >= 128:
+        assert float(outs[True][0][:, 64:128].abs().max()) == 0.0      # dead filters: exactly zero outputs
 
 
 def test_skipped_block_report_on_structured_and_iid_masks(dev):
