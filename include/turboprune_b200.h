@@ -56,13 +56,28 @@ int         tp_device_sm_count(void);      /* cached multiprocessor count of the
  *   new mask          : mask_out[i][j] = score <= thr ? 0.f : 1.f   (ties pruned)
  *   info_out          : optional HOST int64[4] = {path (0 bracketed single sweep, 1 exact
  *                       3-pass radix fallback), candidates, n_lt, nan_threshold}
- * The call synchronises the stream once (it has to learn whether the fast path held).
+ * The call synchronises the stream once (it has to learn whether the fast path held); see tp_topk_enqueue /
+ * tp_topk_finish for the non-blocking form.
  */
 size_t tp_topk_workspace_bytes(int n_seg, int64_t total_numel);
 int tp_topk_threshold_mask(const void* const* w, const void* const* g, const void* const* m,
                            void* const* mask_out, const int64_t* numel, int n_seg,
                            int64_t k, int score_kind, float* thr_out,
                            void* ws, size_t ws_bytes, int64_t* info_out, void* stream);
+/* The same call split in two, for callers that must not block the stream (benchmarks, a pruning step queued behind
+ * other work): tp_topk_enqueue issues the whole fast path — one memset and ONE cooperative kernel (sample, bracket,
+ * sweep, resolve, patch, see csrc/tp_prune.cu) — and returns without synchronising; tp_topk_finish synchronises,
+ * reads the status back and, only if the bracket missed (adversarial ties) or the threshold is NaN, runs the exact
+ * radix fallback / the all-ones apply pass.  Masks and thr_out must not be consumed before tp_topk_finish returned.
+ * table_cached != 0: `ws` still holds the segment table uploaded by an earlier call with identical pointers (no
+ * host->device copy; w / g may then be NULL).  Both take the same numel / n_seg / k / score_kind / ws. */
+int tp_topk_enqueue(const void* const* w, const void* const* g, const void* const* m,
+                    void* const* mask_out, const int64_t* numel, int n_seg,
+                    int64_t k, int score_kind, float* thr_out,
+                    void* ws, size_t ws_bytes, int table_cached, void* stream);
+int tp_topk_finish(const void* const* m, void* const* mask_out, const int64_t* numel, int n_seg,
+                   int64_t k, int score_kind, float* thr_out,
+                   void* ws, size_t ws_bytes, int64_t* info_out, void* stream);
 
 /* mask_out = score <= *thr ? 0 : 1 with a caller-supplied DEVICE threshold
  * (utils/pruning_utils.py:84-87,140-143).  thr semantics follow fp32 compare: a NaN
@@ -89,8 +104,9 @@ int tp_stage_weights(const void* w, const void* mask, int cout, int cin, int r, 
 /* K-block occupancy masks ("skip all-zero tiles", BASELINE.json north_star; the reference multiplies the dense
  * mask*weight every forward, utils/mask_layers.py:25-34).  For every group of 64 ROWS of a staged operand (wf: output
  * channels; wd: input channels) a bitmask over its 64-column K blocks: bit b of word (b / 32) is set when the 64 x 64 block
- * holds a non-zero masked weight.  kmask_f: uint32 [ceil(cout/64)][tp_kblock_mask_words(wf_ld)], kmask_d: uint32
- * [ceil(cin/64)][tp_kblock_mask_words(r*s*cout_p)]; both optional (NULL = not produced); the staging call zeroes and fills
+ * holds a non-zero masked weight.  kmask_f: uint32 [ceil(cout/64)][tp_kblock_mask_words(wf_ld)] + 1, kmask_d: uint32
+ * [ceil(cin/64)][tp_kblock_mask_words(r*s*cout_p)] + 1; the trailing element is the number of EMPTY blocks (zero lets the
+ * GEMM kernels drop the per-block test entirely); both optional (NULL = not produced); the staging call zeroes and fills
  * them.  tp_conv_fprop_stats / tp_conv_dgrad skip a K block (no TMA load, no MMA) when it is empty for every row group
  * of their output-channel tile; results are bit-identical to the dense walk for finite activations (a skipped block only
  * ever adds +-0). */

@@ -9,6 +9,10 @@
                        rank order and scale by 1/W once; for W a power of two the two are
                        bit-identical, otherwise equal to 1 ulp (tolerance stated in tests).
   train_step           harness_definitions/base_harness.py:115-134
+  triangular_schedule  utils/schedulers.py:79-117 (np.interp over [0, warmup, total] -> [0.2, 1, 0], LambdaLR)
+  train_epoch          harness_definitions/base_harness.py:151-202 (per-iteration scheduler.step() for the
+                       OneCycleLR / Triangular / Trapezoidal schedules, epoch loss = mean of the per-step losses,
+                       accuracy over all samples of the epoch in percent)
 """
 import numpy as np
 import torch
@@ -51,3 +55,23 @@ def train_step(model, optimizer, inputs, targets, amp_dtype=torch.bfloat16, use_
     loss.backward()
     optimizer.step()
     return float(loss.item()), out.detach()
+
+
+def triangular_schedule(optimizer, steps_per_epoch, epochs, warmup_fraction):
+    """utils/schedulers.py:79-117: LambdaLR over the interpolated table (index = number of scheduler steps taken)."""
+    total = epochs * steps_per_epoch
+    table = np.interp(np.arange(1 + total), [0, int(warmup_fraction * total), total], [0.2, 1, 0])
+    return torch.optim.lr_scheduler.LambdaLR(optimizer, table.__getitem__)
+
+
+def train_epoch(model, optimizer, scheduler, loader, amp_dtype=torch.bfloat16, use_amp=True, device_type="cpu"):
+    """base_harness.py:151-202 for a per-iteration schedule: returns (mean loss, accuracy %, per-step lrs, losses)."""
+    model.train()
+    total, correct, seen, lrs, losses = 0.0, 0, 0, [], []
+    for x, t in loader:
+        lrs.append(optimizer.param_groups[0]["lr"])
+        loss, out = train_step(model, optimizer, x, t, amp_dtype, use_amp, device_type)
+        total += loss; losses.append(loss)
+        correct += int((out.argmax(1) == t).sum()); seen += int(t.numel())
+        scheduler.step()
+    return total / len(loader), 100.0 * correct / max(seen, 1), lrs, losses

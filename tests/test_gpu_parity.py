@@ -795,7 +795,7 @@ def test_kblock_skipping_bit_identical_to_dense_walk(dev, case):
     padr = (-cout) % 64
     ref_f = torch.nn.functional.pad(ref_f, (0, 0, 0, padr)).reshape((cout + padr) // 64, 64, k * k * cin // 64, 64)
     occ_f = (ref_f != 0).any(dim=3).any(dim=1).cpu()
-    words = wf.kmask.cpu().to(torch.int64) & 0xFFFFFFFF
+    words = ops.kmask_rows(wf.kmask, wf.shape[1]).cpu().to(torch.int64) & 0xFFFFFFFF
     got_f = torch.tensor([[(int(words[r, b // 32]) >> (b % 32)) & 1 for b in range(occ_f.shape[1])] for r in range(occ_f.shape[0])]).bool()
     assert torch.equal(got_f, occ_f)
     empty, total = ops.kblock_occupancy(wf.kmask, wf.shape[1])
@@ -843,3 +843,46 @@ def test_skipped_block_report_on_structured_and_iid_masks(dev):
     assert rep2["fraction"] > 0.3
     for l in st.layers:
         ops.take_staged(l)
+
+
+def test_harness_train_epoch_vs_oracle(dev, tmp_path):
+    """``PruningHarness.train_epoch`` (reference base_harness.py:151-202) over a 5-step epoch of ResNet-18 / CIFAR-shape
+    batches with the TriangularSchedule stepped every iteration: the learning rate seen by every step equals the oracle's,
+    the epoch loss (mean of the per-step losses, read once at the end) and the accuracy follow the CPU oracle's epoch;
+    the last three steps are CUDA-graph replays whose LR comes from the device scalar."""
+    import refshim
+    import oracle.model as om
+    from oracle.train import train_epoch, triangular_schedule
+    from turboprune_b200.utils import custom_models as cm, pruning_utils as pu
+    cfg = refshim.make_cfg("resnet18", "cifar10", precision="bfloat16")
+    cfg["optimizer_params"]["lr"] = 0.02
+    cfg["experiment_params"]["epochs_per_level"] = 1
+    torch.manual_seed(0)
+    mine = cm.TorchVisionModel(cfg)
+    torch.manual_seed(1)
+    pu.prune_er_erk(mine, 0.2)
+    ref = om.build("resnet18", "cifar10")
+    ref.load_state_dict(mine.model.state_dict())
+    g = torch.Generator().manual_seed(3)
+    batches = [(torch.randn(64, 3, 32, 32, generator=g), torch.randint(0, 10, (64,), generator=g)) for _ in range(5)]
+    o = cfg.optimizer_params
+    opt_ref = torch.optim.SGD(ref.parameters(), lr=o.lr, momentum=o.momentum, weight_decay=o.weight_decay)
+    sch_ref = triangular_schedule(opt_ref, len(batches), 1, o.warmup_fraction)
+    loss_ref, acc_ref, lrs_ref, losses_ref = train_epoch(ref, opt_ref, sch_ref, batches)
+    h = refshim.make_harness(cfg, mine, 64, str(tmp_path))
+    h.train_loader = [(x.to(dev), t.to(dev)) for x, t in batches]
+    h._setup_scheduler(1)
+    seen_lr = []
+    real_step = h.train_step
+
+    def spy(batch):
+        seen_lr.append(h.optimizer.param_groups[0]["lr"])
+        return real_step(batch)
+    h.train_step = spy
+    out = h.train_epoch()
+    assert h._graph is not None
+    assert np.allclose(seen_lr, lrs_ref, rtol=1e-12)
+    dev_lr = float(next(iter(h.optimizer._lr_dev.values())).item())
+    assert abs(dev_lr - lrs_ref[-1]) <= 1e-6 * lrs_ref[-1]                   # the scalar the last replay consumed
+    assert abs(out["train_loss"] - loss_ref) / loss_ref <= 5e-3, (out, loss_ref, losses_ref)
+    assert abs(out["train_acc"] - acc_ref) <= 100.0 * 8 / 320                # a handful of argmax flips between two bf16 paths

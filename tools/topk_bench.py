@@ -21,8 +21,9 @@ def run(n, nseg, density, kind=0, reps=7, flush=True):
     for _ in range(reps):
         if flush: fl.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); _, thr, info = plan.run(k); b.record(); torch.cuda.synchronize()
+        a.record(); plan.enqueue(k); b.record(); torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))
+        _, thr, info = plan.finish(k)
     t = statistics.median(ts); bpe = 12 if kind == 0 else 16
     print(f"N={n} segs={nseg} density={density} kind={kind}: {t*1e3:.1f} us  {bpe*n/t/1e6:.0f} GB/s  info={info}", flush=True)
 

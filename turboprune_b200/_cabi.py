@@ -37,6 +37,10 @@ SIGNATURES = {
     "tp_topk_threshold_mask": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                        POINTER(c_int64), c_int, c_int64, c_int, c_void_p, c_void_p, c_size_t,
                                        POINTER(c_int64), c_void_p]),
+    "tp_topk_enqueue": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
+                                POINTER(c_int64), c_int, c_int64, c_int, c_void_p, c_void_p, c_size_t, c_int, c_void_p]),
+    "tp_topk_finish": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64), c_int, c_int64, c_int, c_void_p,
+                               c_void_p, c_size_t, POINTER(c_int64), c_void_p]),
     "tp_apply_threshold": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                    POINTER(c_int64), c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "tp_count_zeros": (c_int, [POINTER(c_void_p), POINTER(c_int64), c_int, c_void_p, c_void_p, c_size_t, c_void_p]),

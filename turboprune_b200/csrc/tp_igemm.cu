@@ -62,6 +62,13 @@ struct FwdParams {
   TapEntry taps[kMaxTaps];
 };
 
+// The staging call leaves the number of empty blocks behind the last mask row: zero (any iid unstructured mask) means
+// the K loop needs no per-block test at all.
+__device__ __forceinline__ const uint32_t* live_kmask(const uint32_t* km, int words, int N) {
+  if (km && __ldg(km + (size_t)((N + 63) >> 6) * words) == 0u) return nullptr;
+  return km;
+}
+
 // Which K blocks of an output-channel tile hold any non-zero weight: the OR of the occupancy words of the tile's 64-row
 // groups.  Producer and MMA thread walk the K loop with one of these each and must take identical decisions: a block is
 // processed when its bit is set, or when it is the last one and nothing was processed yet (the accumulator must be
@@ -163,6 +170,7 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      const uint32_t* const km = live_kmask(p.kmask, p.kmask_words, p.N);
       for (int tile = cl_id; tile < total_tiles; tile += n_cl) {
         const int m_g = tile / n_tiles, n_t = tile - m_g * n_tiles;   // m-major: CTAs running together share A tiles, weights stay in L2
         const int m_t = m_g * CL + cta_rank;
@@ -171,13 +179,13 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (p.a_mode == 1) decompose_pixel(m0, p.P_it, p.Q_it, cn, cp, cq);
         const int cw = p.base_w + cq * p.step_w, ch = p.base_h + cp * p.step_h;
         KSkip ks; bool any = false;
-        if (p.kmask) ks.begin(p.kmask, p.kmask_words, n_t * BLOCK_N, BLOCK_N, p.N);
+        if (km) ks.begin(km, p.kmask_words, n_t * BLOCK_N, BLOCK_N, p.N);
         // nested tap / channel-chunk loops: no integer division on the single producer thread
         // (the first ncu source view showed the producer, not TMA or the tensor pipe, as the limiter)
         for (int tap = 0; tap < p.ntaps; ++tap) {
           const TapEntry te = p.taps[tap];
           for (int cc = 0; cc < p.cchunks; ++cc) {
-            if (p.kmask) {
+            if (km) {
               const bool last = tap == p.ntaps - 1 && cc == p.cchunks - 1;
               if (!ks.on((te.kofs >> 6) + cc) && !(last && !any)) continue;      // all-zero weight block: no load, no MMA
               any = true;
@@ -214,16 +222,17 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       constexpr uint32_t idesc = make_idesc_bf16(kBlockM * CL, BLOCK_N, 0, 0);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      const uint32_t* const km = live_kmask(p.kmask, p.kmask_words, p.N);
       for (int tile = cl_id; tile < total_tiles; tile += n_cl) {
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
         KSkip ks; uint32_t any = 0;
-        if (p.kmask) { const int n_t = tile % n_tiles; ks.begin(p.kmask, p.kmask_words, n_t * BLOCK_N, BLOCK_N, p.N); }
+        if (km) { const int n_t = tile % n_tiles; ks.begin(km, p.kmask_words, n_t * BLOCK_N, BLOCK_N, p.N); }
         for (int tap = 0; tap < p.ntaps; ++tap) {
-          const int kb0 = p.kmask ? (p.taps[tap].kofs >> 6) : 0;
+          const int kb0 = km ? (p.taps[tap].kofs >> 6) : 0;
           for (int cc = 0; cc < p.cchunks; ++cc) {
-            if (p.kmask) {
+            if (km) {
               const bool last = tap == p.ntaps - 1 && cc == p.cchunks - 1;
               if (!ks.on(kb0 + cc) && !(last && !any)) continue;               // same decision as the producer
             }

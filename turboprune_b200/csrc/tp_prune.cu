@@ -2,27 +2,31 @@
 //
 // Replaces utils/pruning_utils.py:73-87 / :186-203 / :263-283 of the reference
 // (per-layer score temporaries, torch.cat, single-CTA 16-pass torch.kthvalue, per-layer
-// torch.where) with a bracketed single sweep over the weights:
+// torch.where) with ONE cooperative kernel (k_topk_fused) whose phases are separated by grid-wide barriers:
 //
-//   1. k_sample_coarse: 2^20 strided samples -> sample keys + 2048-bin histogram of key bits [30:20]
-//   2. k_sample_fine  : histograms of bits [19:9] inside the coarse bins that hold the sample
-//                       quantile +- 5 sigma of its rank error (shared-memory privatised, no hot atomics);
-//                       the sweep's prologue turns them into a key bracket [lo, hi) that contains
-//                       the true k-th key w.h.p.
-//   3. k_sweep       : ONE pass over (w, m[, g]) at HBM rate: counts keys < lo and == lo,
-//                      writes the final mask for every key outside (lo, hi) and appends the
-//                      few keys inside to a candidate list            (12 B/elem mag, 16 snip)
-//   4. k_resolve     : one CTA selects the exact (k - n_lt - n_eq)-th candidate (8-bit radix,
-//                      data in L2), emits the threshold and patches the candidates' masks.
+//   P0 sample   : 2^20 strided samples (runs of 4 neighbours), kept in shared memory; 2048-bin histogram of key
+//                 bits [30:20], shared-memory privatised
+//   P1 refine   : every CTA locates the coarse bins of the two bracket ranks (sample quantile +- 5 sigma of its
+//                 rank error) and histograms bits [19:9] of its own samples inside them
+//   P2 sweep    : bracket [lo, hi) from the fine histograms, then ONE pass over (w, m[, g]) at HBM rate: counts keys
+//                 < lo and == lo, writes the final mask for every key outside (lo, hi) and appends the few keys
+//                 inside to a candidate list                                   (12 B/elem mag, 16 snip / synflow)
+//   P3 digit    : all CTAs histogram the top radix digit of the candidates (data in L2)
+//   P4 narrow   : every CTA picks the digit, the candidates that match it (a few dozen) go to a second list
+//   P5 finish   : every CTA selects the exact key among those in shared memory (no further barrier), patches its
+//                 share of the candidates' masks; CTA 0 publishes threshold and status.
 //
-// If the bracket misses (adversarial ties, overflow of the candidate list) the host falls
-// back to an exact 3-pass 11/11/10-bit radix select over the full data + one apply pass.
+// (Round 1 ran this as six kernels + a blocking status read-back: 158 us for ResNet-50's 25.5 M weights of which the
+// sweep was 60 us.)  If the bracket misses (adversarial ties, overflow of a list) the status says so and the host
+// runs an exact 3-pass 11/11/10-bit radix select over the full data + one apply pass — tp_topk_finish, which is
+// also where the status is read back, so the fast path itself never blocks the stream.
 // Both paths are bit-exact with torch.kthvalue + torch.where(score <= thr, 0, 1).
 //
 // Keys: scores are |.| of fp32 products, so their IEEE bit patterns order like unsigned
 // integers; NaN patterns (> 0x7f800000) sort above +inf exactly like ATen's radix key
 // (SortingRadixSelect.cuh:20-39).
 #include "tp_common.cuh"
+#include <cooperative_groups.h>
 
 namespace tp {
 
@@ -36,6 +40,7 @@ struct SelState {
   unsigned int c_lo, c_hi;            // coarse sample bins of the two bracket ranks
   unsigned long long before_lo, before_hi;
   unsigned long long k_rem;
+  unsigned long long n_cand2;         // second-level list (candidates matching the top digit)
 };
 
 constexpr int kSampleBits = 20;
@@ -101,65 +106,7 @@ __device__ __forceinline__ void block_find_rank(const unsigned int* __restrict__
   __syncthreads();
 }
 
-// Bracket search, level 1: strided sample -> keys (kept for level 2) + 2048-bin histogram of key
-// bits [30:20], privatised in shared memory (no hot global atomics).
 constexpr int kCoarseShift = 20, kFineShift = 9, kDigitBins = 2048;
-
-template <int KIND>
-__global__ void __launch_bounds__(256) k_sample_coarse(const Seg* __restrict__ segs, int n_seg, long long N, long long S,
-                                                       unsigned int* __restrict__ skeys, unsigned int* __restrict__ hist_c) {
-  __shared__ unsigned int s_h[kDigitBins];
-  const int t = threadIdx.x;
-  for (int i = t; i < kDigitBins; i += 256) s_h[i] = 0;
-  __syncthreads();
-  // samples are taken in runs of 4 neighbouring elements: one 32-byte sector per operand serves 4 samples
-  // (a quarter of the scattered DRAM traffic and of the segment searches of single-element sampling)
-  const long long G = (S + 3) >> 2;
-  for (long long gi = blockIdx.x * 256ll + t; gi < G; gi += (long long)gridDim.x * 256) {
-    long long e = (long long)(((unsigned long long)gi * (unsigned long long)N) / (unsigned long long)G);
-    const int si = find_seg_by_elem(segs, n_seg, e);
-    const Seg& sg = segs[si];
-    long long l0 = (e - sg.start) & ~3ll;
-    if (l0 + 3 >= sg.n) l0 = sg.n >= 4 ? sg.n - 4 : 0;
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-      const long long j = gi * 4 + u;
-      if (j >= S) break;
-      const long long l = l0 + u < sg.n ? l0 + u : sg.n - 1;
-      const unsigned int key = seg_key<KIND>(sg, l);
-      skeys[j] = key;
-      atomicAdd(&s_h[key >> kCoarseShift], 1u);
-    }
-  }
-  __syncthreads();
-  for (int i = t; i < kDigitBins; i += 256) if (s_h[i]) atomicAdd(&hist_c[i], s_h[i]);
-}
-
-// Level 2: every CTA locates the coarse bins of the two bracket ranks (8 KB of L2 reads), then the
-// sample keys inside those bins are histogrammed on bits [19:9].
-__global__ void __launch_bounds__(256) k_sample_fine(const unsigned int* __restrict__ skeys, long long S,
-                                                     const unsigned int* __restrict__ hist_c,
-                                                     long long r_lo, long long r_hi,
-                                                     unsigned int* __restrict__ hist_f, SelState* st) {
-  __shared__ unsigned int s_h[2][kDigitBins];
-  __shared__ unsigned int s_bin[2];
-  __shared__ unsigned long long s_before[2], s_warp[32];
-  const int t = threadIdx.x;
-  if (t < 2) { s_bin[t] = 0; s_before[t] = 0; }
-  for (int i = t; i < 2 * kDigitBins; i += 256) (&s_h[0][0])[i] = 0;
-  __syncthreads();
-  block_find_rank<kDigitBins / 256>(hist_c, (unsigned long long)(r_lo < 1 ? 1 : r_lo), &s_bin[0], &s_before[0], s_warp);
-  block_find_rank<kDigitBins / 256>(hist_c, (unsigned long long)(r_hi > S ? S : r_hi), &s_bin[1], &s_before[1], s_warp);
-  const unsigned int c_lo = s_bin[0], c_hi = s_bin[1];
-  if (blockIdx.x == 0 && t == 0) { st->c_lo = c_lo; st->c_hi = c_hi; st->before_lo = s_before[0]; st->before_hi = s_before[1]; }
-  for (long long j = blockIdx.x * 256ll + t; j < S; j += (long long)gridDim.x * 256) {
-    const unsigned int key = skeys[j], c = key >> kCoarseShift, f = (key >> kFineShift) & (kDigitBins - 1);
-    if (c == c_lo) atomicAdd(&s_h[0][f], 1u);
-    if (c == c_hi) atomicAdd(&s_h[1][f], 1u);
-  }
-  __syncthreads();
-  for (int i = t; i < 2 * kDigitBins; i += 256) { unsigned int v = (&s_h[0][0])[i]; if (v) atomicAdd(&hist_f[i], v); }
-}
 
 // ---------------------------------------------------------------------------------------------
 struct SweepCtx {
@@ -184,40 +131,118 @@ __device__ __forceinline__ float classify(SweepCtx& c, unsigned int key, long lo
   return 0.f;   // provisional; k_resolve patches it
 }
 
+__device__ __forceinline__ int resolve_shift0(unsigned int lo, unsigned int hi) {
+  const unsigned int span = lo ^ (hi - 1u);
+  const int top = span ? (31 - __clz(span)) : 0;
+  return (top / 11) * 11;
+}
+
+constexpr int kLocalKeys = 4096;      // sample keys one CTA keeps in shared memory between P0 and P1
+constexpr int kCand2 = 4096;          // capacity of the second-level list
+
+struct TopkArgs {
+  const Seg* segs; int n_seg;
+  long long tiles, N, S, k, r_lo, r_hi;
+  SelState* st;
+  unsigned int* hist;                 // [0,2048) coarse, [2048,6144) two fine, [6144,8192) candidate digit
+  uint2* cand; unsigned int cap;
+  unsigned int* cand2;                // keys of the second-level list
+  float* thr_out;
+};
+
 template <int KIND, bool WRITE>
-__global__ void __launch_bounds__(kSweepThreads) k_sweep(const Seg* __restrict__ segs, int n_seg, long long tiles,
-                                                         SelState* st, uint2* __restrict__ cand, unsigned int cap,
-                                                         const unsigned int* __restrict__ hist_f,
-                                                         long long r_lo, long long r_hi, long long S) {
+__global__ void __launch_bounds__(kSweepThreads) k_topk_fused(const TopkArgs a) {
+  namespace cg = cooperative_groups;
+  cg::grid_group grid = cg::this_grid();
+  __shared__ __align__(16) unsigned int s_keys[kLocalKeys];          // P0/P1: this CTA's sample keys;  P5: the second-level list
+  __shared__ unsigned int s_h[2 * kDigitBins];          // histograms (coarse, then the two fine ones, then select digits)
   __shared__ uint2 s_cand[kSmemCand];
   __shared__ unsigned int s_ncand;
   __shared__ unsigned long long s_base;
   __shared__ unsigned int s_red[2][kSweepThreads / 32];
   __shared__ unsigned int s_bin[2];
   __shared__ unsigned long long s_before[2], s_warp[32];
-  // bracket [lo, hi) from the fine sample histograms — every CTA derives the same two keys
-  if (threadIdx.x < 2) { s_bin[threadIdx.x] = 0; s_before[threadIdx.x] = 0; }
+  const int t = threadIdx.x;
+  SelState* st = a.st;
+  unsigned int* hist_c = a.hist;
+  unsigned int* hist_f = a.hist + kDigitBins;
+  unsigned int* hist_r = a.hist + 3 * kDigitBins;
+
+  // ---------------- P0: strided sample in runs of 4 neighbouring elements (one 32-byte sector per operand serves 4
+  // samples), keys stay in shared memory; coarse histogram of key bits [30:20] ----------------
+  for (int i = t; i < kDigitBins; i += kSweepThreads) s_h[i] = 0;
   __syncthreads();
-  block_find_rank<kDigitBins / kSweepThreads>(hist_f, (unsigned long long)(r_lo < 1 ? 1 : r_lo) - st->before_lo,
+  const long long G = (a.S + 3) >> 2;
+  const long long first = blockIdx.x * (long long)kSweepThreads, gstride = (long long)gridDim.x * kSweepThreads;
+  const int rounds = first < G ? (int)((G - first + gstride - 1) / gstride) : 0;   // uniform over the CTA; host keeps it <= kLocalKeys / 1024
+  for (int r = 0; r < rounds; ++r) {
+    const long long gi = first + t + r * gstride;
+    unsigned int key4[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};     // "no sample" (runs past S)
+    if (gi < G) {
+      long long e = (long long)(((unsigned long long)gi * (unsigned long long)a.N) / (unsigned long long)G);
+      const int si = find_seg_by_elem(a.segs, a.n_seg, e);
+      const Seg& sg = a.segs[si];
+      long long l0 = (e - sg.start) & ~3ll;
+      if (l0 + 3 >= sg.n) l0 = sg.n >= 4 ? sg.n - 4 : 0;
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long j = gi * 4 + u;
+        if (j < a.S) {
+          const long long l = l0 + u < sg.n ? l0 + u : sg.n - 1;
+          key4[u] = seg_key<KIND>(sg, l);
+          atomicAdd(&s_h[key4[u] >> kCoarseShift], 1u);
+        }
+      }
+    }
+    *reinterpret_cast<uint4*>(&s_keys[(r * kSweepThreads + t) * 4]) = make_uint4(key4[0], key4[1], key4[2], key4[3]);
+  }
+  __syncthreads();
+  for (int i = t; i < kDigitBins; i += kSweepThreads) if (s_h[i]) atomicAdd(&hist_c[i], s_h[i]);
+  grid.sync();
+
+  // ---------------- P1: coarse bins of the two bracket ranks (every CTA, 8 KB of L2 reads), fine histograms of the
+  // own samples that fall inside them ----------------
+  if (t < 2) { s_bin[t] = 0; s_before[t] = 0; }
+  for (int i = t; i < 2 * kDigitBins; i += kSweepThreads) s_h[i] = 0;
+  __syncthreads();
+  block_find_rank<kDigitBins / kSweepThreads>(hist_c, (unsigned long long)(a.r_lo < 1 ? 1 : a.r_lo), &s_bin[0], &s_before[0], s_warp);
+  block_find_rank<kDigitBins / kSweepThreads>(hist_c, (unsigned long long)(a.r_hi > a.S ? a.S : a.r_hi), &s_bin[1], &s_before[1], s_warp);
+  const unsigned int c_lo = s_bin[0], c_hi = s_bin[1];
+  const unsigned long long before_lo = s_before[0], before_hi = s_before[1];
+  if (blockIdx.x == 0 && t == 0) { st->c_lo = c_lo; st->c_hi = c_hi; st->before_lo = before_lo; st->before_hi = before_hi; }
+  for (int i = t; i < rounds * kSweepThreads * 4; i += kSweepThreads) {
+    const unsigned int key = s_keys[i];
+    if (key == 0xFFFFFFFFu) continue;
+    const unsigned int c = key >> kCoarseShift, f = (key >> kFineShift) & (kDigitBins - 1);
+    if (c == c_lo) atomicAdd(&s_h[f], 1u);
+    if (c == c_hi) atomicAdd(&s_h[kDigitBins + f], 1u);
+  }
+  __syncthreads();
+  for (int i = t; i < 2 * kDigitBins; i += kSweepThreads) if (s_h[i]) atomicAdd(&hist_f[i], s_h[i]);
+  grid.sync();
+
+  // ---------------- P2: bracket [lo, hi) from the fine histograms — every CTA derives the same two keys — and the
+  // sweep ----------------
+  if (t < 2) { s_bin[t] = 0; s_before[t] = 0; }
+  __syncthreads();
+  block_find_rank<kDigitBins / kSweepThreads>(hist_f, (unsigned long long)(a.r_lo < 1 ? 1 : a.r_lo) - before_lo,
                                               &s_bin[0], &s_before[0], s_warp);
-  block_find_rank<kDigitBins / kSweepThreads>(hist_f + kDigitBins, (unsigned long long)(r_hi > S ? S : r_hi) - st->before_hi,
+  block_find_rank<kDigitBins / kSweepThreads>(hist_f + kDigitBins, (unsigned long long)(a.r_hi > a.S ? a.S : a.r_hi) - before_hi,
                                               &s_bin[1], &s_before[1], s_warp);
-  unsigned int lo = (st->c_lo << kCoarseShift) | (s_bin[0] << kFineShift);
-  unsigned int hi = (((st->c_hi << 11) | s_bin[1]) + 1u) << kFineShift;
-  if (r_lo < 1) lo = 0u;                              // no lower bound
-  if (r_hi > S || hi > 0x80000000u || hi == 0u) hi = 0x80000000u;   // no upper bound (keys are <= 0x7fffffff)
-  if (blockIdx.x == 0 && threadIdx.x == 0) { st->lo = lo; st->hi = hi; }
+  unsigned int lo = (c_lo << kCoarseShift) | (s_bin[0] << kFineShift);
+  unsigned int hi = (((c_hi << 11) | s_bin[1]) + 1u) << kFineShift;
+  if (a.r_lo < 1) lo = 0u;                              // no lower bound
+  if (a.r_hi > a.S || hi > 0x80000000u || hi == 0u) hi = 0x80000000u;   // no upper bound (keys are <= 0x7fffffff)
+  if (blockIdx.x == 0 && t == 0) { st->lo = lo; st->hi = hi; }
   SweepCtx c;
   c.lo = lo; c.hi = hi; c.n_lt = 0; c.n_eq = 0;
-  c.s_cand = s_cand; c.s_ncand = &s_ncand; c.st = st; c.cand = cand; c.cap = cap;
-  const int t = threadIdx.x;
+  c.s_cand = s_cand; c.s_ncand = &s_ncand; c.st = st; c.cand = a.cand; c.cap = a.cap;
   constexpr int kVecIters = kTileElems / (kSweepThreads * 4);   // 4
-
-  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+  for (long long tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
     if (t == 0) s_ncand = 0;
     __syncthreads();
-    const int si = find_seg(segs, n_seg, tile);
-    const Seg sg = segs[si];
+    const int si = find_seg(a.segs, a.n_seg, tile);
+    const Seg sg = a.segs[si];
     const long long base = (tile - sg.tile0) * kTileElems;
     const long long rem = sg.n - base;
     const int n_in = rem < kTileElems ? (int)rem : kTileElems;
@@ -263,119 +288,100 @@ __global__ void __launch_bounds__(kSweepThreads) k_sweep(const Seg* __restrict__
       __syncthreads();
       unsigned long long b = s_base;
       for (unsigned int i = t; i < nc; i += kSweepThreads)
-        if (b + i < cap) cand[b + i] = s_cand[i];
+        if (b + i < a.cap) a.cand[b + i] = s_cand[i];
     }
     __syncthreads();
   }
-  // block-reduce the two counters, one atomic pair per CTA
-  unsigned int a = c.n_lt, b = c.n_eq;
-  for (int o = 16; o; o >>= 1) { a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o); }
-  if ((t & 31) == 0) { s_red[0][t >> 5] = a; s_red[1][t >> 5] = b; }
-  __syncthreads();
-  if (t == 0) {
-    unsigned long long A = 0, B = 0;
-    for (int i = 0; i < kSweepThreads / 32; ++i) { A += s_red[0][i]; B += s_red[1][i]; }
-    if (A) atomicAdd(&st->n_lt, A);
-    if (B) atomicAdd(&st->n_eq, B);
-  }
-}
-
-// ---------------------------------------------------------------------------------------------
-// Resolve, stage 1 (multi-CTA): decide success of the bracket and histogram the FIRST radix digit of all
-// candidates (the pass that touches every candidate) with shared-memory privatised bins.
-__device__ __forceinline__ int resolve_shift0(unsigned int lo, unsigned int hi) {
-  const unsigned int span = lo ^ (hi - 1u);
-  const int top = span ? (31 - __clz(span)) : 0;
-  return (top / 11) * 11;
-}
-
-__global__ void __launch_bounds__(256) k_cand_hist(const SelState* __restrict__ st, const uint2* __restrict__ cand,
-                                                   unsigned int cap, unsigned int* __restrict__ hist_r) {
-  __shared__ unsigned int s_h[kDigitBins];
-  const unsigned long long k = st->k, A = st->n_lt, B = st->n_eq, C = st->n_cand;
-  if (k <= A + B || C > cap || k > A + B + C) return;        // nothing to select (k_resolve decides what it means)
-  const int t = threadIdx.x;
-  for (int i = t; i < kDigitBins; i += 256) s_h[i] = 0;
-  __syncthreads();
-  const int shift = resolve_shift0(st->lo, st->hi);
-  const unsigned int n = (unsigned int)C;
-  for (unsigned int i = blockIdx.x * 256u + t; i < n; i += gridDim.x * 256u)
-    atomicAdd(&s_h[(cand[i].x >> shift) & (kDigitBins - 1)], 1u);
-  __syncthreads();
-  for (int i = t; i < kDigitBins; i += 256) if (s_h[i]) atomicAdd(&hist_r[i], s_h[i]);
-}
-
-// Resolve, stage 2 (one CTA): pick the first digit from the global histogram, finish the remaining digits over
-// the (now ~1/2048-th) matching candidates, publish threshold and status.
-__global__ void __launch_bounds__(1024) k_resolve(SelState* st, const uint2* __restrict__ cand, unsigned int cap,
-                                                  const unsigned int* __restrict__ hist_r, float* __restrict__ thr_out) {
-  __shared__ unsigned int s_hist[kDigitBins];
-  __shared__ unsigned int s_prefix, s_bin;
-  __shared__ unsigned long long s_before, s_krem, s_warp[32];
-  __shared__ int s_status;
-  const int t = threadIdx.x;
-  const unsigned long long k = st->k, A = st->n_lt, B = st->n_eq, C = st->n_cand;
-  if (t == 0) {
-    int status = 0;
-    if (k <= A || C > cap) status = 1;            // k-th lies below the bracket / list overflow
-    else if (k <= A + B) { st->thr_key = st->lo; }
-    else if (k > A + B + C) status = 1;           // k-th lies above the bracket
-    s_status = status;
-    s_krem = k - A - B;
-  }
-  __syncthreads();
-  if (s_status == 1) { if (t == 0) st->status = 1; return; }
-  const unsigned int n = (unsigned int)C;
-  constexpr int U = 8;                            // independent L2 loads in flight per thread
-  if (k > A + B) {
-    const int shift0 = resolve_shift0(st->lo, st->hi);
-    if (t == 0) { s_prefix = (shift0 + 11 >= 32) ? 0u : (st->lo & (0xFFFFFFFFu << (shift0 + 11))); s_bin = 0; s_before = 0; }
+  {  // block-reduce the two counters, one atomic pair per CTA
+    unsigned int x = c.n_lt, y = c.n_eq;
+    for (int o = 16; o; o >>= 1) { x += __shfl_xor_sync(0xffffffffu, x, o); y += __shfl_xor_sync(0xffffffffu, y, o); }
+    if ((t & 31) == 0) { s_red[0][t >> 5] = x; s_red[1][t >> 5] = y; }
     __syncthreads();
-    block_find_rank<kDigitBins / 1024>(hist_r, s_krem, &s_bin, &s_before, s_warp);
-    if (t == 0) { s_prefix |= (s_bin << shift0); s_krem -= s_before; }
+    if (t == 0) {
+      unsigned long long A = 0, B = 0;
+      for (int i = 0; i < kSweepThreads / 32; ++i) { A += s_red[0][i]; B += s_red[1][i]; }
+      if (A) atomicAdd(&st->n_lt, A);
+      if (B) atomicAdd(&st->n_eq, B);
+    }
+  }
+  grid.sync();
+
+  // ---------------- P3: does the bracket hold the k-th key?  (every CTA takes the same decision from the same counters)
+  const unsigned long long k = (unsigned long long)a.k, A = st->n_lt, B = st->n_eq, C = st->n_cand;
+  if (k <= A || C > a.cap || k > A + B + C) {           // below / above the bracket, or the list overflowed: exact fallback
+    if (blockIdx.x == 0 && t == 0) st->status = 1;
+    return;
+  }
+  const unsigned int n = (unsigned int)C;
+  unsigned int thr;
+  if (k <= A + B) {
+    thr = lo;                                             // the k-th key is the lower bracket edge itself
+  } else {
+    unsigned long long krem = k - A - B;
+    const int shift0 = resolve_shift0(lo, hi);
+    for (int i = t; i < kDigitBins; i += kSweepThreads) s_h[i] = 0;
     __syncthreads();
-    for (int shift = shift0 - 11; shift >= 0; shift -= 11) {
-      for (int i = t; i < kDigitBins; i += 1024) s_hist[i] = 0;
-      if (t == 0) { s_bin = 0; s_before = 0; }
-      __syncthreads();
-      const unsigned int prefix = s_prefix;
-      const unsigned int pmask = 0xFFFFFFFFu << (shift + 11);
-      for (unsigned int base = 0; base < n; base += 1024 * U) {
-        unsigned int key[U]; bool ok[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-          const unsigned int i = base + u * 1024 + t;
-          ok[u] = i < n;
-          key[u] = ok[u] ? cand[i].x : 0u;
+    for (unsigned int i = blockIdx.x * (unsigned)kSweepThreads + t; i < n; i += gridDim.x * (unsigned)kSweepThreads)
+      atomicAdd(&s_h[(a.cand[i].x >> shift0) & (kDigitBins - 1)], 1u);
+    __syncthreads();
+    for (int i = t; i < kDigitBins; i += kSweepThreads) if (s_h[i]) atomicAdd(&hist_r[i], s_h[i]);
+    grid.sync();
+
+    // ---------------- P4: pick the top digit (every CTA); candidates that carry it form the second-level list
+    if (t < 2) { s_bin[t] = 0; s_before[t] = 0; }
+    __syncthreads();
+    block_find_rank<kDigitBins / kSweepThreads>(hist_r, krem, &s_bin[0], &s_before[0], s_warp);
+    unsigned int prefix = ((shift0 + 11 >= 32) ? 0u : (lo & (0xFFFFFFFFu << (shift0 + 11)))) | (s_bin[0] << shift0);
+    krem -= s_before[0];
+    if (shift0 > 0) {
+      const unsigned int pmask = 0xFFFFFFFFu << shift0;
+      for (unsigned int i = blockIdx.x * (unsigned)kSweepThreads + t; i < n; i += gridDim.x * (unsigned)kSweepThreads) {
+        const unsigned int key = a.cand[i].x;
+        if ((key & pmask) == prefix) {
+          const unsigned long long slot = atomicAdd(&st->n_cand2, 1ull);
+          if (slot < (unsigned long long)kCand2) a.cand2[slot] = key;
         }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-          if (ok[u] && (key[u] & pmask) == prefix) atomicAdd(&s_hist[(key[u] >> shift) & (kDigitBins - 1)], 1u);
       }
-      __syncthreads();
-      block_find_rank<kDigitBins / 1024>(s_hist, s_krem, &s_bin, &s_before, s_warp);
-      if (t == 0) { s_prefix = prefix | (s_bin << shift); s_krem -= s_before; }
-      __syncthreads();
-    }
-    if (t == 0) st->thr_key = s_prefix;
-  }
-  __syncthreads();
-  if (t == 0) {
-    const unsigned int thr = st->thr_key;
-    *thr_out = __uint_as_float(thr);
-    st->status = (thr > 0x7f800000u) ? 2 : 0;
-  }
-}
+      grid.sync();
 
-// Resolve, stage 3 (multi-CTA): final mask value of every candidate (the sweep wrote a provisional 0).
-__global__ void __launch_bounds__(256) k_cand_patch(const Seg* __restrict__ segs, int n_seg, const SelState* __restrict__ st,
-                                                    const uint2* __restrict__ cand, unsigned int cap) {
-  if (st->status != 0 || st->n_cand > cap) return;          // fallback / NaN threshold: another kernel rewrites every mask
-  const unsigned int thr = st->thr_key, n = (unsigned int)st->n_cand;
-  for (unsigned int i = blockIdx.x * 256u + threadIdx.x; i < n; i += gridDim.x * 256u) {
-    const uint2 c = cand[i];
-    const int si = find_seg_by_elem(segs, n_seg, (long long)c.y);
-    segs[si].mo[(long long)c.y - segs[si].start] = (c.x <= thr) ? 0.f : 1.f;
+      // ---------------- P5: finish the remaining digits over the second-level list in shared memory (every CTA, no barrier)
+      const unsigned long long n2 = st->n_cand2;
+      if (n2 > (unsigned long long)kCand2) {            // thousands of candidates share 11+ leading bits (heavy ties): exact fallback
+        if (blockIdx.x == 0 && t == 0) st->status = 1;
+        return;
+      }
+      for (unsigned int i = t; i < (unsigned int)n2; i += kSweepThreads) s_keys[i] = a.cand2[i];
+      __syncthreads();
+      for (int shift = shift0 - 11; shift >= 0; shift -= 11) {
+        for (int i = t; i < kDigitBins; i += kSweepThreads) s_h[i] = 0;
+        if (t < 2) { s_bin[t] = 0; s_before[t] = 0; }
+        __syncthreads();
+        const unsigned int pm = 0xFFFFFFFFu << (shift + 11);
+        for (unsigned int i = t; i < (unsigned int)n2; i += kSweepThreads)
+          if ((s_keys[i] & pm) == prefix) atomicAdd(&s_h[(s_keys[i] >> shift) & (kDigitBins - 1)], 1u);
+        __syncthreads();
+        block_find_rank<kDigitBins / kSweepThreads>(s_h, krem, &s_bin[0], &s_before[0], s_warp);
+        prefix |= (s_bin[0] << shift);
+        krem -= s_before[0];
+        __syncthreads();
+      }
+    }
+    thr = prefix;
+  }
+  // final mask value of every candidate (the sweep wrote a provisional 0); a NaN threshold keeps everything (host applies)
+  if (WRITE && thr <= 0x7f800000u) {
+    for (unsigned int i = blockIdx.x * (unsigned)kSweepThreads + t; i < n; i += gridDim.x * (unsigned)kSweepThreads) {
+      const uint2 cd = a.cand[i];
+      if (cd.x > thr) {
+        const int si = find_seg_by_elem(a.segs, a.n_seg, (long long)cd.y);
+        a.segs[si].mo[(long long)cd.y - a.segs[si].start] = 1.f;
+      }
+    }
+  }
+  if (blockIdx.x == 0 && t == 0) {
+    st->thr_key = thr;
+    *a.thr_out = __uint_as_float(thr);
+    st->status = (thr > 0x7f800000u) ? 2 : 0;
   }
 }
 
@@ -513,17 +519,45 @@ static int sweep_grid(long long tiles) {
   return (int)(tiles < g ? (tiles > 0 ? tiles : 1) : g);
 }
 
-template <int KIND>
-static int run_topk(const Seg* d_segs, int n_seg, long long tiles, long long N, long long k, bool write,
-                    SelState* d_st, unsigned int* d_hist, unsigned int* d_skeys, uint2* d_cand, unsigned int cap,
-                    float* thr_out, int64_t* info, cudaStream_t st) {
-  SelState h = {};
-  h.k = (unsigned long long)k;
-  h.hi = 0x80000000u;
-  TP_CUDA_CHECK(cudaMemcpyAsync(d_st, &h, sizeof(h), cudaMemcpyHostToDevice, st));
-  // d_hist layout: [0,2048) coarse sample histogram, [2048, 6144) two fine histograms, [6144, 8192) candidate digit
-  TP_CUDA_CHECK(cudaMemsetAsync(d_hist, 0, sizeof(unsigned int) * 4 * kDigitBins, st));
-  const long long S = N < (1ll << kSampleBits) ? N : (1ll << kSampleBits);
+// Workspace layout shared by enqueue / finish (both re-derive it from the same arguments).
+struct TopkWs {
+  Seg* segs; SelState* st; unsigned int* hist; unsigned int* cand2; uint2* cand; unsigned int cap;
+};
+static int carve_topk_ws(void* ws, size_t ws_bytes, int n_seg, long long N, TopkWs* out) {
+  Arena ar(ws, ws_bytes);
+  out->segs = (Seg*)ar.take(sizeof(Seg) * (size_t)n_seg);
+  // state and histograms are adjacent: one memset clears both before every call
+  out->st = (SelState*)ar.take(align_up(sizeof(SelState), 256) + sizeof(unsigned int) * 4 * kDigitBins);
+  out->hist = out->st ? (unsigned int*)((char*)out->st + align_up(sizeof(SelState), 256)) : nullptr;
+  out->cand2 = (unsigned int*)ar.take(sizeof(unsigned int) * kCand2);
+  out->cap = cand_cap(N);
+  out->cand = (uint2*)ar.take(sizeof(uint2) * (size_t)out->cap);
+  return (out->segs && out->st && out->cand2 && out->cand) ? TP_OK : TP_ERR_WORKSPACE;
+}
+
+template <int KIND, bool WRITE>
+static int fused_grid(int* grid_out) {
+  static int cached = 0;
+  if (!cached) {
+    int occ = 0;
+    TP_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_topk_fused<KIND, WRITE>, kSweepThreads, 0));
+    if (occ < 1) return TP_ERR_UNSUPPORTED;
+    if (occ > 4) occ = 4;
+    cached = occ * sm_count();
+  }
+  *grid_out = cached;
+  return TP_OK;
+}
+
+// The whole fast path: one memset + one cooperative kernel, no host synchronisation.
+template <int KIND, bool WRITE>
+static int enqueue_topk(const TopkWs& w, int n_seg, long long tiles, long long N, long long k, float* thr_out, cudaStream_t st) {
+  int grid = 0;
+  int rc = fused_grid<KIND, WRITE>(&grid); if (rc) return rc;
+  TP_CUDA_CHECK(cudaMemsetAsync(w.st, 0, align_up(sizeof(SelState), 256) + sizeof(unsigned int) * 4 * kDigitBins, st));
+  long long S = N < (1ll << kSampleBits) ? N : (1ll << kSampleBits);
+  const long long smax = (long long)grid * kLocalKeys;             // what the CTAs can keep in shared memory
+  if (S > smax) S = smax;
   // sample rank of the population's k-th element and the +-5 sigma band of its sampling error
   long long rs = (long long)(((unsigned __int128)(unsigned long long)k * (unsigned long long)S + (unsigned long long)N - 1) /
                              (unsigned long long)N);
@@ -532,43 +566,48 @@ static int run_topk(const Seg* d_segs, int n_seg, long long tiles, long long N, 
   const double pq = (double)rs / (double)S;
   // +4 per segment: runs are clamped at segment ends, so a few samples may repeat (also when S == N)
   const long long delta = (long long)(5.0 * sqrt((double)S * pq * (1.0 - pq)) + 8.0) + 4ll * n_seg;
-  const long long r_lo = rs - delta, r_hi = rs + delta;
-  const int sgrid = (int)((S + 255) / 256 < (long long)sm_count() * 4 ? (S + 255) / 256 : (long long)sm_count() * 4);
-  k_sample_coarse<KIND><<<sgrid, 256, 0, st>>>(d_segs, n_seg, N, S, d_skeys, d_hist);
-  k_sample_fine<<<sgrid, 256, 0, st>>>(d_skeys, S, d_hist, r_lo, r_hi, d_hist + kDigitBins, d_st);
-  const int grid = sweep_grid(tiles);
-  if (write) k_sweep<KIND, true><<<grid, kSweepThreads, 0, st>>>(d_segs, n_seg, tiles, d_st, d_cand, cap, d_hist + kDigitBins, r_lo, r_hi, S);
-  else       k_sweep<KIND, false><<<grid, kSweepThreads, 0, st>>>(d_segs, n_seg, tiles, d_st, d_cand, cap, d_hist + kDigitBins, r_lo, r_hi, S);
-  k_cand_hist<<<64, 256, 0, st>>>(d_st, d_cand, cap, d_hist + 3 * kDigitBins);
-  k_resolve<<<1, 1024, 0, st>>>(d_st, d_cand, cap, d_hist + 3 * kDigitBins, thr_out);
-  if (write) k_cand_patch<<<64, 256, 0, st>>>(d_segs, n_seg, d_st, d_cand, cap);
-  TP_LAUNCH_CHECK();
-  TP_CUDA_CHECK(cudaMemcpyAsync(&h, d_st, sizeof(h), cudaMemcpyDeviceToHost, st));
+  TopkArgs a;
+  a.segs = w.segs; a.n_seg = n_seg; a.tiles = tiles; a.N = N; a.S = S; a.k = k; a.r_lo = rs - delta; a.r_hi = rs + delta;
+  a.st = w.st; a.hist = w.hist; a.cand = w.cand; a.cap = w.cap; a.cand2 = w.cand2; a.thr_out = thr_out;
+  void* args[] = {&a};
+  TP_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_topk_fused<KIND, WRITE>, dim3(grid), dim3(kSweepThreads), args, 0, st));
+  return TP_OK;
+}
+
+// Status read-back (the only host synchronisation of the path) and the slow paths it may call for.
+template <int KIND>
+static int finish_topk(const TopkWs& w, int n_seg, long long tiles, long long k, bool write, float* thr_out, int64_t* info,
+                       cudaStream_t st) {
+  SelState h = {};
+  TP_CUDA_CHECK(cudaMemcpyAsync(&h, w.st, sizeof(h), cudaMemcpyDeviceToHost, st));
   TP_CUDA_CHECK(cudaStreamSynchronize(st));
+  const long long n_cand = (long long)h.n_cand, n_lt = (long long)h.n_lt;
+  const int grid = sweep_grid(tiles);
   int path = 0;
   if (h.status == 1) {
     // exact fallback: 3 radix passes over the full data
     path = 1;
     SelState f = {};
     f.k = (unsigned long long)k; f.k_rem = (unsigned long long)k;
-    TP_CUDA_CHECK(cudaMemcpyAsync(d_st, &f, sizeof(f), cudaMemcpyHostToDevice, st));
+    TP_CUDA_CHECK(cudaMemcpyAsync(w.st, &f, sizeof(f), cudaMemcpyHostToDevice, st));
     const int shifts[3] = {21, 10, 0}, bits[3] = {11, 11, 10};
     for (int p = 0; p < 3; ++p) {
-      TP_CUDA_CHECK(cudaMemsetAsync(d_hist, 0, sizeof(unsigned int) * 2048, st));
-      k_hist_pass<KIND><<<grid, kSweepThreads, 0, st>>>(d_segs, n_seg, tiles, d_st, shifts[p], bits[p], d_hist);
-      k_pick_digit<<<1, 32, 0, st>>>(d_hist, shifts[p], bits[p], d_st);
+      TP_CUDA_CHECK(cudaMemsetAsync(w.hist, 0, sizeof(unsigned int) * 2048, st));
+      k_hist_pass<KIND><<<grid, kSweepThreads, 0, st>>>(w.segs, n_seg, tiles, w.st, shifts[p], bits[p], w.hist);
+      k_pick_digit<<<1, 32, 0, st>>>(w.hist, shifts[p], bits[p], w.st);
     }
-    k_publish_thr<<<1, 1, 0, st>>>(d_st, thr_out);
-    if (write) k_apply<KIND><<<grid, kSweepThreads, 0, st>>>(d_segs, n_seg, tiles, thr_out);
+    k_publish_thr<<<1, 1, 0, st>>>(w.st, thr_out);
+    if (write) k_apply<KIND><<<grid, kSweepThreads, 0, st>>>(w.segs, n_seg, tiles, thr_out);
     TP_LAUNCH_CHECK();
-    TP_CUDA_CHECK(cudaMemcpyAsync(&h, d_st, sizeof(h), cudaMemcpyDeviceToHost, st));
+    TP_CUDA_CHECK(cudaMemcpyAsync(&h, w.st, sizeof(h), cudaMemcpyDeviceToHost, st));
     TP_CUDA_CHECK(cudaStreamSynchronize(st));
-  } else if (h.status == 2 && write) {
+  }
+  if (h.status == 2 && write && path == 0) {
     // NaN threshold: `score <= nan` is false everywhere -> every mask entry becomes 1
-    k_apply<KIND><<<grid, kSweepThreads, 0, st>>>(d_segs, n_seg, tiles, thr_out);
+    k_apply<KIND><<<grid, kSweepThreads, 0, st>>>(w.segs, n_seg, tiles, thr_out);
     TP_LAUNCH_CHECK();
   }
-  if (info) { info[0] = path; info[1] = (int64_t)h.n_cand; info[2] = (int64_t)h.n_lt; info[3] = (h.status == 2); }
+  if (info) { info[0] = path; info[1] = n_cand; info[2] = n_lt; info[3] = (h.status == 2); }
   return TP_OK;
 }
 
@@ -581,41 +620,65 @@ extern "C" {
 size_t tp_topk_workspace_bytes(int n_seg, int64_t total_numel) {
   size_t b = 0;
   b += align_up(sizeof(Seg) * (size_t)(n_seg > 0 ? n_seg : 1), 256);
-  b += align_up(sizeof(SelState), 256);
-  b += align_up(sizeof(unsigned int) * 4 * kDigitBins, 256);
-  b += align_up(sizeof(unsigned int) * (size_t)(1u << kSampleBits), 256);
+  b += align_up(align_up(sizeof(SelState), 256) + sizeof(unsigned int) * 4 * kDigitBins, 256);
+  b += align_up(sizeof(unsigned int) * kCand2, 256);
   b += align_up(sizeof(uint2) * (size_t)cand_cap(total_numel), 256);
   return b + 1024;
+}
+
+static int topk_common(const void* const* w, const void* const* g, const void* const* m, void* const* mask_out,
+                       const int64_t* numel, int n_seg, int64_t k, int score_kind, float* thr_out, void* ws, size_t ws_bytes,
+                       int table_cached, bool do_enqueue, bool do_finish, int64_t* info_out, cudaStream_t st) {
+  if (!m || !numel || n_seg <= 0 || !thr_out || !ws) return TP_ERR_INVALID;
+  if (!table_cached && (!w || (score_kind != TP_SCORE_MAG && !g))) return TP_ERR_INVALID;
+  if (score_kind < 0 || score_kind > 2) return TP_ERR_INVALID;
+  long long N = 0, tiles = 0;
+  for (int i = 0; i < n_seg; ++i) { if (numel[i] < 0) return TP_ERR_INVALID; N += numel[i]; tiles += (numel[i] + kTileElems - 1) / kTileElems; }
+  if (k < 1 || k > N) return TP_ERR_K_RANGE;          // torch.kthvalue raises (pruning_utils.py:79)
+  if (N >= (1ll << 32)) return TP_ERR_UNSUPPORTED;    // candidate records carry 32-bit indices
+  TopkWs t;
+  int rc = carve_topk_ws(ws, ws_bytes, n_seg, N, &t); if (rc) return rc;
+  const bool write = mask_out != nullptr;
+  if (do_enqueue) {
+    if (!table_cached) {
+      Arena ar(ws, ws_bytes);
+      Seg* d_segs = nullptr;
+      rc = upload_segs(ar, w, g, m, mask_out, nullptr, numel, n_seg, &d_segs, nullptr, nullptr, st); if (rc) return rc;
+      if (d_segs != t.segs) return TP_ERR_WORKSPACE;
+    }
+#define TP_ENQ(KIND) (write ? enqueue_topk<KIND, true>(t, n_seg, tiles, N, k, thr_out, st) : enqueue_topk<KIND, false>(t, n_seg, tiles, N, k, thr_out, st))
+    rc = score_kind == TP_SCORE_MAG ? TP_ENQ(TP_SCORE_MAG) : (score_kind == TP_SCORE_SNIP ? TP_ENQ(TP_SCORE_SNIP) : TP_ENQ(TP_SCORE_SYNFLOW));
+#undef TP_ENQ
+    if (rc) return rc;
+  }
+  if (do_finish) {
+    switch (score_kind) {
+      case TP_SCORE_MAG: return finish_topk<TP_SCORE_MAG>(t, n_seg, tiles, k, write, thr_out, info_out, st);
+      case TP_SCORE_SNIP: return finish_topk<TP_SCORE_SNIP>(t, n_seg, tiles, k, write, thr_out, info_out, st);
+      default: return finish_topk<TP_SCORE_SYNFLOW>(t, n_seg, tiles, k, write, thr_out, info_out, st);
+    }
+  }
+  return TP_OK;
 }
 
 int tp_topk_threshold_mask(const void* const* w, const void* const* g, const void* const* m,
                            void* const* mask_out, const int64_t* numel, int n_seg,
                            int64_t k, int score_kind, float* thr_out,
                            void* ws, size_t ws_bytes, int64_t* info_out, void* stream) {
-  if (!w || !m || !numel || n_seg <= 0 || !thr_out || !ws) return TP_ERR_INVALID;
-  if (score_kind != TP_SCORE_MAG && !g) return TP_ERR_INVALID;
-  if (score_kind < 0 || score_kind > 2) return TP_ERR_INVALID;
-  cudaStream_t st = (cudaStream_t)stream;
-  long long N = 0;
-  for (int i = 0; i < n_seg; ++i) { if (numel[i] < 0) return TP_ERR_INVALID; N += numel[i]; }
-  if (k < 1 || k > N) return TP_ERR_K_RANGE;          // torch.kthvalue raises (pruning_utils.py:79)
-  if (N >= (1ll << 32)) return TP_ERR_UNSUPPORTED;    // candidate records carry 32-bit indices
-  Arena ar(ws, ws_bytes);
-  Seg* d_segs = nullptr; long long tiles = 0, total = 0;
-  int rc = upload_segs(ar, w, g, m, mask_out, nullptr, numel, n_seg, &d_segs, &tiles, &total, st);
-  if (rc) return rc;
-  SelState* d_st = (SelState*)ar.take(sizeof(SelState));
-  unsigned int* d_hist = (unsigned int*)ar.take(sizeof(unsigned int) * 4 * kDigitBins);
-  unsigned int* d_skeys = (unsigned int*)ar.take(sizeof(unsigned int) * (size_t)(1u << kSampleBits));
-  const unsigned int cap = cand_cap(N);
-  uint2* d_cand = (uint2*)ar.take(sizeof(uint2) * (size_t)cap);
-  if (!d_st || !d_hist || !d_skeys || !d_cand) return TP_ERR_WORKSPACE;
-  const bool write = mask_out != nullptr;
-  switch (score_kind) {
-    case TP_SCORE_MAG: return run_topk<TP_SCORE_MAG>(d_segs, n_seg, tiles, N, k, write, d_st, d_hist, d_skeys, d_cand, cap, thr_out, info_out, st);
-    case TP_SCORE_SNIP: return run_topk<TP_SCORE_SNIP>(d_segs, n_seg, tiles, N, k, write, d_st, d_hist, d_skeys, d_cand, cap, thr_out, info_out, st);
-    default: return run_topk<TP_SCORE_SYNFLOW>(d_segs, n_seg, tiles, N, k, write, d_st, d_hist, d_skeys, d_cand, cap, thr_out, info_out, st);
-  }
+  return topk_common(w, g, m, mask_out, numel, n_seg, k, score_kind, thr_out, ws, ws_bytes, 0, true, true, info_out, (cudaStream_t)stream);
+}
+
+int tp_topk_enqueue(const void* const* w, const void* const* g, const void* const* m,
+                    void* const* mask_out, const int64_t* numel, int n_seg,
+                    int64_t k, int score_kind, float* thr_out,
+                    void* ws, size_t ws_bytes, int table_cached, void* stream) {
+  return topk_common(w, g, m, mask_out, numel, n_seg, k, score_kind, thr_out, ws, ws_bytes, table_cached, true, false, nullptr, (cudaStream_t)stream);
+}
+
+int tp_topk_finish(const void* const* m, void* const* mask_out, const int64_t* numel, int n_seg,
+                   int64_t k, int score_kind, float* thr_out,
+                   void* ws, size_t ws_bytes, int64_t* info_out, void* stream) {
+  return topk_common(nullptr, nullptr, m, mask_out, numel, n_seg, k, score_kind, thr_out, ws, ws_bytes, 1, false, true, info_out, (cudaStream_t)stream);
 }
 
 int tp_apply_threshold(const void* const* w, const void* const* g, const void* const* m,

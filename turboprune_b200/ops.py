@@ -137,7 +137,7 @@ def topk_threshold_mask(ws, ms, k, gs=None, kind=_cabi.TP_SCORE_MAG, write_masks
     if rc == _cabi.TP_ERR_K_RANGE:
         raise RuntimeError(f"kthvalue(): selected number k out of range for dimension 0 (k={k}, N={total})")
     _cabi.check(rc, "tp_topk_threshold_mask")
-    _count(4)
+    _count(1)
     return outs, thr, {"path": int(info[0]), "candidates": int(info[1]), "n_lt": int(info[2]), "nan_thr": bool(info[3])}
 
 
@@ -160,18 +160,34 @@ class TopKPlan:
         self.args = (_cabi.ptr_array(self.ws), _cabi.ptr_array(self.gs), _cabi.ptr_array(self.ms), _cabi.ptr_array(self.outs),
                      _cabi.i64_array([w.numel() for w in self.ws]))
         self.info = (ctypes.c_int64 * 4)()
+        self._cached = False
 
-    def run(self, k):
+    def enqueue(self, k):
+        """Issue the whole fast path (one memset + one cooperative kernel) without blocking the stream.  The masks /
+        threshold must not be consumed before ``finish(k)``."""
         with torch.cuda.device(self.dev):
-            rc = self.lib.tp_topk_threshold_mask(*self.args, self.n, int(k), self.kind, c_void_p(self.thr.data_ptr()),
-                                                 c_void_p(self.wsb.data_ptr()), self.wsb.numel(), self.info,
-                                                 _cabi.stream_ptr(self.dev))
+            rc = self.lib.tp_topk_enqueue(*self.args, self.n, int(k), self.kind, c_void_p(self.thr.data_ptr()),
+                                          c_void_p(self.wsb.data_ptr()), self.wsb.numel(), int(self._cached),
+                                          _cabi.stream_ptr(self.dev))
         if rc == _cabi.TP_ERR_K_RANGE:
             raise RuntimeError(f"kthvalue(): selected number k out of range for dimension 0 (k={k}, N={self.total})")
-        _cabi.check(rc, "tp_topk_threshold_mask")
-        _count(6)
+        _cabi.check(rc, "tp_topk_enqueue")
+        self._cached = True                      # the segment table now lives in the workspace
+        _count(1)
+
+    def finish(self, k):
+        """Synchronise, read the status back, run the exact fallback if the bracket missed.  Returns (masks, thr, info)."""
+        with torch.cuda.device(self.dev):
+            rc = self.lib.tp_topk_finish(self.args[2], self.args[3], self.args[4], self.n, int(k), self.kind,
+                                         c_void_p(self.thr.data_ptr()), c_void_p(self.wsb.data_ptr()), self.wsb.numel(),
+                                         self.info, _cabi.stream_ptr(self.dev))
+        _cabi.check(rc, "tp_topk_finish")
         return self.outs, self.thr, {"path": int(self.info[0]), "candidates": int(self.info[1]), "n_lt": int(self.info[2]),
                                      "nan_thr": bool(self.info[3])}
+
+    def run(self, k):
+        self.enqueue(k)
+        return self.finish(k)
 
 
 def apply_threshold(ws, ms, thr, gs=None, kind=_cabi.TP_SCORE_MAG):
@@ -267,10 +283,8 @@ def kmask_shapes(cout, cin, r, s, wf_ld, cout_p):
 def kblock_occupancy(kmask, columns):
     """(empty, total) 64x64 weight blocks described by an occupancy mask over ``columns`` K columns (host sync)."""
     kb = (columns + 63) // 64
-    words = kmask.to(torch.int64).cpu() & 0xFFFFFFFF
-    set_bits = sum(bin(int(v)).count("1") for v in words.reshape(-1).tolist())
-    total = kmask.shape[0] * kb
-    return total - set_bits, total
+    rows = kmask_rows(kmask, columns)
+    return int(kmask[-1].item()), rows.shape[0] * kb            # the staging call left the count behind the last row
 
 
 def stage_weights(weight4d, mask4d, cin_p, need_dgrad, cout_p=None, wf_ld=0, want_kmask=None):
@@ -291,8 +305,8 @@ def stage_weights(weight4d, mask4d, cin_p, need_dgrad, cout_p=None, wf_ld=0, wan
     kf = kd = None
     if KBLOCK_SKIP if want_kmask is None else want_kmask:
         sf, sd = kmask_shapes(cout, cin, r, s, wf.shape[1], cout_p)
-        kf = torch.empty(sf, dtype=torch.int32, device=dev)
-        kd = torch.empty(sd, dtype=torch.int32, device=dev) if wd is not None else None
+        kf = torch.empty(sf[0] * sf[1] + 1, dtype=torch.int32, device=dev)      # [rows][words] + the empty-block count
+        kd = torch.empty(sd[0] * sd[1] + 1, dtype=torch.int32, device=dev) if wd is not None else None
     with torch.cuda.device(dev):
         rc = lib.tp_stage_weights(c_void_p(weight4d.data_ptr()), c_void_p(mask4d.data_ptr()), cout, cin, r, s,
                                   c_void_p(wf.data_ptr()), cin_p, int(wf_ld), c_void_p(wd.data_ptr()) if wd is not None else None,
@@ -304,6 +318,12 @@ def stage_weights(weight4d, mask4d, cin_p, need_dgrad, cout_p=None, wf_ld=0, wan
     if wd is not None:
         wd.kmask = kd
     return wf, wd
+
+
+def kmask_rows(kmask, columns):
+    """[row groups, words] view of an occupancy mask buffer (its last element is the empty-block count)."""
+    words = ((columns + 63) // 64 + 31) // 32
+    return kmask[:-1].view(-1, words)
 
 
 def padded_cin(cin, r, s):
@@ -369,16 +389,17 @@ class WeightStager:
                     shapes.append(None); continue
                 cout, cin, r, s = self._shape4(l)
                 shapes.append(kmask_shapes(cout, cin, r, s, b[0].shape[1], b[3]))
-            total = sum(sf[0] * sf[1] + (sd[0] * sd[1] if b[1] is not None else 0) for (sh, b) in zip(shapes, self._bufs) if sh is not None for sf, sd in [sh])
+            total = sum(sf[0] * sf[1] + 1 + ((sd[0] * sd[1] + 1) if b[1] is not None else 0)
+                        for (sh, b) in zip(shapes, self._bufs) if sh is not None for sf, sd in [sh])
             self._kmask_all = torch.zeros(max(total, 1), dtype=torch.int32, device=dev)
             off = 0
             for sh, b in zip(shapes, self._bufs):
                 if sh is None:
                     continue
                 sf, sd = sh
-                b[0].kmask = self._kmask_all[off:off + sf[0] * sf[1]].view(sf); off += sf[0] * sf[1]
+                b[0].kmask = self._kmask_all[off:off + sf[0] * sf[1] + 1]; off += sf[0] * sf[1] + 1
                 if b[1] is not None:
-                    b[1].kmask = self._kmask_all[off:off + sd[0] * sd[1]].view(sd); off += sd[0] * sd[1]
+                    b[1].kmask = self._kmask_all[off:off + sd[0] * sd[1] + 1]; off += sd[0] * sd[1] + 1
         live = [(l, b) for l, b in zip(self.layers, self._bufs) if b is not None]
         items = (_cabi.StageItem * len(live))()
         for it, (l, (wf, wd, cin_p, cout_p)) in zip(items, live):
