@@ -28,6 +28,8 @@ def timeit(fn, reps=5):
     return statistics.median(ts)
 
 def main():
+    if os.environ.get("TP_KSKIP", "1") == "0":
+        ops.set_kblock_skip(False)
     B = int(sys.argv[1]) if len(sys.argv) > 1 else 256
     only = sys.argv[2] if len(sys.argv) > 2 else None
     pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6487.1, "bf16_tflops": 1736.2}

@@ -39,15 +39,32 @@ __host__ __device__ constexpr int fwd_stages(int block_n, int cl) {
 
 struct TapEntry { uint16_t off_w, off_h; int32_t kofs; };
 
+constexpr int kMaxCls = 4;
+
+// One "class" of output pixels.  fprop and stride-1 dgrad have a single class (every output pixel, every tap).  The
+// dgrad of a strided convolution splits dX into stride_h x stride_w parity classes: class (a, b) = the input pixels
+// (stride*h' + a, stride*w' + b), each a stride-1 gather over dY with its own subset of taps (possibly none: those
+// pixels only receive the fused addend, or zero).  All classes run in ONE launch: a work item is (class, M tile, N tile).
+struct ClsEntry {
+  int M;                    // iteration pixels of this class (n_img * P_it * Q_it)
+  int P_it, Q_it;           // iteration grid per image
+  int ntaps, tap0;          // taps[tap0 .. tap0 + ntaps)
+  int base_w, base_h;       // im2col coordinate of iteration pixel (p,q): base + q*step
+  int oah, oaw;             // output pixel = (p*osh + oah, q*osw + oaw)
+  int tile0, m_groups;      // first work item of the class; M tile groups (of CL tiles) it has
+};
+
 struct FwdParams {
-  int M, N;                 // iteration pixels, output channels
-  int P_it, Q_it;           // iteration grid per image (M = n_img * P_it * Q_it)
-  int cchunks, ntaps;       // K loop = ntaps x cchunks blocks of 64 channels
+  int M, N;                 // iteration pixels (all classes), output channels
+  int ncls;
+  ClsEntry cls[kMaxCls];
+  int cchunks;              // K loop = ntaps x cchunks blocks of 64 channels
   int a_mode;               // 0: tiled 2-D A[M, K];  1: im2col 4-D
-  int base_w, base_h, step_w, step_h;   // im2col coordinate of iteration pixel (p,q): base + q*step
+  int step_w, step_h;
   long long out_img_pix;    // output pixels per image
   int out_row_pix;          // output pixels per row
-  int osh, oah, osw, oaw;   // output pixel = (p*osh+oah, q*osw+oaw)
+  int osh, osw;
+  int linear;               // output pixel index == iteration pixel index (single class, unit output stride)
   int ldc;                  // elements between consecutive output pixels
   int cluster;              // thread-block cluster size along M (1 or 2): weight tile multicast
   int tma_store;            // 1: epilogue stages 32x64 sub-tiles in smem and stores them with TMA (tmC)
@@ -115,10 +132,21 @@ __device__ __forceinline__ void decompose_pixel(int m, int P, int Q, int& n, int
 // own 128 rows.  L2 -> SM operand bytes per K block drop from 2 x 48 KB to 2 x 32 KB and the 32 KB stages leave room
 // for 6 of them in flight: the ncu captures showed the mainloop pinned at ~10 TB/s of L2 -> SM traffic with every
 // role waiting (profiles/r01_notes.md); TMA multicast does not reduce L2 reads at cluster size 2, operand halving does.
+struct AMaps { CUtensorMap m[kMaxCls]; };      // activation-side tensor map of every class
+
+// work item -> (class, M-tile group, N tile); identical in the three roles
+__device__ __forceinline__ void decode_tile(const FwdParams& p, int tile, int n_tiles, int& c, int& m_g, int& n_t) {
+  c = 0;
+#pragma unroll
+  for (int j = 1; j < kMaxCls; ++j) if (j < p.ncls && tile >= p.cls[j].tile0) c = j;
+  const int local = tile - p.cls[c].tile0;
+  m_g = local / n_tiles; n_t = local - m_g * n_tiles;     // m-major: CTAs running together share A tiles, weights stay in L2
+}
+
 template <int BLOCK_N, int CL>
 __global__ void __launch_bounds__(kFwdThreads, 1)
-k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-            const __grid_constant__ CUtensorMap tmC, const __grid_constant__ FwdParams p) {
+k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorMap tmB,
+            const __grid_constant__ FwdParams p) {
   constexpr int kABytes = kBlockM * kBlockK * 2;           // 16 KB
   constexpr int kBRows = BLOCK_N / CL;                     // weight rows THIS CTA loads
   constexpr int kBBytes = kBRows * kBlockK * 2;
@@ -138,18 +166,17 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + kAccStages);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m_tiles = (p.M + kBlockM - 1) / kBlockM;
   const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
-  // work items are CLUSTER tiles: (group of CL neighbouring M tiles) x (N tile); CTA rank r takes M tile g*CL + r
-  // (an M tile past the end simply has no valid rows: its loads are zero-filled and its stores are masked)
+  // work items are CLUSTER tiles: (class) x (group of CL neighbouring M tiles) x (N tile); CTA rank r takes M tile
+  // g*CL + r (an M tile past the end simply has no valid rows: its loads are zero-filled and its stores are masked)
   const int cta_rank = (CL > 1) ? (int)cluster_ctarank() : 0;
   const int cl_id = (int)blockIdx.x / CL, n_cl = (int)gridDim.x / CL;
-  const int m_groups = (m_tiles + CL - 1) / CL;
-  const int total_tiles = m_groups * n_tiles;
+  const int total_tiles = p.cls[p.ncls - 1].tile0 + p.cls[p.ncls - 1].m_groups * n_tiles;
   constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&tmA); prefetch_tmap(&tmB); prefetch_tmap(&tmC);
+    for (int j = 0; j < p.ncls; ++j) prefetch_tmap(&tmA.m[j]);
+    prefetch_tmap(&tmB);
     // full / tempty are only used in the leader CTA of a pair: full gets ONE arrive (the leader's expect_tx for both
     // CTAs' bytes), tempty gets one arrive per epilogue warp of both CTAs; empty / tfull exist in both CTAs and get
     // one (multicast) commit arrival from the leader's MMA thread
@@ -172,21 +199,23 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int stage = 0; uint32_t phase = 0;
       const uint32_t* const km = live_kmask(p.kmask, p.kmask_words, p.N);
       for (int tile = cl_id; tile < total_tiles; tile += n_cl) {
-        const int m_g = tile / n_tiles, n_t = tile - m_g * n_tiles;   // m-major: CTAs running together share A tiles, weights stay in L2
+        int ci, m_g, n_t; decode_tile(p, tile, n_tiles, ci, m_g, n_t);
+        const ClsEntry& ce = p.cls[ci];
+        const CUtensorMap* const mapA = &tmA.m[ci];
         const int m_t = m_g * CL + cta_rank;
         const int m0 = m_t * kBlockM;
         int cn = 0, cp = 0, cq = 0;
-        if (p.a_mode == 1) decompose_pixel(m0, p.P_it, p.Q_it, cn, cp, cq);
-        const int cw = p.base_w + cq * p.step_w, ch = p.base_h + cp * p.step_h;
+        if (p.a_mode == 1) decompose_pixel(m0, ce.P_it, ce.Q_it, cn, cp, cq);
+        const int cw = ce.base_w + cq * p.step_w, ch = ce.base_h + cp * p.step_h;
         KSkip ks; bool any = false;
         if (km) ks.begin(km, p.kmask_words, n_t * BLOCK_N, BLOCK_N, p.N);
         // nested tap / channel-chunk loops: no integer division on the single producer thread
         // (the first ncu source view showed the producer, not TMA or the tensor pipe, as the limiter)
-        for (int tap = 0; tap < p.ntaps; ++tap) {
-          const TapEntry te = p.taps[tap];
+        for (int tap = 0; tap < ce.ntaps; ++tap) {
+          const TapEntry te = p.taps[ce.tap0 + tap];
           for (int cc = 0; cc < p.cchunks; ++cc) {
             if (km) {
-              const bool last = tap == p.ntaps - 1 && cc == p.cchunks - 1;
+              const bool last = tap == ce.ntaps - 1 && cc == p.cchunks - 1;
               if (!ks.on((te.kofs >> 6) + cc) && !(last && !any)) continue;      // all-zero weight block: no load, no MMA
               any = true;
             }
@@ -196,9 +225,9 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (CL == 1) {
               mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
               if (p.a_mode == 1)
-                tma_load_im2col_4d(sA, &tmA, &full_bar[stage], cc * kBlockK, cw, ch, cn, te.off_w, te.off_h);
+                tma_load_im2col_4d(sA, mapA, &full_bar[stage], cc * kBlockK, cw, ch, cn, te.off_w, te.off_h);
               else
-                tma_load_2d(sA, &tmA, &full_bar[stage], te.kofs + cc * kBlockK, m0);
+                tma_load_2d(sA, mapA, &full_bar[stage], te.kofs + cc * kBlockK, m0);
               tma_load_2d(sB, &tmB, &full_bar[stage], te.kofs + cc * kBlockK, n_t * BLOCK_N);
             } else {
               // pair: my A tile and my half of the weight tile land in MY shared memory, the bytes are credited to the
@@ -206,9 +235,9 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
               if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], kStageBytes * CL);
               const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
               if (p.a_mode == 1)
-                tma_load_im2col_4d_pair(sA, &tmA, lead_full, cc * kBlockK, cw, ch, cn, te.off_w, te.off_h);
+                tma_load_im2col_4d_pair(sA, mapA, lead_full, cc * kBlockK, cw, ch, cn, te.off_w, te.off_h);
               else
-                tma_load_2d_pair(sA, &tmA, lead_full, te.kofs + cc * kBlockK, m0);
+                tma_load_2d_pair(sA, mapA, lead_full, te.kofs + cc * kBlockK, m0);
               tma_load_2d_pair(sB, &tmB, lead_full, te.kofs + cc * kBlockK, n_t * BLOCK_N + cta_rank * kBRows);
             }
             if (++stage == kStages) { stage = 0; phase ^= 1; }
@@ -228,12 +257,14 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
         KSkip ks; uint32_t any = 0;
-        if (km) { const int n_t = tile % n_tiles; ks.begin(km, p.kmask_words, n_t * BLOCK_N, BLOCK_N, p.N); }
-        for (int tap = 0; tap < p.ntaps; ++tap) {
-          const int kb0 = km ? (p.taps[tap].kofs >> 6) : 0;
+        int ci, m_g, n_t; decode_tile(p, tile, n_tiles, ci, m_g, n_t);
+        const ClsEntry& ce = p.cls[ci];
+        if (km) ks.begin(km, p.kmask_words, n_t * BLOCK_N, BLOCK_N, p.N);
+        for (int tap = 0; tap < ce.ntaps; ++tap) {                            // a class without taps issues nothing: its
+          const int kb0 = km ? (p.taps[ce.tap0 + tap].kofs >> 6) : 0;         // epilogue writes the addend (or zero) alone
           for (int cc = 0; cc < p.cchunks; ++cc) {
             if (km) {
-              const bool last = tap == p.ntaps - 1 && cc == p.cchunks - 1;
+              const bool last = tap == ce.ntaps - 1 && cc == p.cchunks - 1;
               if (!ks.on(kb0 + cc) && !(last && !any)) continue;               // same decision as the producer
             }
             mbar_wait(&full_bar[stage], phase, 3);
@@ -267,14 +298,19 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     const int half = (warp - 2) >> 2;         // which half of the 64-column chunks this warp drains
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = cl_id; tile < total_tiles; tile += n_cl) {
-      const int m_g = tile / n_tiles, n_t = tile - m_g * n_tiles;
+      int ci, m_g, n_t; decode_tile(p, tile, n_tiles, ci, m_g, n_t);
+      const ClsEntry& ce = p.cls[ci];
+      const bool has_acc = ce.ntaps > 0;        // a class no tap reaches: the accumulator was never written, its value is zero
       const int m_t = m_g * CL + cta_rank;
       const int row = m_t * kBlockM + quarter * 32 + lane;
-      const bool row_ok = row < p.M;
+      const bool row_ok = row < ce.M;
       long long opix = 0;
-      if (row_ok && !p.tma_store) {       // strided output mapping (dgrad parity classes): one division chain per tile
-        int n, pp, qq; decompose_pixel(row, p.P_it, p.Q_it, n, pp, qq);
-        opix = (long long)n * p.out_img_pix + (long long)(pp * p.osh + p.oah) * p.out_row_pix + (qq * p.osw + p.oaw);
+      if (row_ok && !p.tma_store) {       // generic output mapping, one division chain per tile
+        opix = row;
+        if (!p.linear) {
+          int n, pp, qq; decompose_pixel(row, ce.P_it, ce.Q_it, n, pp, qq);
+          opix = (long long)n * p.out_img_pix + (long long)(pp * p.osh + ce.oah) * p.out_row_pix + (qq * p.osw + ce.oaw);
+        }
       }
       __nv_bfloat16* orow = p.out + opix * p.ldc;
       mbar_wait(&tfull_bar[acc], acc_phase, 4);
@@ -290,11 +326,24 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         const uint32_t buf = smem_u32(stg_base + (warp - 2) * kStgBytes);
         const int r_in = lane >> 3, c16 = lane & 7;
         const long long wrow0 = (long long)m_t * kBlockM + quarter * 32;        // first row of this warp's 32
-        const int rows_left = (int)(p.M - wrow0 < 32 ? (p.M - wrow0 < 0 ? 0 : p.M - wrow0) : 32);
+        const int rows_left = (int)(ce.M - wrow0 < 32 ? (ce.M - wrow0 < 0 ? 0 : ce.M - wrow0) : 32);
         const long long ldc = p.ldc;
         const int N = p.N;
-        __nv_bfloat16* gout = p.out + (wrow0 + r_in) * ldc + c16 * 8;           // + i*4*ldc + n0
-        const __nv_bfloat16* gadd = p.addend ? p.addend + (wrow0 + r_in) * ldc + c16 * 8 : nullptr;
+        // element offset of the 8 output rows this lane moves (rows r_in + 4i of the warp's 32): the iteration pixel itself
+        // for a linear output, the parity-class pixel of a strided dgrad otherwise (8 division chains per tile)
+        long long ooff[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const long long r = wrow0 + r_in + 4 * i;
+          long long px = r;
+          if (!p.linear && i * 4 + r_in < rows_left) {
+            int n, pp, qq; decompose_pixel((int)r, ce.P_it, ce.Q_it, n, pp, qq);
+            px = (long long)n * p.out_img_pix + (long long)(pp * p.osh + ce.oah) * p.out_row_pix + (qq * p.osw + ce.oaw);
+          }
+          ooff[i] = px * ldc + c16 * 8;
+        }
+        __nv_bfloat16* const gout = p.out;
+        const __nv_bfloat16* const gadd = p.addend;
         const float* bias = p.bias;
         float* stats = p.stats ? p.stats + (long long)(m_t * 4 + quarter) * 2 * N + c16 * 8 : nullptr;
         const uint32_t wr_base = buf + lane * 128;                              // my row (TMEM lane) in the staging tile
@@ -318,7 +367,7 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 a_pref[i] = make_uint4(0u, 0u, 0u, 0u);
-                if (i * 4 + r_in < rows_left && col_ok) a_pref[i] = *reinterpret_cast<const uint4*>(gadd + (long long)(i * 4) * ldc + n0);
+                if (i * 4 + r_in < rows_left && col_ok) a_pref[i] = *reinterpret_cast<const uint4*>(gadd + ooff[i] + n0);
               }
             }
 #pragma unroll
@@ -328,7 +377,7 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 a_pref[i] = make_uint4(0u, 0u, 0u, 0u);
-                if (i * 4 + r_in < rows_left && col_ok2) a_pref[i] = *reinterpret_cast<const uint4*>(gadd + (long long)(i * 4) * ldc + n0 + 128);
+                if (i * 4 + r_in < rows_left && col_ok2) a_pref[i] = *reinterpret_cast<const uint4*>(gadd + ooff[i] + n0 + 128);
               }
             }
             __syncwarp();
@@ -338,7 +387,7 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int j = 0; j < 64; j += 8) {
             float f[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) f[q] = __uint_as_float(v[j + q]);
+            for (int q = 0; q < 8; ++q) f[q] = has_acc ? __uint_as_float(v[j + q]) : 0.f;
             if (bias) {
 #pragma unroll
               for (int q = 0; q < 8; ++q) if (n0 + j + q < N) f[q] += bias[n0 + j + q];
@@ -369,7 +418,7 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           for (int i = 0; i < 8; ++i) o[i] = lds128(((i & 1) ? rd_odd : rd_even) + (uint32_t)((i >> 1) * 1024));
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            if (i * 4 + r_in < rows_left && col_ok) *reinterpret_cast<uint4*>(gout + (long long)(i * 4) * ldc + n0) = o[i];
+            if (i * 4 + r_in < rows_left && col_ok) *reinterpret_cast<uint4*>(gout + ooff[i] + n0) = o[i];
           if (stats) {
             // BatchNorm batch statistics of exactly the values just stored (bf16-rounded): this thread owns 8 channels
             // of rows r_in, r_in+4, ...; a fixed-order xor tree over the 4 row groups finishes the 32 rows
@@ -412,7 +461,7 @@ k_igemm_fwd(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         if (row_ok && n0 < p.N) {
           float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 32; ++j) f[j] = has_acc ? __uint_as_float(v[j]) : 0.f;
           if (p.bias) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) if (n0 + j < p.N) f[j] += p.bias[n0 + j];
@@ -790,7 +839,7 @@ static int pick_block_n(long long m_tiles, int n) {
 }
 
 template <int BN, int CL>
-static int launch_fwd(const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c, const FwdParams& p, cudaStream_t st) {
+static int launch_fwd(const AMaps& a, const CUtensorMap& b, FwdParams& p, cudaStream_t st) {
   constexpr int kStages = fwd_stages(BN, CL);
   constexpr int smem = kStages * (kBlockM * kBlockK * 2 + (BN / CL) * kBlockK * 2) + 8 * 32 * 128 + 1024 + 256;
   static bool attr_set = false;
@@ -798,8 +847,17 @@ static int launch_fwd(const CUtensorMap& a, const CUtensorMap& b, const CUtensor
     TP_CUDA_CHECK(cudaFuncSetAttribute(k_igemm_fwd<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
-  const long long m_tiles = (p.M + kBlockM - 1) / kBlockM;
-  const long long ctiles = ((m_tiles + CL - 1) / CL) * ((p.N + BN - 1) / BN);
+  // work items: per class, (groups of CL M tiles) x (N tiles), classes back to back
+  const int n_tiles = (p.N + BN - 1) / BN;
+  long long ctiles = 0;
+  for (int c = 0; c < p.ncls; ++c) {
+    const long long m_tiles = (p.cls[c].M + kBlockM - 1) / kBlockM;
+    p.cls[c].m_groups = (int)((m_tiles + CL - 1) / CL);
+    if (ctiles > 0x7fffffffll) return TP_ERR_UNSUPPORTED;
+    p.cls[c].tile0 = (int)ctiles;
+    ctiles += (long long)p.cls[c].m_groups * n_tiles;
+  }
+  if (ctiles > 0x7fffffffll || ctiles <= 0) return TP_ERR_UNSUPPORTED;
   const long long max_cl = sm_count() / CL;
   const int grid = (int)(ctiles < max_cl ? ctiles : max_cl) * CL;
   cudaLaunchConfig_t cfg = {};
@@ -808,36 +866,27 @@ static int launch_fwd(const CUtensorMap& a, const CUtensorMap& b, const CUtensor
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  TP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_igemm_fwd<BN, CL>, a, b, c, p));
+  TP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_igemm_fwd<BN, CL>, a, b, p));
   TP_LAUNCH_CHECK();
   return TP_OK;
 }
 
-// Output map for the TMA-store epilogue: [M rows][N cols] bf16, box = 32 rows x 64 cols, SW128.
-static int make_out_map(CUtensorMap* m, const void* ptr, uint64_t cols, uint64_t rows, uint64_t ld_elems) {
-  return make_tiled_map(m, ptr, cols, rows, ld_elems, 32);
-}
-
-static int run_fwd(const CUtensorMap& a, const CUtensorMap& b, FwdParams& p, cudaStream_t st) {
-  // linear output pixel order + 16-byte aligned rows -> stage through smem and store with TMA
-  CUtensorMap c = a;
-  const bool linear = p.osh == 1 && p.osw == 1 && p.oah == 0 && p.oaw == 0 &&
-                      p.out_row_pix == p.Q_it && p.out_img_pix == (long long)p.P_it * p.Q_it;
-  p.tma_store = 0;
-  if (linear && p.ldc % 8 == 0 && p.N % 8 == 0 && (((uintptr_t)p.out) & 15) == 0) {
-    int rc = make_out_map(&c, p.out, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldc); if (rc) return rc;
-    p.tma_store = 1;
-  }
-  if (p.stats && !p.tma_store) return TP_ERR_UNSUPPORTED;
-  const int bn = pick_block_n((p.M + kBlockM - 1) / kBlockM, p.N);
+static int run_fwd(const AMaps& a, const CUtensorMap& b, FwdParams& p, int bn, cudaStream_t st) {
+  // 16-byte aligned output rows -> the epilogue stages 32x64 sub-tiles through smem and writes full 128-byte lines
+  // (for any pixel mapping: a strided dgrad's parity classes compute the destination pixel of each row)
+  p.linear = p.ncls == 1 && p.osh == 1 && p.osw == 1 && p.cls[0].oah == 0 && p.cls[0].oaw == 0 &&
+             p.out_row_pix == p.cls[0].Q_it && p.out_img_pix == (long long)p.cls[0].P_it * p.cls[0].Q_it;
+  p.tma_store = (p.ldc % 8 == 0 && p.N % 8 == 0 && (((uintptr_t)p.out) & 15) == 0 &&
+                 (!p.addend || (((uintptr_t)p.addend) & 15) == 0)) ? 1 : 0;
+  if (p.stats && !(p.tma_store && p.linear)) return TP_ERR_UNSUPPORTED;
   if (p.cluster == 2) {
-    if (bn == 256) return launch_fwd<256, 2>(a, b, c, p, st);
-    if (bn == 128) return launch_fwd<128, 2>(a, b, c, p, st);
-    return launch_fwd<64, 2>(a, b, c, p, st);
+    if (bn == 256) return launch_fwd<256, 2>(a, b, p, st);
+    if (bn == 128) return launch_fwd<128, 2>(a, b, p, st);
+    return launch_fwd<64, 2>(a, b, p, st);
   }
-  if (bn == 256) return launch_fwd<256, 1>(a, b, c, p, st);
-  if (bn == 128) return launch_fwd<128, 1>(a, b, c, p, st);
-  return launch_fwd<64, 1>(a, b, c, p, st);
+  if (bn == 256) return launch_fwd<256, 1>(a, b, p, st);
+  if (bn == 128) return launch_fwd<128, 1>(a, b, p, st);
+  return launch_fwd<64, 1>(a, b, p, st);
 }
 
 // Cluster size for a problem: pairs of M tiles share the weight tile (multicast) whenever there are enough tiles.
@@ -901,10 +950,12 @@ int tp_conv_fprop_stats(const tp_conv_desc* d, const void* x, const void* wf, co
   cudaStream_t st = (cudaStream_t)stream;
   FwdParams p = {};
   p.M = d->n * d->p * d->q; p.N = d->cout;
-  p.P_it = d->p; p.Q_it = d->q;
-  p.cchunks = (d->cin + 63) / 64; p.ntaps = d->r * d->s;
+  p.ncls = 1;
+  ClsEntry& ce = p.cls[0];
+  ce.M = p.M; ce.P_it = d->p; ce.Q_it = d->q; ce.ntaps = d->r * d->s; ce.tap0 = 0; ce.oah = 0; ce.oaw = 0;
+  p.cchunks = (d->cin + 63) / 64;
   p.out_img_pix = (long long)d->p * d->q; p.out_row_pix = d->q;
-  p.osh = 1; p.oah = 0; p.osw = 1; p.oaw = 0;
+  p.osh = 1; p.osw = 1;
   p.ldc = d->cout; p.out = (__nv_bfloat16*)y; p.bias = (const float*)bias_f32;
   p.stats = (float*)stats;
   p.kmask = (const uint32_t*)kmask_f; p.kmask_words = (int)tp_kblock_mask_words((int64_t)d->r * d->s * d->cin);
@@ -912,21 +963,22 @@ int tp_conv_fprop_stats(const tp_conv_desc* d, const void* x, const void* wf, co
     TapEntry& t = p.taps[r * d->s + s];
     t.off_w = (uint16_t)s; t.off_h = (uint16_t)r; t.kofs = (r * d->s + s) * d->cin;
   }
-  CUtensorMap ta, tb;
+  AMaps ta; CUtensorMap tb;
   if (is_plain_gemm(d)) {
     p.a_mode = 0;
-    rc = make_tiled_map(&ta, x, (uint64_t)d->cin, (uint64_t)p.M, (uint64_t)d->cin, kBlockM); if (rc) return rc;
+    rc = make_tiled_map(&ta.m[0], x, (uint64_t)d->cin, (uint64_t)p.M, (uint64_t)d->cin, kBlockM); if (rc) return rc;
   } else {
     p.a_mode = 1;
-    p.base_w = -d->pad_w; p.base_h = -d->pad_h; p.step_w = d->stride_w; p.step_h = d->stride_h;
-    rc = make_im2col_map(&ta, x, d->n, d->h, d->w, d->cin, p.base_w, p.base_h, p.step_w, p.step_h, d->p, d->q, kBlockM);
+    ce.base_w = -d->pad_w; ce.base_h = -d->pad_h; p.step_w = d->stride_w; p.step_h = d->stride_h;
+    rc = make_im2col_map(&ta.m[0], x, d->n, d->h, d->w, d->cin, ce.base_w, ce.base_h, p.step_w, p.step_h, d->p, d->q, kBlockM);
     if (rc) return rc;
   }
+  for (int c = 1; c < kMaxCls; ++c) ta.m[c] = ta.m[0];
   const int bn = pick_block_n((p.M + kBlockM - 1) / kBlockM, p.N);
   p.cluster = pick_cluster((p.M + kBlockM - 1) / kBlockM);
   rc = make_tiled_map(&tb, wf, (uint64_t)d->r * d->s * d->cin, (uint64_t)d->cout, (uint64_t)d->r * d->s * d->cin, (uint32_t)(bn / p.cluster));
   if (rc) return rc;
-  return run_fwd(ta, tb, p, st);
+  return run_fwd(ta, tb, p, bn, st);
 }
 
 int tp_conv_dgrad(const tp_conv_desc* d, const void* dy, const void* wd, const void* kmask_d, const void* addend,
@@ -942,79 +994,79 @@ int tp_conv_dgrad(const tp_conv_desc* d, const void* dy, const void* wd, const v
   cudaStream_t st = (cudaStream_t)stream;
   const int R = d->r, S = d->s;
   const long long ktot = (long long)R * S * cop;
-  if (d->stride_h == 1 && d->stride_w == 1) {
+  const int sh = d->stride_h, sw = d->stride_w;
+  FwdParams p = {};
+  p.N = d->cin;
+  p.cchunks = (cop + 63) / 64;
+  p.out_img_pix = (long long)d->h * d->w; p.out_row_pix = d->w;
+  p.ldc = d->cin; p.out = (__nv_bfloat16*)dx; p.bias = nullptr; p.addend = (const __nv_bfloat16*)addend;
+  p.kmask = (const uint32_t*)kmask_d; p.kmask_words = (int)tp_kblock_mask_words(ktot);
+  p.step_w = 1; p.step_h = 1;
+  AMaps ta; CUtensorMap tb;
+  if (sh == 1 && sw == 1) {
     // dX = conv(dY, rot180(W)^T) with padding (R-1-pad): wd is stored already rotated
-    FwdParams p = {};
-    p.M = d->n * d->h * d->w; p.N = d->cin;
-    p.P_it = d->h; p.Q_it = d->w;
-    p.cchunks = (cop + 63) / 64; p.ntaps = R * S;
-    p.out_img_pix = (long long)d->h * d->w; p.out_row_pix = d->w;
-    p.osh = 1; p.oah = 0; p.osw = 1; p.oaw = 0;
-    p.ldc = d->cin; p.out = (__nv_bfloat16*)dx; p.bias = nullptr; p.addend = (const __nv_bfloat16*)addend;
-    p.kmask = (const uint32_t*)kmask_d; p.kmask_words = (int)tp_kblock_mask_words(ktot);
+    p.M = d->n * d->h * d->w;
+    p.ncls = 1; p.osh = 1; p.osw = 1;
+    ClsEntry& ce = p.cls[0];
+    ce.M = p.M; ce.P_it = d->h; ce.Q_it = d->w; ce.ntaps = R * S; ce.tap0 = 0; ce.oah = 0; ce.oaw = 0;
     for (int r = 0; r < R; ++r) for (int s = 0; s < S; ++s) {
       TapEntry& t = p.taps[r * S + s];
       t.off_w = (uint16_t)s; t.off_h = (uint16_t)r; t.kofs = (r * S + s) * cop;
     }
-    CUtensorMap ta, tb;
     if (is_plain_gemm(d)) {
       p.a_mode = 0;
-      rc = make_tiled_map(&ta, dy, (uint64_t)cop, (uint64_t)p.M, (uint64_t)cop, kBlockM); if (rc) return rc;
+      rc = make_tiled_map(&ta.m[0], dy, (uint64_t)cop, (uint64_t)p.M, (uint64_t)cop, kBlockM); if (rc) return rc;
     } else {
       p.a_mode = 1;
-      p.base_w = -(S - 1 - d->pad_w); p.base_h = -(R - 1 - d->pad_h); p.step_w = 1; p.step_h = 1;
-      rc = make_im2col_map(&ta, dy, d->n, d->p, d->q, cop, p.base_w, p.base_h, 1, 1, d->h, d->w, kBlockM);
+      ce.base_w = -(S - 1 - d->pad_w); ce.base_h = -(R - 1 - d->pad_h);
+      rc = make_im2col_map(&ta.m[0], dy, d->n, d->p, d->q, cop, ce.base_w, ce.base_h, 1, 1, d->h, d->w, kBlockM);
       if (rc) return rc;
     }
-    const int bn = pick_block_n((p.M + kBlockM - 1) / kBlockM, p.N);
-    p.cluster = pick_cluster((p.M + kBlockM - 1) / kBlockM);
-    rc = make_tiled_map(&tb, wd, (uint64_t)ktot, (uint64_t)d->cin, (uint64_t)ktot, (uint32_t)(bn / p.cluster)); if (rc) return rc;
-    return run_fwd(ta, tb, p, st);
-  }
-  // strided conv: decompose dX into stride_h x stride_w parity classes; each class is a
-  // stride-1 gather over dY with its own subset of taps, scattered to every stride-th pixel.
-  const int sh = d->stride_h, sw = d->stride_w;
-  // pixels no tap reaches keep this initial value: zero, or the fused addend
-  if (addend) TP_CUDA_CHECK(cudaMemcpyAsync(dx, addend, (size_t)d->n * d->h * d->w * d->cin * 2, cudaMemcpyDeviceToDevice, st));
-  else TP_CUDA_CHECK(cudaMemsetAsync(dx, 0, (size_t)d->n * d->h * d->w * d->cin * 2, st));
-  for (int a = 0; a < sh; ++a) for (int b = 0; b < sw; ++b) {
-    const int Hc = (d->h - a + sh - 1) / sh, Wc = (d->w - b + sw - 1) / sw;   // pixels of this class
-    if (Hc <= 0 || Wc <= 0) continue;
-    // taps: input row h = sh*h' + a receives dY row p = h' + (a + pad - r)/sh when divisible
-    int dh_min = 1 << 30, dw_min = 1 << 30, nt = 0;
-    for (int r = 0; r < R; ++r) if ((a + d->pad_h - r) % sh == 0) dh_min = min(dh_min, (a + d->pad_h - r) / sh);
-    for (int s = 0; s < S; ++s) if ((b + d->pad_w - s) % sw == 0) dw_min = min(dw_min, (b + d->pad_w - s) / sw);
-    if (dh_min == (1 << 30) || dw_min == (1 << 30)) continue;     // no tap reaches this class: stays zero
-    FwdParams p = {};
-    p.M = d->n * Hc * Wc; p.N = d->cin;
-    p.P_it = Hc; p.Q_it = Wc;
-    p.cchunks = (cop + 63) / 64;
-    p.a_mode = 1;
-    p.base_w = dw_min; p.base_h = dh_min; p.step_w = 1; p.step_h = 1;
-    p.out_img_pix = (long long)d->h * d->w; p.out_row_pix = d->w;
-    p.osh = sh; p.oah = a; p.osw = sw; p.oaw = b;
-    p.ldc = d->cin; p.out = (__nv_bfloat16*)dx; p.bias = nullptr; p.addend = (const __nv_bfloat16*)addend;
-    p.kmask = (const uint32_t*)kmask_d; p.kmask_words = (int)tp_kblock_mask_words(ktot);
-    for (int r = 0; r < R; ++r) {
-      if ((a + d->pad_h - r) % sh != 0) continue;
-      for (int s = 0; s < S; ++s) {
-        if ((b + d->pad_w - s) % sw != 0) continue;
-        TapEntry& t = p.taps[nt++];
-        t.off_h = (uint16_t)((a + d->pad_h - r) / sh - dh_min);
-        t.off_w = (uint16_t)((b + d->pad_w - s) / sw - dw_min);
-        // wd stores tap (r,s) at rotated position (R-1-r, S-1-s)
-        t.kofs = ((R - 1 - r) * S + (S - 1 - s)) * cop;
-      }
+    for (int c = 1; c < kMaxCls; ++c) ta.m[c] = ta.m[0];
+  } else {
+    // strided conv: dX splits into stride_h x stride_w parity classes; each class is a stride-1 gather over dY with its
+    // own subset of taps, written to every stride-th pixel.  ONE launch covers all classes (round 1: a memset / memcpy
+    // of dX plus one launch per class with scattered 16-byte stores — 2.5-4x the roofline of these layers); a class
+    // no tap reaches is written by the epilogue alone (the fused addend, or zero).
+    if (sh * sw > kMaxCls || R * S > kMaxTaps) return TP_ERR_UNSUPPORTED;
+    p.a_mode = 1; p.osh = sh; p.osw = sw;
+    int nc = 0, nt = 0; long long Mtot = 0;
+    for (int a = 0; a < sh; ++a) for (int b = 0; b < sw; ++b) {
+      const int Hc = (d->h - a + sh - 1) / sh, Wc = (d->w - b + sw - 1) / sw;   // pixels of this class
+      if (Hc <= 0 || Wc <= 0) continue;
+      ClsEntry& ce = p.cls[nc];
+      ce.M = d->n * Hc * Wc; ce.P_it = Hc; ce.Q_it = Wc; ce.oah = a; ce.oaw = b; ce.tap0 = nt; ce.ntaps = 0;
+      // taps: input row h = sh*h' + a receives dY row p = h' + (a + pad - r)/sh when divisible
+      int dh_min = 1 << 30, dw_min = 1 << 30;
+      for (int r = 0; r < R; ++r) if ((a + d->pad_h - r) % sh == 0) dh_min = min(dh_min, (a + d->pad_h - r) / sh);
+      for (int s = 0; s < S; ++s) if ((b + d->pad_w - s) % sw == 0) dw_min = min(dw_min, (b + d->pad_w - s) / sw);
+      if (dh_min != (1 << 30) && dw_min != (1 << 30)) {
+        for (int r = 0; r < R; ++r) {
+          if ((a + d->pad_h - r) % sh != 0) continue;
+          for (int s = 0; s < S; ++s) {
+            if ((b + d->pad_w - s) % sw != 0) continue;
+            TapEntry& t = p.taps[nt++];
+            t.off_h = (uint16_t)((a + d->pad_h - r) / sh - dh_min);
+            t.off_w = (uint16_t)((b + d->pad_w - s) / sw - dw_min);
+            t.kofs = ((R - 1 - r) * S + (S - 1 - s)) * cop;          // wd stores tap (r,s) at rotated position (R-1-r, S-1-s)
+            ++ce.ntaps;
+          }
+        }
+      } else { dh_min = 0; dw_min = 0; }
+      ce.base_w = dw_min; ce.base_h = dh_min;
+      rc = make_im2col_map(&ta.m[nc], dy, d->n, d->p, d->q, cop, ce.base_w, ce.base_h, 1, 1, Hc, Wc, kBlockM); if (rc) return rc;
+      Mtot += ce.M; ++nc;
     }
-    p.ntaps = nt;
-    CUtensorMap ta, tb;
-    rc = make_im2col_map(&ta, dy, d->n, d->p, d->q, cop, p.base_w, p.base_h, 1, 1, Hc, Wc, kBlockM); if (rc) return rc;
-    const int bn = pick_block_n((p.M + kBlockM - 1) / kBlockM, p.N);
-    p.cluster = pick_cluster((p.M + kBlockM - 1) / kBlockM);
-    rc = make_tiled_map(&tb, wd, (uint64_t)ktot, (uint64_t)d->cin, (uint64_t)ktot, (uint32_t)(bn / p.cluster)); if (rc) return rc;
-    rc = run_fwd(ta, tb, p, st); if (rc) return rc;
+    if (nc == 0) return TP_OK;
+    for (int c = nc; c < kMaxCls; ++c) ta.m[c] = ta.m[0];
+    p.ncls = nc; p.M = (int)Mtot;
   }
-  return TP_OK;
+  long long m_tiles = 0;
+  for (int c = 0; c < p.ncls; ++c) m_tiles += (p.cls[c].M + kBlockM - 1) / kBlockM;
+  const int bn = pick_block_n(m_tiles, p.N);
+  p.cluster = pick_cluster(m_tiles);
+  rc = make_tiled_map(&tb, wd, (uint64_t)ktot, (uint64_t)d->cin, (uint64_t)ktot, (uint32_t)(bn / p.cluster)); if (rc) return rc;
+  return run_fwd(ta, tb, p, bn, st);
 }
 
 int tp_conv_wgrad(const tp_conv_desc* d, const void* x, const void* dy, const void* mask,

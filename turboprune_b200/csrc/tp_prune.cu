@@ -41,6 +41,7 @@ struct SelState {
   unsigned long long before_lo, before_hi;
   unsigned long long k_rem;
   unsigned long long n_cand2;         // second-level list (candidates matching the top digit)
+  unsigned long long t_phase[8];      // %globaltimer (ns) when CTA 0 entered P0..P5 and left (tools/topk_bench.py prints the deltas)
 };
 
 constexpr int kSampleBits = 20;
@@ -108,11 +109,18 @@ __device__ __forceinline__ void block_find_rank(const unsigned int* __restrict__
 
 constexpr int kCoarseShift = 20, kFineShift = 9, kDigitBins = 2048;
 
+__device__ __forceinline__ int resolve_shift0(unsigned int lo, unsigned int hi) {
+  const unsigned int span = lo ^ (hi - 1u);
+  const int top = span ? (31 - __clz(span)) : 0;
+  return (top / 11) * 11;
+}
+
 // ---------------------------------------------------------------------------------------------
 struct SweepCtx {
   unsigned int lo, hi;
   unsigned int n_lt, n_eq;
   uint2* s_cand; unsigned int* s_ncand;
+  unsigned int* s_dig; int shift0;
   SelState* st; uint2* cand; unsigned int cap;
 };
 
@@ -120,7 +128,8 @@ __device__ __forceinline__ float classify(SweepCtx& c, unsigned int key, long lo
   if (key < c.lo) { c.n_lt++; return 0.f; }
   if (key == c.lo) { c.n_eq++; return 0.f; }
   if (key >= c.hi) return 1.f;
-  // inside the bracket: rare (~0.1-1 %) -> candidate list
+  // inside the bracket: rare (~0.1-1 %) -> candidate list, and its top radix digit is counted right away
+  atomicAdd(&c.s_dig[(key >> c.shift0) & (kDigitBins - 1)], 1u);
   unsigned int slot = atomicAdd(c.s_ncand, 1u);
   if (slot < kSmemCand) {
     c.s_cand[slot] = make_uint2(key, (unsigned int)gidx);
@@ -131,13 +140,8 @@ __device__ __forceinline__ float classify(SweepCtx& c, unsigned int key, long lo
   return 0.f;   // provisional; k_resolve patches it
 }
 
-__device__ __forceinline__ int resolve_shift0(unsigned int lo, unsigned int hi) {
-  const unsigned int span = lo ^ (hi - 1u);
-  const int top = span ? (31 - __clz(span)) : 0;
-  return (top / 11) * 11;
-}
-
-constexpr int kLocalKeys = 4096;      // sample keys one CTA keeps in shared memory between P0 and P1
+constexpr int kRun = 16;               // neighbouring elements per sample run
+constexpr int kLocalKeys = 4096;      // sample keys one CTA keeps in shared memory between P0 and P1 (one round of 256 runs)
 constexpr int kCand2 = 4096;          // capacity of the second-level list
 
 struct TopkArgs {
@@ -149,6 +153,13 @@ struct TopkArgs {
   unsigned int* cand2;                // keys of the second-level list
   float* thr_out;
 };
+
+__device__ __forceinline__ void stamp(SelState* st, int i) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    st->t_phase[i] = t;
+  }
+}
 
 template <int KIND, bool WRITE>
 __global__ void __launch_bounds__(kSweepThreads) k_topk_fused(const TopkArgs a) {
@@ -170,35 +181,55 @@ __global__ void __launch_bounds__(kSweepThreads) k_topk_fused(const TopkArgs a) 
 
   // ---------------- P0: strided sample in runs of 4 neighbouring elements (one 32-byte sector per operand serves 4
   // samples), keys stay in shared memory; coarse histogram of key bits [30:20] ----------------
+  stamp(st, 0);
   for (int i = t; i < kDigitBins; i += kSweepThreads) s_h[i] = 0;
   __syncthreads();
-  const long long G = (a.S + 3) >> 2;
+  // samples are taken in runs of kRun = 16 neighbouring elements: one 64-byte DRAM burst per operand serves 16 samples.
+  // (Runs of 4 — one 32-byte sector — made this phase 28 us for ResNet-50: 2 x 262144 scattered sectors is a random-access
+  // rate problem, not a bandwidth one; the host widens the rank band for the clustering.)
+  const long long G = (a.S + kRun - 1) / kRun;
   const long long first = blockIdx.x * (long long)kSweepThreads, gstride = (long long)gridDim.x * kSweepThreads;
-  const int rounds = first < G ? (int)((G - first + gstride - 1) / gstride) : 0;   // uniform over the CTA; host keeps it <= kLocalKeys / 1024
+  const int rounds = first < G ? (int)((G - first + gstride - 1) / gstride) : 0;   // uniform over the CTA; host keeps rounds * 256 * kRun <= kLocalKeys
   for (int r = 0; r < rounds; ++r) {
     const long long gi = first + t + r * gstride;
-    unsigned int key4[4] = {0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu, 0xFFFFFFFFu};     // "no sample" (runs past S)
+    unsigned int key[kRun];
+#pragma unroll
+    for (int u = 0; u < kRun; ++u) key[u] = 0xFFFFFFFFu;                             // "no sample" (runs past S)
     if (gi < G) {
       long long e = (long long)(((unsigned long long)gi * (unsigned long long)a.N) / (unsigned long long)G);
       const int si = find_seg_by_elem(a.segs, a.n_seg, e);
-      const Seg& sg = a.segs[si];
-      long long l0 = (e - sg.start) & ~3ll;
-      if (l0 + 3 >= sg.n) l0 = sg.n >= 4 ? sg.n - 4 : 0;
+      const Seg sg = a.segs[si];
+      long long l0 = (e - sg.start) & ~(long long)(kRun - 1);
+      if (l0 + kRun > sg.n) l0 = sg.n >= kRun ? ((sg.n - kRun) & ~3ll) : 0;
+      const long long nvalid = min((long long)kRun, min(sg.n - l0, a.S - gi * kRun));
+      if (nvalid == kRun && (((uintptr_t)(sg.w + l0) | (uintptr_t)(sg.m + l0) | (KIND == TP_SCORE_MAG ? 0 : (uintptr_t)(sg.g + l0))) & 15) == 0) {
+        float4 wv[kRun / 4], mv[kRun / 4], gv[kRun / 4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const long long j = gi * 4 + u;
-        if (j < a.S) {
-          const long long l = l0 + u < sg.n ? l0 + u : sg.n - 1;
-          key4[u] = seg_key<KIND>(sg, l);
-          atomicAdd(&s_h[key4[u] >> kCoarseShift], 1u);
+        for (int q = 0; q < kRun / 4; ++q) {                                          // all loads in flight before the first use
+          wv[q] = ld_stream((const float4*)(sg.w + l0) + q);
+          mv[q] = ld_stream((const float4*)(sg.m + l0) + q);
+          gv[q] = (KIND == TP_SCORE_MAG) ? make_float4(0.f, 0.f, 0.f, 0.f) : ld_stream((const float4*)(sg.g + l0) + q);
         }
+#pragma unroll
+        for (int q = 0; q < kRun / 4; ++q) {
+          key[4 * q + 0] = score_key<KIND>(wv[q].x, gv[q].x, mv[q].x); key[4 * q + 1] = score_key<KIND>(wv[q].y, gv[q].y, mv[q].y);
+          key[4 * q + 2] = score_key<KIND>(wv[q].z, gv[q].z, mv[q].z); key[4 * q + 3] = score_key<KIND>(wv[q].w, gv[q].w, mv[q].w);
+        }
+      } else {
+#pragma unroll
+        for (int u = 0; u < kRun; ++u) if (u < nvalid) key[u] = seg_key<KIND>(sg, l0 + u);
       }
+#pragma unroll
+      for (int u = 0; u < kRun; ++u) if (key[u] != 0xFFFFFFFFu) atomicAdd(&s_h[key[u] >> kCoarseShift], 1u);
     }
-    *reinterpret_cast<uint4*>(&s_keys[(r * kSweepThreads + t) * 4]) = make_uint4(key4[0], key4[1], key4[2], key4[3]);
+#pragma unroll
+    for (int q = 0; q < kRun / 4; ++q)
+      *reinterpret_cast<uint4*>(&s_keys[((r * kSweepThreads + t) * kRun) + 4 * q]) = make_uint4(key[4 * q], key[4 * q + 1], key[4 * q + 2], key[4 * q + 3]);
   }
   __syncthreads();
   for (int i = t; i < kDigitBins; i += kSweepThreads) if (s_h[i]) atomicAdd(&hist_c[i], s_h[i]);
   grid.sync();
+  stamp(st, 1);
 
   // ---------------- P1: coarse bins of the two bracket ranks (every CTA, 8 KB of L2 reads), fine histograms of the
   // own samples that fall inside them ----------------
@@ -210,7 +241,7 @@ __global__ void __launch_bounds__(kSweepThreads) k_topk_fused(const TopkArgs a) 
   const unsigned int c_lo = s_bin[0], c_hi = s_bin[1];
   const unsigned long long before_lo = s_before[0], before_hi = s_before[1];
   if (blockIdx.x == 0 && t == 0) { st->c_lo = c_lo; st->c_hi = c_hi; st->before_lo = before_lo; st->before_hi = before_hi; }
-  for (int i = t; i < rounds * kSweepThreads * 4; i += kSweepThreads) {
+  for (int i = t; i < rounds * kSweepThreads * kRun; i += kSweepThreads) {
     const unsigned int key = s_keys[i];
     if (key == 0xFFFFFFFFu) continue;
     const unsigned int c = key >> kCoarseShift, f = (key >> kFineShift) & (kDigitBins - 1);
@@ -220,6 +251,7 @@ __global__ void __launch_bounds__(kSweepThreads) k_topk_fused(const TopkArgs a) 
   __syncthreads();
   for (int i = t; i < 2 * kDigitBins; i += kSweepThreads) if (s_h[i]) atomicAdd(&hist_f[i], s_h[i]);
   grid.sync();
+  stamp(st, 2);
 
   // ---------------- P2: bracket [lo, hi) from the fine histograms — every CTA derives the same two keys — and the
   // sweep ----------------
@@ -237,6 +269,10 @@ __global__ void __launch_bounds__(kSweepThreads) k_topk_fused(const TopkArgs a) 
   SweepCtx c;
   c.lo = lo; c.hi = hi; c.n_lt = 0; c.n_eq = 0;
   c.s_cand = s_cand; c.s_ncand = &s_ncand; c.st = st; c.cand = a.cand; c.cap = a.cap;
+  const int shift0 = resolve_shift0(lo, hi);
+  c.s_dig = s_h; c.shift0 = shift0;                     // top radix digit of every candidate, counted while sweeping
+  for (int i = t; i < kDigitBins; i += kSweepThreads) s_h[i] = 0;
+  __syncthreads();
   constexpr int kVecIters = kTileElems / (kSweepThreads * 4);   // 4
   for (long long tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
     if (t == 0) s_ncand = 0;
@@ -303,8 +339,10 @@ __global__ void __launch_bounds__(kSweepThreads) k_topk_fused(const TopkArgs a) 
       if (A) atomicAdd(&st->n_lt, A);
       if (B) atomicAdd(&st->n_eq, B);
     }
+    for (int i = t; i < kDigitBins; i += kSweepThreads) if (s_h[i]) atomicAdd(&hist_r[i], s_h[i]);
   }
   grid.sync();
+  stamp(st, 3);
 
   // ---------------- P3: does the bracket hold the k-th key?  (every CTA takes the same decision from the same counters)
   const unsigned long long k = (unsigned long long)a.k, A = st->n_lt, B = st->n_eq, C = st->n_cand;
@@ -318,16 +356,9 @@ __global__ void __launch_bounds__(kSweepThreads) k_topk_fused(const TopkArgs a) 
     thr = lo;                                             // the k-th key is the lower bracket edge itself
   } else {
     unsigned long long krem = k - A - B;
-    const int shift0 = resolve_shift0(lo, hi);
-    for (int i = t; i < kDigitBins; i += kSweepThreads) s_h[i] = 0;
-    __syncthreads();
-    for (unsigned int i = blockIdx.x * (unsigned)kSweepThreads + t; i < n; i += gridDim.x * (unsigned)kSweepThreads)
-      atomicAdd(&s_h[(a.cand[i].x >> shift0) & (kDigitBins - 1)], 1u);
-    __syncthreads();
-    for (int i = t; i < kDigitBins; i += kSweepThreads) if (s_h[i]) atomicAdd(&hist_r[i], s_h[i]);
-    grid.sync();
+    stamp(st, 4);
 
-    // ---------------- P4: pick the top digit (every CTA); candidates that carry it form the second-level list
+    // ---------------- P4: pick the top digit (its histogram was accumulated during the sweep) (every CTA); candidates that carry it form the second-level list
     if (t < 2) { s_bin[t] = 0; s_before[t] = 0; }
     __syncthreads();
     block_find_rank<kDigitBins / kSweepThreads>(hist_r, krem, &s_bin[0], &s_before[0], s_warp);
@@ -343,6 +374,7 @@ __global__ void __launch_bounds__(kSweepThreads) k_topk_fused(const TopkArgs a) 
         }
       }
       grid.sync();
+      stamp(st, 5);
 
       // ---------------- P5: finish the remaining digits over the second-level list in shared memory (every CTA, no barrier)
       const unsigned long long n2 = st->n_cand2;
@@ -383,6 +415,7 @@ __global__ void __launch_bounds__(kSweepThreads) k_topk_fused(const TopkArgs a) 
     *a.thr_out = __uint_as_float(thr);
     st->status = (thr > 0x7f800000u) ? 2 : 0;
   }
+  stamp(st, 6);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -556,7 +589,7 @@ static int enqueue_topk(const TopkWs& w, int n_seg, long long tiles, long long N
   int rc = fused_grid<KIND, WRITE>(&grid); if (rc) return rc;
   TP_CUDA_CHECK(cudaMemsetAsync(w.st, 0, align_up(sizeof(SelState), 256) + sizeof(unsigned int) * 4 * kDigitBins, st));
   long long S = N < (1ll << kSampleBits) ? N : (1ll << kSampleBits);
-  const long long smax = (long long)grid * kLocalKeys;             // what the CTAs can keep in shared memory
+  const long long smax = (long long)grid * kLocalKeys;             // what the CTAs can keep in shared memory (one round of runs each)
   if (S > smax) S = smax;
   // sample rank of the population's k-th element and the +-5 sigma band of its sampling error
   long long rs = (long long)(((unsigned __int128)(unsigned long long)k * (unsigned long long)S + (unsigned long long)N - 1) /
@@ -564,8 +597,10 @@ static int enqueue_topk(const TopkWs& w, int n_seg, long long tiles, long long N
   if (rs < 1) rs = 1;
   if (rs > S) rs = S;
   const double pq = (double)rs / (double)S;
-  // +4 per segment: runs are clamped at segment ends, so a few samples may repeat (also when S == N)
-  const long long delta = (long long)(5.0 * sqrt((double)S * pq * (1.0 - pq)) + 8.0) + 4ll * n_seg;
+  // The samples come in runs of kRun neighbours (same filter: correlated scale), so the band is 8 sigma of the iid
+  // rank error instead of 5 (design effect up to 2.5); + kRun per segment: runs are clamped at segment ends, so a few
+  // samples may repeat (also when S == N).  A miss is not an error, only the slow exact path.
+  const long long delta = (long long)(8.0 * sqrt((double)S * pq * (1.0 - pq)) + 8.0) + (long long)kRun * n_seg;
   TopkArgs a;
   a.segs = w.segs; a.n_seg = n_seg; a.tiles = tiles; a.N = N; a.S = S; a.k = k; a.r_lo = rs - delta; a.r_hi = rs + delta;
   a.st = w.st; a.hist = w.hist; a.cand = w.cand; a.cap = w.cap; a.cand2 = w.cand2; a.thr_out = thr_out;
