@@ -28,7 +28,7 @@ def run(n, nseg, density, kind=0, reps=7, flush=True):
     import struct
     off = (nseg * 64 + 255) // 256 * 256                      # sizeof(Seg) = 64
     raw = bytes(plan.wsb[off:off + 256].cpu().numpy().tobytes())
-    tp = struct.unpack_from("<8Q", raw, 8 * 4 + 4 * 4 + 4 * 2 + 4 * 2 + 8 * 4)   # after k,n_lt,n_eq,n_cand | lo,hi,thr,status | prefix,mask | c_lo,c_hi | before_lo,before_hi,k_rem,n_cand2
+    tp = struct.unpack_from("<8Q", raw, 8 * 4 + 4 * 4 + 4 * 2 + 4 * 2 + 8 * 4 + 8)   # after k,n_lt,n_eq,n_cand | lo,hi,thr,status | prefix,mask | c_lo,c_hi | before_lo,before_hi,k_rem,n_cand2 | barrier,pad
     names = ["P0 sample", "P1 refine", "P2 sweep", "P3 decide", "P4 narrow", "P5 finish"]
     ph = ", ".join(f"{n} {(tp[i + 1] - tp[i]) / 1e3:.1f}" for i, n in enumerate(names) if tp[i + 1] > tp[i] > 0)
     t = statistics.median(ts); bpe = 12 if kind == 0 else 16

@@ -143,7 +143,10 @@ __device__ __forceinline__ void decode_tile(const FwdParams& p, int tile, int n_
   m_g = local / n_tiles; n_t = local - m_g * n_tiles;     // m-major: CTAs running together share A tiles, weights stay in L2
 }
 
-template <int BLOCK_N, int CL>
+// MULTI = false: one class of output pixels (fprop, stride-1 dgrad) — the class decode, the per-row destination
+// arithmetic and the "class without taps" handling are compiled out (they cost the short-K layers up to 1.7x when they
+// sat in the common kernel: 1600 more instructions around loops that run once per 2-4 us tile).
+template <int BLOCK_N, int CL, bool MULTI>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ FwdParams p) {
@@ -199,9 +202,11 @@ k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorM
       int stage = 0; uint32_t phase = 0;
       const uint32_t* const km = live_kmask(p.kmask, p.kmask_words, p.N);
       for (int tile = cl_id; tile < total_tiles; tile += n_cl) {
-        int ci, m_g, n_t; decode_tile(p, tile, n_tiles, ci, m_g, n_t);
-        const ClsEntry& ce = p.cls[ci];
-        const CUtensorMap* const mapA = &tmA.m[ci];
+        int ci = 0, m_g, n_t;
+        if (MULTI) decode_tile(p, tile, n_tiles, ci, m_g, n_t);
+        else { m_g = tile / n_tiles; n_t = tile - m_g * n_tiles; }   // m-major: CTAs running together share A tiles, weights stay in L2
+        const ClsEntry& ce = p.cls[MULTI ? ci : 0];
+        const CUtensorMap* const mapA = &tmA.m[MULTI ? ci : 0];
         const int m_t = m_g * CL + cta_rank;
         const int m0 = m_t * kBlockM;
         int cn = 0, cp = 0, cq = 0;
@@ -257,8 +262,10 @@ k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorM
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
         KSkip ks; uint32_t any = 0;
-        int ci, m_g, n_t; decode_tile(p, tile, n_tiles, ci, m_g, n_t);
-        const ClsEntry& ce = p.cls[ci];
+        int ci = 0, m_g = 0, n_t = 0;
+        if (MULTI) decode_tile(p, tile, n_tiles, ci, m_g, n_t);
+        else if (km) n_t = tile % n_tiles;                                    // the dense single-class walk needs no tile arithmetic here
+        const ClsEntry& ce = p.cls[MULTI ? ci : 0];
         if (km) ks.begin(km, p.kmask_words, n_t * BLOCK_N, BLOCK_N, p.N);
         for (int tap = 0; tap < ce.ntaps; ++tap) {                            // a class without taps issues nothing: its
           const int kb0 = km ? (p.taps[ce.tap0 + tap].kofs >> 6) : 0;         // epilogue writes the addend (or zero) alone
@@ -298,16 +305,18 @@ k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorM
     const int half = (warp - 2) >> 2;         // which half of the 64-column chunks this warp drains
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = cl_id; tile < total_tiles; tile += n_cl) {
-      int ci, m_g, n_t; decode_tile(p, tile, n_tiles, ci, m_g, n_t);
-      const ClsEntry& ce = p.cls[ci];
-      const bool has_acc = ce.ntaps > 0;        // a class no tap reaches: the accumulator was never written, its value is zero
+      int ci = 0, m_g, n_t;
+      if (MULTI) decode_tile(p, tile, n_tiles, ci, m_g, n_t);
+      else { m_g = tile / n_tiles; n_t = tile - m_g * n_tiles; }
+      const ClsEntry& ce = p.cls[MULTI ? ci : 0];
+      const bool has_acc = MULTI ? ce.ntaps > 0 : true;   // a class no tap reaches: the accumulator was never written, its value is zero
       const int m_t = m_g * CL + cta_rank;
       const int row = m_t * kBlockM + quarter * 32 + lane;
       const bool row_ok = row < ce.M;
       long long opix = 0;
       if (row_ok && !p.tma_store) {       // generic output mapping, one division chain per tile
         opix = row;
-        if (!p.linear) {
+        if (MULTI || !p.linear) {
           int n, pp, qq; decompose_pixel(row, ce.P_it, ce.Q_it, n, pp, qq);
           opix = (long long)n * p.out_img_pix + (long long)(pp * p.osh + ce.oah) * p.out_row_pix + (qq * p.osw + ce.oaw);
         }
@@ -336,7 +345,7 @@ k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorM
         for (int i = 0; i < 8; ++i) {
           const long long r = wrow0 + r_in + 4 * i;
           long long px = r;
-          if (!p.linear && i * 4 + r_in < rows_left) {
+          if (MULTI && i * 4 + r_in < rows_left) {
             int n, pp, qq; decompose_pixel((int)r, ce.P_it, ce.Q_it, n, pp, qq);
             px = (long long)n * p.out_img_pix + (long long)(pp * p.osh + ce.oah) * p.out_row_pix + (qq * p.osw + ce.oaw);
           }
@@ -838,13 +847,13 @@ static int pick_block_n(long long m_tiles, int n) {
   return best;
 }
 
-template <int BN, int CL>
+template <int BN, int CL, bool MULTI>
 static int launch_fwd(const AMaps& a, const CUtensorMap& b, FwdParams& p, cudaStream_t st) {
   constexpr int kStages = fwd_stages(BN, CL);
   constexpr int smem = kStages * (kBlockM * kBlockK * 2 + (BN / CL) * kBlockK * 2) + 8 * 32 * 128 + 1024 + 256;
   static bool attr_set = false;
   if (!attr_set) {
-    TP_CUDA_CHECK(cudaFuncSetAttribute(k_igemm_fwd<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TP_CUDA_CHECK(cudaFuncSetAttribute(k_igemm_fwd<BN, CL, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     attr_set = true;
   }
   // work items: per class, (groups of CL M tiles) x (N tiles), classes back to back
@@ -866,7 +875,7 @@ static int launch_fwd(const AMaps& a, const CUtensorMap& b, FwdParams& p, cudaSt
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  TP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_igemm_fwd<BN, CL>, a, b, p));
+  TP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_igemm_fwd<BN, CL, MULTI>, a, b, p));
   TP_LAUNCH_CHECK();
   return TP_OK;
 }
@@ -879,14 +888,27 @@ static int run_fwd(const AMaps& a, const CUtensorMap& b, FwdParams& p, int bn, c
   p.tma_store = (p.ldc % 8 == 0 && p.N % 8 == 0 && (((uintptr_t)p.out) & 15) == 0 &&
                  (!p.addend || (((uintptr_t)p.addend) & 15) == 0)) ? 1 : 0;
   if (p.stats && !(p.tma_store && p.linear)) return TP_ERR_UNSUPPORTED;
-  if (p.cluster == 2) {
-    if (bn == 256) return launch_fwd<256, 2>(a, b, p, st);
-    if (bn == 128) return launch_fwd<128, 2>(a, b, p, st);
-    return launch_fwd<64, 2>(a, b, p, st);
+  // the general-mapping instantiation only where it is needed: parity classes, or a single class whose output is not
+  // the iteration order itself
+  const bool multi = !p.linear;
+  if (multi) {
+    if (p.cluster == 2) {
+      if (bn == 256) return launch_fwd<256, 2, true>(a, b, p, st);
+      if (bn == 128) return launch_fwd<128, 2, true>(a, b, p, st);
+      return launch_fwd<64, 2, true>(a, b, p, st);
+    }
+    if (bn == 256) return launch_fwd<256, 1, true>(a, b, p, st);
+    if (bn == 128) return launch_fwd<128, 1, true>(a, b, p, st);
+    return launch_fwd<64, 1, true>(a, b, p, st);
   }
-  if (bn == 256) return launch_fwd<256, 1>(a, b, p, st);
-  if (bn == 128) return launch_fwd<128, 1>(a, b, p, st);
-  return launch_fwd<64, 1>(a, b, p, st);
+  if (p.cluster == 2) {
+    if (bn == 256) return launch_fwd<256, 2, false>(a, b, p, st);
+    if (bn == 128) return launch_fwd<128, 2, false>(a, b, p, st);
+    return launch_fwd<64, 2, false>(a, b, p, st);
+  }
+  if (bn == 256) return launch_fwd<256, 1, false>(a, b, p, st);
+  if (bn == 128) return launch_fwd<128, 1, false>(a, b, p, st);
+  return launch_fwd<64, 1, false>(a, b, p, st);
 }
 
 // Cluster size for a problem: pairs of M tiles share the weight tile (multicast) whenever there are enough tiles.

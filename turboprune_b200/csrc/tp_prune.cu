@@ -2,7 +2,7 @@
 //
 // Replaces utils/pruning_utils.py:73-87 / :186-203 / :263-283 of the reference
 // (per-layer score temporaries, torch.cat, single-CTA 16-pass torch.kthvalue, per-layer
-// torch.where) with ONE cooperative kernel (k_topk_fused) whose phases are separated by grid-wide barriers:
+// torch.where) with ONE kernel of resident CTAs (k_topk_fused) whose phases are separated by grid-wide barriers:
 //
 //   P0 sample   : 2^20 strided samples (runs of 4 neighbours), kept in shared memory; 2048-bin histogram of key
 //                 bits [30:20], shared-memory privatised
@@ -26,7 +26,6 @@
 // integers; NaN patterns (> 0x7f800000) sort above +inf exactly like ATen's radix key
 // (SortingRadixSelect.cuh:20-39).
 #include "tp_common.cuh"
-#include <cooperative_groups.h>
 
 namespace tp {
 
@@ -41,6 +40,7 @@ struct SelState {
   unsigned long long before_lo, before_hi;
   unsigned long long k_rem;
   unsigned long long n_cand2;         // second-level list (candidates matching the top digit)
+  unsigned int barrier; unsigned int pad_;   // arrival counter of the grid barrier
   unsigned long long t_phase[8];      // %globaltimer (ns) when CTA 0 entered P0..P5 and left (tools/topk_bench.py prints the deltas)
 };
 
@@ -143,6 +143,7 @@ __device__ __forceinline__ float classify(SweepCtx& c, unsigned int key, long lo
 constexpr int kRun = 16;               // neighbouring elements per sample run
 constexpr int kLocalKeys = 4096;      // sample keys one CTA keeps in shared memory between P0 and P1 (one round of 256 runs)
 constexpr int kCand2 = 4096;          // capacity of the second-level list
+constexpr int kSmemSegs = 128;        // segment tables up to this size are searched in shared memory
 
 struct TopkArgs {
   const Seg* segs; int n_seg;
@@ -154,6 +155,24 @@ struct TopkArgs {
   float* thr_out;
 };
 
+// Grid-wide barrier for a grid that is fully resident (<= occupancy x SMs CTAs, checked on the host): one monotonically
+// increasing arrival counter (zeroed with the rest of the state before the launch), release on arrive, acquire on the spin.
+// A plain launch + this barrier costs less than a cooperative launch + cooperative_groups' grid.sync() per phase.
+struct GridBarrier {
+  unsigned int* ctr; unsigned int target;
+  __device__ __forceinline__ void sync() {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      target += gridDim.x;
+      __threadfence();
+      atomicAdd(ctr, 1u);
+      unsigned int v;
+      do { asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(ctr) : "memory"); } while (v < target);
+    }
+    __syncthreads();
+  }
+};
+
 __device__ __forceinline__ void stamp(SelState* st, int i) {
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
@@ -163,11 +182,11 @@ __device__ __forceinline__ void stamp(SelState* st, int i) {
 
 template <int KIND, bool WRITE>
 __global__ void __launch_bounds__(kSweepThreads) k_topk_fused(const TopkArgs a) {
-  namespace cg = cooperative_groups;
-  cg::grid_group grid = cg::this_grid();
-  __shared__ __align__(16) unsigned int s_keys[kLocalKeys];          // P0/P1: this CTA's sample keys;  P5: the second-level list
-  __shared__ unsigned int s_h[2 * kDigitBins];          // histograms (coarse, then the two fine ones, then select digits)
-  __shared__ uint2 s_cand[kSmemCand];
+  __shared__ __align__(16) unsigned int s_keys[kLocalKeys];          // P0/P1: this CTA's sample keys; P2: candidate staging; P5: the second-level list
+  __shared__ unsigned int s_h[2 * kDigitBins];          // histograms (coarse, then the two fine ones, then the candidates' top digit, then select digits)
+  __shared__ __align__(16) Seg s_seg[kSmemSegs];        // the segment table (evicted from L2 by whatever ran before: every binary-search
+                                                        // step of every thread was a DRAM round trip when it was read from global)
+  uint2* const s_cand = reinterpret_cast<uint2*>(s_keys);             // kSmemCand * 8 B <= sizeof(s_keys); the sample keys are dead by P2
   __shared__ unsigned int s_ncand;
   __shared__ unsigned long long s_base;
   __shared__ unsigned int s_red[2][kSweepThreads / 32];
@@ -182,6 +201,12 @@ __global__ void __launch_bounds__(kSweepThreads) k_topk_fused(const TopkArgs a) 
   // ---------------- P0: strided sample in runs of 4 neighbouring elements (one 32-byte sector per operand serves 4
   // samples), keys stay in shared memory; coarse histogram of key bits [30:20] ----------------
   stamp(st, 0);
+  GridBarrier grid; grid.ctr = &st->barrier; grid.target = 0;
+  const bool seg_smem = a.n_seg <= kSmemSegs;
+  if (seg_smem)
+    for (int i = t; i < a.n_seg * (int)(sizeof(Seg) / 16); i += kSweepThreads)
+      reinterpret_cast<uint4*>(s_seg)[i] = reinterpret_cast<const uint4*>(a.segs)[i];
+  const Seg* const segs = seg_smem ? s_seg : a.segs;
   for (int i = t; i < kDigitBins; i += kSweepThreads) s_h[i] = 0;
   __syncthreads();
   // samples are taken in runs of kRun = 16 neighbouring elements: one 64-byte DRAM burst per operand serves 16 samples.
@@ -197,8 +222,8 @@ __global__ void __launch_bounds__(kSweepThreads) k_topk_fused(const TopkArgs a) 
     for (int u = 0; u < kRun; ++u) key[u] = 0xFFFFFFFFu;                             // "no sample" (runs past S)
     if (gi < G) {
       long long e = (long long)(((unsigned long long)gi * (unsigned long long)a.N) / (unsigned long long)G);
-      const int si = find_seg_by_elem(a.segs, a.n_seg, e);
-      const Seg sg = a.segs[si];
+      const int si = find_seg_by_elem(segs, a.n_seg, e);
+      const Seg& sg = segs[si];
       long long l0 = (e - sg.start) & ~(long long)(kRun - 1);
       if (l0 + kRun > sg.n) l0 = sg.n >= kRun ? ((sg.n - kRun) & ~3ll) : 0;
       const long long nvalid = min((long long)kRun, min(sg.n - l0, a.S - gi * kRun));
@@ -277,8 +302,8 @@ __global__ void __launch_bounds__(kSweepThreads) k_topk_fused(const TopkArgs a) 
   for (long long tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
     if (t == 0) s_ncand = 0;
     __syncthreads();
-    const int si = find_seg(a.segs, a.n_seg, tile);
-    const Seg sg = a.segs[si];
+    const int si = find_seg(segs, a.n_seg, tile);
+    const Seg sg = segs[si];
     const long long base = (tile - sg.tile0) * kTileElems;
     const long long rem = sg.n - base;
     const int n_in = rem < kTileElems ? (int)rem : kTileElems;
@@ -405,8 +430,8 @@ __global__ void __launch_bounds__(kSweepThreads) k_topk_fused(const TopkArgs a) 
     for (unsigned int i = blockIdx.x * (unsigned)kSweepThreads + t; i < n; i += gridDim.x * (unsigned)kSweepThreads) {
       const uint2 cd = a.cand[i];
       if (cd.x > thr) {
-        const int si = find_seg_by_elem(a.segs, a.n_seg, (long long)cd.y);
-        a.segs[si].mo[(long long)cd.y - a.segs[si].start] = 1.f;
+        const int si = find_seg_by_elem(segs, a.n_seg, (long long)cd.y);
+        segs[si].mo[(long long)cd.y - segs[si].start] = 1.f;
       }
     }
   }
@@ -597,15 +622,16 @@ static int enqueue_topk(const TopkWs& w, int n_seg, long long tiles, long long N
   if (rs < 1) rs = 1;
   if (rs > S) rs = S;
   const double pq = (double)rs / (double)S;
-  // The samples come in runs of kRun neighbours (same filter: correlated scale), so the band is 8 sigma of the iid
-  // rank error instead of 5 (design effect up to 2.5); + kRun per segment: runs are clamped at segment ends, so a few
+  // The samples come in runs of kRun neighbours (same filter: correlated scale), so the band is 6 sigma of the iid
+  // rank error instead of 5 (covers a design effect of ~1.5 at 5 sigma); + kRun per segment: runs are clamped at segment ends, so a few
   // samples may repeat (also when S == N).  A miss is not an error, only the slow exact path.
-  const long long delta = (long long)(8.0 * sqrt((double)S * pq * (1.0 - pq)) + 8.0) + (long long)kRun * n_seg;
+  const long long delta = (long long)(6.0 * sqrt((double)S * pq * (1.0 - pq)) + 8.0) + (long long)kRun * n_seg;
   TopkArgs a;
   a.segs = w.segs; a.n_seg = n_seg; a.tiles = tiles; a.N = N; a.S = S; a.k = k; a.r_lo = rs - delta; a.r_hi = rs + delta;
   a.st = w.st; a.hist = w.hist; a.cand = w.cand; a.cap = w.cap; a.cand2 = w.cand2; a.thr_out = thr_out;
-  void* args[] = {&a};
-  TP_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)k_topk_fused<KIND, WRITE>, dim3(grid), dim3(kSweepThreads), args, 0, st));
+  // grid <= occupancy x SMs: every CTA is resident, which is what the in-kernel barrier needs
+  k_topk_fused<KIND, WRITE><<<grid, kSweepThreads, 0, st>>>(a);
+  TP_LAUNCH_CHECK();
   return TP_OK;
 }
 
