@@ -17,7 +17,8 @@ NVCC_FLAGS = [
 
 
 def lib_path() -> str:
-    return os.path.join(LIBDIR, LIBNAME)
+    # TURBOPRUNE_B200_LIB: load an alternative build of the same ABI (kernel experiments: tools/build_variant.py)
+    return os.environ.get("TURBOPRUNE_B200_LIB") or os.path.join(LIBDIR, LIBNAME)
 
 
 def _nvcc() -> str:
@@ -38,13 +39,36 @@ def _digest() -> str:
     return h.hexdigest()
 
 
+def build_variant(name: str, defines=()) -> str:
+    """Experiment build: the same sources with extra -D defines, linked to lib/variants/<name>.so (not the product library)."""
+    vdir = os.path.join(LIBDIR, "variants", name)
+    os.makedirs(vdir, exist_ok=True)
+    nvcc = _nvcc()
+    objs, procs = [], []
+    for src in SOURCES:
+        obj = os.path.join(vdir, src.replace(".cu", ".o"))
+        objs.append(obj)
+        cmd = [nvcc, *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, src), "-o", obj]
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
+    out = os.path.join(LIBDIR, "variants", f"{name}.so")
+    r = subprocess.run([nvcc, "-shared", "-cudart", "static", "-o", out, *objs], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}")
+    return out
+
+
 def build(force: bool = False, verbose: bool = True) -> str:
     """Compile every .cu for sm_100a and link lib/libturboprune_b200.so. Returns its path."""
     os.makedirs(LIBDIR, exist_ok=True)
     stamp = os.path.join(LIBDIR, "build.sha256")
     dig = _digest()
-    if not force and os.path.isfile(lib_path()) and os.path.isfile(stamp) and open(stamp).read().strip() == dig:
-        return lib_path()
+    default = os.path.join(LIBDIR, LIBNAME)
+    if not force and os.path.isfile(default) and os.path.isfile(stamp) and open(stamp).read().strip() == dig:
+        return default
     nvcc = _nvcc()
     objs, procs = [], []
     for src in SOURCES:
@@ -58,13 +82,13 @@ def build(force: bool = False, verbose: bool = True) -> str:
             raise RuntimeError(f"nvcc failed on {src}:\n{out}")
         if verbose and out.strip():
             print(out, file=sys.stderr)
-    link = [nvcc, "-shared", "-cudart", "static", "-o", lib_path(), *objs]
+    link = [nvcc, "-shared", "-cudart", "static", "-o", default, *objs]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}")
     with open(stamp, "w") as f:
         f.write(dig)
-    return lib_path()
+    return default
 
 
 if __name__ == "__main__":

@@ -82,8 +82,12 @@ struct FwdParams {
 // The staging call leaves the number of empty blocks behind the last mask row: zero (any iid unstructured mask) means
 // the K loop needs no per-block test at all.
 __device__ __forceinline__ const uint32_t* live_kmask(const uint32_t* km, int words, int N) {
+#ifdef TP_NO_KMASK          // experiment builds only: compile the skip walk out
+  return nullptr;
+#else
   if (km && __ldg(km + (size_t)((N + 63) >> 6) * words) == 0u) return nullptr;
   return km;
+#endif
 }
 
 // Which K blocks of an output-channel tile hold any non-zero weight: the OR of the occupancy words of the tile's 64-row
@@ -212,40 +216,50 @@ k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorM
         int cn = 0, cp = 0, cq = 0;
         if (p.a_mode == 1) decompose_pixel(m0, ce.P_it, ce.Q_it, cn, cp, cq);
         const int cw = ce.base_w + cq * p.step_w, ch = ce.base_h + cp * p.step_h;
-        KSkip ks; bool any = false;
-        if (km) ks.begin(km, p.kmask_words, n_t * BLOCK_N, BLOCK_N, p.N);
-        // nested tap / channel-chunk loops: no integer division on the single producer thread
-        // (the first ncu source view showed the producer, not TMA or the tensor pipe, as the limiter)
-        for (int tap = 0; tap < ce.ntaps; ++tap) {
-          const TapEntry te = p.taps[ce.tap0 + tap];
-          for (int cc = 0; cc < p.cchunks; ++cc) {
-            if (km) {
+        auto load_block = [&](const TapEntry& te, int cc) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, 1);
+          uint8_t* sA = smem + stage * kStageBytes;
+          uint8_t* sB = sA + kABytes;
+          if (CL == 1) {
+            mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+            if (p.a_mode == 1)
+              tma_load_im2col_4d(sA, mapA, &full_bar[stage], cc * kBlockK, cw, ch, cn, te.off_w, te.off_h);
+            else
+              tma_load_2d(sA, mapA, &full_bar[stage], te.kofs + cc * kBlockK, m0);
+            tma_load_2d(sB, &tmB, &full_bar[stage], te.kofs + cc * kBlockK, n_t * BLOCK_N);
+          } else {
+            // pair: my A tile and my half of the weight tile land in MY shared memory, the bytes are credited to the
+            // LEADER's full barrier (which expects both CTAs' stage bytes)
+            if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], kStageBytes * CL);
+            const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            if (p.a_mode == 1)
+              tma_load_im2col_4d_pair(sA, mapA, lead_full, cc * kBlockK, cw, ch, cn, te.off_w, te.off_h);
+            else
+              tma_load_2d_pair(sA, mapA, lead_full, te.kofs + cc * kBlockK, m0);
+            tma_load_2d_pair(sB, &tmB, lead_full, te.kofs + cc * kBlockK, n_t * BLOCK_N + cta_rank * kBRows);
+          }
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        };
+        const int tap_base = MULTI ? ce.tap0 : 0;     // single class: a static table offset (no dependent parameter load)
+        if (!km) {
+          // dense walk — nested tap / channel-chunk loops: no integer division on the single producer thread
+          // (the first ncu source view showed the producer, not TMA or the tensor pipe, as the limiter)
+          for (int tap = 0; tap < ce.ntaps; ++tap) {
+            const TapEntry te = p.taps[tap_base + tap];
+            for (int cc = 0; cc < p.cchunks; ++cc) load_block(te, cc);
+          }
+        } else {
+          // some weight blocks are empty: all-zero blocks are neither loaded nor multiplied
+          KSkip ks; bool any = false;
+          ks.begin(km, p.kmask_words, n_t * BLOCK_N, BLOCK_N, p.N);
+          for (int tap = 0; tap < ce.ntaps; ++tap) {
+            const TapEntry te = p.taps[tap_base + tap];
+            for (int cc = 0; cc < p.cchunks; ++cc) {
               const bool last = tap == ce.ntaps - 1 && cc == p.cchunks - 1;
-              if (!ks.on((te.kofs >> 6) + cc) && !(last && !any)) continue;      // all-zero weight block: no load, no MMA
+              if (!ks.on((te.kofs >> 6) + cc) && !(last && !any)) continue;
               any = true;
+              load_block(te, cc);
             }
-            mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-            uint8_t* sA = smem + stage * kStageBytes;
-            uint8_t* sB = sA + kABytes;
-            if (CL == 1) {
-              mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
-              if (p.a_mode == 1)
-                tma_load_im2col_4d(sA, mapA, &full_bar[stage], cc * kBlockK, cw, ch, cn, te.off_w, te.off_h);
-              else
-                tma_load_2d(sA, mapA, &full_bar[stage], te.kofs + cc * kBlockK, m0);
-              tma_load_2d(sB, &tmB, &full_bar[stage], te.kofs + cc * kBlockK, n_t * BLOCK_N);
-            } else {
-              // pair: my A tile and my half of the weight tile land in MY shared memory, the bytes are credited to the
-              // LEADER's full barrier (which expects both CTAs' stage bytes)
-              if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[stage], kStageBytes * CL);
-              const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
-              if (p.a_mode == 1)
-                tma_load_im2col_4d_pair(sA, mapA, lead_full, cc * kBlockK, cw, ch, cn, te.off_w, te.off_h);
-              else
-                tma_load_2d_pair(sA, mapA, lead_full, te.kofs + cc * kBlockK, m0);
-              tma_load_2d_pair(sB, &tmB, lead_full, te.kofs + cc * kBlockK, n_t * BLOCK_N + cta_rank * kBRows);
-            }
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -258,38 +272,53 @@ k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorM
       int acc = 0; uint32_t acc_phase = 0;
       const uint32_t* const km = live_kmask(p.kmask, p.kmask_words, p.N);
       for (int tile = cl_id; tile < total_tiles; tile += n_cl) {
+        if (MULTI) {      // a class no tap reaches has no accumulator: its tiles belong to the epilogue warps alone
+          int ci0, mg0, nt0; decode_tile(p, tile, n_tiles, ci0, mg0, nt0);
+          if (p.cls[ci0].ntaps == 0) continue;
+        }
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-        KSkip ks; uint32_t any = 0;
-        int ci = 0, m_g = 0, n_t = 0;
-        if (MULTI) decode_tile(p, tile, n_tiles, ci, m_g, n_t);
-        else if (km) n_t = tile % n_tiles;                                    // the dense single-class walk needs no tile arithmetic here
-        const ClsEntry& ce = p.cls[MULTI ? ci : 0];
-        if (km) ks.begin(km, p.kmask_words, n_t * BLOCK_N, BLOCK_N, p.N);
-        for (int tap = 0; tap < ce.ntaps; ++tap) {                            // a class without taps issues nothing: its
-          const int kb0 = km ? (p.taps[ce.tap0 + tap].kofs >> 6) : 0;         // epilogue writes the addend (or zero) alone
-          for (int cc = 0; cc < p.cchunks; ++cc) {
-            if (km) {
-              const bool last = tap == ce.ntaps - 1 && cc == p.cchunks - 1;
-              if (!ks.on(kb0 + cc) && !(last && !any)) continue;               // same decision as the producer
-            }
-            mbar_wait(&full_bar[stage], phase, 3);
-            tc_fence_after();
-            const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
-            const uint32_t b_addr = a_addr + kABytes;
-            const uint64_t adesc = make_smem_desc(a_addr, 16, 1024, kLayoutSW128);
-            const uint64_t bdesc = make_smem_desc(b_addr, 16, 1024, kLayoutSW128);
+        auto mma_block = [&](uint32_t accumulate) {
+          mbar_wait(&full_bar[stage], phase, 3);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
+          const uint32_t b_addr = a_addr + kABytes;
+          const uint64_t adesc = make_smem_desc(a_addr, 16, 1024, kLayoutSW128);
+          const uint64_t bdesc = make_smem_desc(b_addr, 16, 1024, kLayoutSW128);
 #pragma unroll
-            for (int k = 0; k < kBlockK / 16; ++k) {
-              // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in 16-B units
-              if (CL == 1) umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, any | (uint32_t)k);
-              else umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, any | (uint32_t)k);
+          for (int k = 0; k < kBlockK / 16; ++k) {
+            // advance 16 elements (32 B) along K inside the 128-B swizzle row: +2 in 16-B units
+            if (CL == 1) umma_bf16(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate | (uint32_t)k);
+            else umma_bf16_pair(d_tmem, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), idesc, accumulate | (uint32_t)k);
+          }
+          // frees this smem stage (in both CTAs of a pair) when the MMAs have read it
+          if (CL == 1) umma_commit(&empty_bar[stage]); else umma_commit_pair(&empty_bar[stage], kMask);
+          if (++stage == kStages) { stage = 0; phase ^= 1; }
+        };
+        if (!MULTI && !km) {
+          // dense single-class walk: no tile arithmetic at all on this thread (it paces the tensor pipe)
+          const int kiters = p.cls[0].ntaps * p.cchunks;
+          for (int it = 0; it < kiters; ++it) mma_block((uint32_t)it);
+        } else {
+          int ci = 0, m_g = 0, n_t = 0;
+          if (MULTI) decode_tile(p, tile, n_tiles, ci, m_g, n_t); else n_t = tile % n_tiles;
+          const ClsEntry& ce = p.cls[MULTI ? ci : 0];       // a class without taps issues nothing: its epilogue writes the addend (or zero) alone
+          if (!km) {
+            const int kiters = ce.ntaps * p.cchunks;
+            for (int it = 0; it < kiters; ++it) mma_block((uint32_t)it);
+          } else {
+            KSkip ks; uint32_t any = 0;
+            ks.begin(km, p.kmask_words, n_t * BLOCK_N, BLOCK_N, p.N);
+            for (int tap = 0; tap < ce.ntaps; ++tap) {
+              const int kb0 = p.taps[(MULTI ? ce.tap0 : 0) + tap].kofs >> 6;
+              for (int cc = 0; cc < p.cchunks; ++cc) {
+                const bool last = tap == ce.ntaps - 1 && cc == p.cchunks - 1;
+                if (!ks.on(kb0 + cc) && !(last && !any)) continue;               // same decision as the producer
+                mma_block(any);
+                any = 1;
+              }
             }
-            any = 1;
-            // frees this smem stage (in both CTAs of a pair) when the MMAs have read it
-            if (CL == 1) umma_commit(&empty_bar[stage]); else umma_commit_pair(&empty_bar[stage], kMask);
-            if (++stage == kStages) { stage = 0; phase ^= 1; }
           }
         }
         // accumulator complete -> epilogue (of both CTAs of a pair)
@@ -322,37 +351,66 @@ k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorM
         }
       }
       __nv_bfloat16* orow = p.out + opix * p.ldc;
+      // staged-path geometry of this lane: rows r_in + 4i of the warp's 32, 16-byte column c16 of each 128-byte row
+      const int r_in = lane >> 3, c16 = lane & 7;
+      const long long wrow0 = (long long)m_t * kBlockM + quarter * 32;        // first row of this warp's 32
+      const int rows_left = (int)(ce.M - wrow0 < 32 ? (ce.M - wrow0 < 0 ? 0 : ce.M - wrow0) : 32);
+      const long long ldc = p.ldc;
+      const int N = p.N;
+      // element offset of output row i (rows r_in + 4i): the iteration pixel itself for a single class; for parity classes
+      // the destination pixel — ONE division chain for the first row, the other seven follow by stepping 4 pixels
+      long long ooff[MULTI ? 8 : 1];
+      const long long rbase = (wrow0 + r_in) * ldc + c16 * 8;
+      if (MULTI && p.tma_store) {
+        int n, pp, qq; decompose_pixel((int)(wrow0 + r_in), ce.P_it, ce.Q_it, n, pp, qq);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const long long px = (long long)n * p.out_img_pix + (long long)(pp * p.osh + ce.oah) * p.out_row_pix + (qq * p.osw + ce.oaw);
+          ooff[i] = px * ldc + c16 * 8;
+          qq += 4;
+          while (qq >= ce.Q_it) { qq -= ce.Q_it; if (++pp == ce.P_it) { pp = 0; ++n; } }
+        }
+      }
+      auto row_off = [&](int i) -> long long { return MULTI ? ooff[MULTI ? i : 0] : rbase + (long long)(i * 4) * ldc; };
+      if (MULTI && !has_acc) {
+        // parity class no tap reaches (e.g. 3 of the 4 classes of a 1x1 stride-2 convolution): dX there is the fused addend
+        // or zero — plain coalesced copies / stores; no accumulator exists, so no hand-shake with the MMA thread either
+        if (p.tma_store) {
+#pragma unroll 1
+          for (int c = half * 64; c < BLOCK_N; c += 128) {
+            const int n0 = n_t * BLOCK_N + c;
+            if (n0 >= N) break;
+            if (n0 + c16 * 8 + 8 > N) continue;
+            uint4 z[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              z[i] = make_uint4(0u, 0u, 0u, 0u);
+              if (p.addend && i * 4 + r_in < rows_left) z[i] = *reinterpret_cast<const uint4*>(p.addend + row_off(i) + n0);
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (i * 4 + r_in < rows_left) *reinterpret_cast<uint4*>(p.out + row_off(i) + n0) = z[i];
+          }
+        } else if (row_ok && half == 0) {
+          for (int j = n_t * BLOCK_N; j < min(p.N, (n_t + 1) * BLOCK_N); ++j)
+            orow[j] = p.addend ? p.addend[opix * p.ldc + j] : __float2bfloat16_rn(0.f);
+        }
+        continue;
+      }
       mbar_wait(&tfull_bar[acc], acc_phase, 4);
       tc_fence_after();
       const uint32_t t_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BLOCK_N);
       if (p.tma_store) {
-        // Linear output: TMEM -> registers -> 128B-swizzled smem sub-tile (32 rows x 64 cols) -> coalesced global
+        // TMEM -> registers -> 128B-swizzled smem sub-tile (32 rows x 64 cols) -> coalesced global
         // stores, so every output line leaves the SM as full 128-byte rows instead of 32 scattered 16-byte pieces.
         // Everything that does not depend on the column chunk is hoisted (row pointers, validity, swizzled
         // staging offsets) and the staging buffer is addressed through the shared window (st/ld.shared, not
         // generic): the ncu source view of the first version had this loop at 2.3 us per 128x256 tile — longer
         // than the tile's MMAs (1.1 us) — with its stalls on generic LD/ST and re-loaded kernel parameters.
         const uint32_t buf = smem_u32(stg_base + (warp - 2) * kStgBytes);
-        const int r_in = lane >> 3, c16 = lane & 7;
-        const long long wrow0 = (long long)m_t * kBlockM + quarter * 32;        // first row of this warp's 32
-        const int rows_left = (int)(ce.M - wrow0 < 32 ? (ce.M - wrow0 < 0 ? 0 : ce.M - wrow0) : 32);
-        const long long ldc = p.ldc;
-        const int N = p.N;
-        // element offset of the 8 output rows this lane moves (rows r_in + 4i of the warp's 32): the iteration pixel itself
-        // for a linear output, the parity-class pixel of a strided dgrad otherwise (8 division chains per tile)
-        long long ooff[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const long long r = wrow0 + r_in + 4 * i;
-          long long px = r;
-          if (MULTI && i * 4 + r_in < rows_left) {
-            int n, pp, qq; decompose_pixel((int)r, ce.P_it, ce.Q_it, n, pp, qq);
-            px = (long long)n * p.out_img_pix + (long long)(pp * p.osh + ce.oah) * p.out_row_pix + (qq * p.osw + ce.oaw);
-          }
-          ooff[i] = px * ldc + c16 * 8;
-        }
         __nv_bfloat16* const gout = p.out;
         const __nv_bfloat16* const gadd = p.addend;
+        {
         const float* bias = p.bias;
         float* stats = p.stats ? p.stats + (long long)(m_t * 4 + quarter) * 2 * N + c16 * 8 : nullptr;
         const uint32_t wr_base = buf + lane * 128;                              // my row (TMEM lane) in the staging tile
@@ -376,7 +434,7 @@ k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorM
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 a_pref[i] = make_uint4(0u, 0u, 0u, 0u);
-                if (i * 4 + r_in < rows_left && col_ok) a_pref[i] = *reinterpret_cast<const uint4*>(gadd + ooff[i] + n0);
+                if (i * 4 + r_in < rows_left && col_ok) a_pref[i] = *reinterpret_cast<const uint4*>(gadd + row_off(i) + n0);
               }
             }
 #pragma unroll
@@ -386,7 +444,7 @@ k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorM
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 a_pref[i] = make_uint4(0u, 0u, 0u, 0u);
-                if (i * 4 + r_in < rows_left && col_ok2) a_pref[i] = *reinterpret_cast<const uint4*>(gadd + ooff[i] + n0 + 128);
+                if (i * 4 + r_in < rows_left && col_ok2) a_pref[i] = *reinterpret_cast<const uint4*>(gadd + row_off(i) + n0 + 128);
               }
             }
             __syncwarp();
@@ -396,7 +454,7 @@ k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorM
           for (int j = 0; j < 64; j += 8) {
             float f[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) f[q] = has_acc ? __uint_as_float(v[j + q]) : 0.f;
+            for (int q = 0; q < 8; ++q) f[q] = __uint_as_float(v[j + q]);
             if (bias) {
 #pragma unroll
               for (int q = 0; q < 8; ++q) if (n0 + j + q < N) f[q] += bias[n0 + j + q];
@@ -427,7 +485,7 @@ k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorM
           for (int i = 0; i < 8; ++i) o[i] = lds128(((i & 1) ? rd_odd : rd_even) + (uint32_t)((i >> 1) * 1024));
 #pragma unroll
           for (int i = 0; i < 8; ++i)
-            if (i * 4 + r_in < rows_left && col_ok) *reinterpret_cast<uint4*>(gout + ooff[i] + n0) = o[i];
+            if (i * 4 + r_in < rows_left && col_ok) *reinterpret_cast<uint4*>(gout + row_off(i) + n0) = o[i];
           if (stats) {
             // BatchNorm batch statistics of exactly the values just stored (bf16-rounded): this thread owns 8 channels
             // of rows r_in, r_in+4, ...; a fixed-order xor tree over the 4 row groups finishes the 32 rows
@@ -460,6 +518,7 @@ k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorM
           }
           __syncwarp();
         }
+        }   // has_acc
       } else {
 #pragma unroll 1
       for (int c = half * 32; c < BLOCK_N; c += 64) {
@@ -470,7 +529,7 @@ k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorM
         if (row_ok && n0 < p.N) {
           float f[32];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = has_acc ? __uint_as_float(v[j]) : 0.f;
+          for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
           if (p.bias) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) if (n0 + j < p.N) f[j] += p.bias[n0 + j];
