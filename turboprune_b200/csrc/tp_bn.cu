@@ -295,16 +295,18 @@ __global__ void __launch_bounds__(kBnThreads) k_bn_bwd_reduce(const __nv_bfloat1
     }
     const long long stride = (long long)gridDim.x * TY;
     long long p = (long long)blockIdx.x * TY + ty;
-    for (; p + 1 * stride < M; p += 2 * stride) {
-      uint4 vd[2], vz[2], vy[2];
+    // 4 pixel rows in flight per thread (8-12 independent 16-byte loads): with 2 the pass ran at 77 % of the copy rate
+    constexpr int UR = 4;
+    for (; p + (UR - 1) * stride < M; p += UR * stride) {
+      uint4 vd[UR], vz[UR], vy[UR];
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < UR; ++u) {
         const size_t off = (size_t)(p + u * stride) * C + (size_t)cvec * 8;
         vd[u] = ldg16(dz + off); vy[u] = ldg16(y + off);
         if (RELU == 1) vz[u] = ldg16(z + off);
       }
 #pragma unroll
-      for (int u = 0; u < 2; ++u) {
+      for (int u = 0; u < UR; ++u) {
         float d[8], yy[8], zz[8]; unpack8(vd[u], d); unpack8(vy[u], yy);
         if (RELU == 1) unpack8(vz[u], zz);
 #pragma unroll
@@ -388,16 +390,17 @@ __global__ void __launch_bounds__(kBnThreads) k_bn_bwd_apply(const __nv_bfloat16
   }
   const long long stride = (long long)gridDim.x * TY;
   long long p = (long long)blockIdx.x * TY + ty;
-  for (; p + 1 * stride < M; p += 2 * stride) {
-    uint4 vd[2], vz[2], vy[2];
+  constexpr int UR = 4;
+  for (; p + (UR - 1) * stride < M; p += UR * stride) {
+    uint4 vd[UR], vz[UR], vy[UR];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < UR; ++u) {
       const size_t off = (size_t)(p + u * stride) * C + (size_t)cvec * 8;
       vd[u] = ldg16(dz + off); vy[u] = ldg16(y + off);
       if (RELU == 1) vz[u] = ldg16(z + off);
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < UR; ++u) {
       const size_t off = (size_t)(p + u * stride) * C + (size_t)cvec * 8;
       float d[8], yy[8], zz[8], o[8]; unpack8(vd[u], d); unpack8(vy[u], yy);
       if (RELU == 1) unpack8(vz[u], zz);
