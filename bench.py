@@ -275,6 +275,7 @@ def main():
     ap.add_argument("--no-gpu-eager", action="store_true", help="skip the cuDNN / ATen / NCCL 'kernels to beat' sub-record")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the train step into a CUDA graph")
     ap.add_argument("--no-overlap", action="store_true", help="launch the gradient exchange after the backward pass")
+    ap.add_argument("--no-wgrad-side-stream", action="store_true", help="keep the weight-gradient GEMMs on the compute stream")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -308,6 +309,7 @@ def main():
         "+dataset_params.synthetic_fresh=true", "optimizer_params.weight_decay=1e-4",
         f"experiment_params.distributed={'true' if world > 1 else 'false'}",
         f"+experiment_params.cuda_graph={'true' if use_graph else 'false'}",
+        f"+experiment_params.wgrad_side_stream={'false' if args.no_wgrad_side_stream else 'true'}",
         f"experiment_params.base_dir={tempfile.gettempdir()}"], os.path.join(ROOT, "conf_b200"))
     torch.manual_seed(0)
     model = cm.TorchVisionModel(cfg)             # seed-0 ResNet-50

@@ -295,8 +295,9 @@ __global__ void __launch_bounds__(kBnThreads) k_bn_bwd_reduce(const __nv_bfloat1
     }
     const long long stride = (long long)gridDim.x * TY;
     long long p = (long long)blockIdx.x * TY + ty;
-    // 4 pixel rows in flight per thread (8-12 independent 16-byte loads): with 2 the pass ran at 77 % of the copy rate
-    constexpr int UR = 4;
+    // 2 pixel rows in flight per thread (4-6 independent 16-byte loads); 4 rows measured SLOWER (6.9 -> 7.5 ms per step
+    // over the 53 layers): the extra registers cost more occupancy than the deeper queue buys
+    constexpr int UR = 2;
     for (; p + (UR - 1) * stride < M; p += UR * stride) {
       uint4 vd[UR], vz[UR], vy[UR];
 #pragma unroll
@@ -390,7 +391,7 @@ __global__ void __launch_bounds__(kBnThreads) k_bn_bwd_apply(const __nv_bfloat16
   }
   const long long stride = (long long)gridDim.x * TY;
   long long p = (long long)blockIdx.x * TY + ty;
-  constexpr int UR = 4;
+  constexpr int UR = 2;
   for (; p + (UR - 1) * stride < M; p += UR * stride) {
     uint4 vd[UR], vz[UR], vy[UR];
 #pragma unroll

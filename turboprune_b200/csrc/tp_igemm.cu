@@ -65,6 +65,7 @@ struct FwdParams {
   int out_row_pix;          // output pixels per row
   int osh, osw;
   int linear;               // output pixel index == iteration pixel index (single class, unit output stride)
+  int ws_stages, ws_b_bytes;   // weight-stationary instantiation: activation stages, bytes of the resident weight blocks
   int ldc;                  // elements between consecutive output pixels
   int cluster;              // thread-block cluster size along M (1 or 2): weight tile multicast
   int tma_store;            // 1: epilogue stages 32x64 sub-tiles in smem and stores them with TMA (tmC)
@@ -150,10 +151,18 @@ __device__ __forceinline__ void decode_tile(const FwdParams& p, int tile, int n_
 // MULTI = false: one class of output pixels (fprop, stride-1 dgrad) — the class decode, the per-row destination
 // arithmetic and the "class without taps" handling are compiled out (they cost the short-K layers up to 1.7x when they
 // sat in the common kernel: 1600 more instructions around loops that run once per 2-4 us tile).
-template <int BLOCK_N, int CL, bool MULTI>
+//
+// WS = true ("weight stationary", single class, CL = 1): when all K blocks of an output-channel tile fit in shared memory
+// next to a few activation stages (K x BLOCK_N x 2 B <= 144 KB: every 1x1 layer of ResNet-50's layer1-3, the 64-channel
+// 3x3s), a CTA keeps ONE output-channel tile for its whole life, loads its weight blocks once and then streams only
+// activation tiles.  The dense walk re-loaded BLOCK_N x 64 weights with every K block of every tile: for the 1x1 layers
+// that was 2/3 of the L2 -> SM operand traffic (128 of 192 KB per 128 x 256 x 256 tile) and it — not HBM, not the tensor
+// pipe — paced them (profiles/r01_notes.md: layer3 1x1 at 3.35 us per tile against 1.1 us of MMA and 1.9 us of HBM time).
+template <int BLOCK_N, int CL, bool MULTI, bool WS>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ FwdParams p) {
+  static_assert(!WS || (CL == 1 && !MULTI), "weight-stationary walk: single CTA, single class");
   constexpr int kABytes = kBlockM * kBlockK * 2;           // 16 KB
   constexpr int kBRows = BLOCK_N / CL;                     // weight rows THIS CTA loads
   constexpr int kBBytes = kBRows * kBlockK * 2;
@@ -165,12 +174,17 @@ k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorM
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   constexpr int kStgBytes = 32 * 128;                      // one epilogue warp's 32 rows x 64 bf16 columns
-  uint8_t* stg_base = smem + kStages * kStageBytes;        // 4 warps x 2 buffers x 4 KB (1024-B aligned)
+  constexpr int kMaxStages = 16;
+  const int n_stages = WS ? p.ws_stages : kStages;         // WS: a stage is the 16 KB activation tile alone
+  const int a_stride = WS ? kABytes : kStageBytes;
+  uint8_t* const a_base = WS ? smem + p.ws_b_bytes : smem; // WS: the resident weight blocks come first
+  uint8_t* stg_base = a_base + n_stages * a_stride;        // 4 warps x 2 buffers x 4 KB (1024-B aligned)
   uint64_t* full_bar = (uint64_t*)(stg_base + 8 * kStgBytes);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tfull_bar = empty_bar + kStages;
+  uint64_t* empty_bar = full_bar + (WS ? kMaxStages : kStages);
+  uint64_t* tfull_bar = empty_bar + (WS ? kMaxStages : kStages);
   uint64_t* tempty_bar = tfull_bar + kAccStages;
-  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + kAccStages);
+  uint64_t* bres_bar = tempty_bar + kAccStages;            // WS: the resident weight blocks have landed
+  uint32_t* tmem_slot = (uint32_t*)(bres_bar + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
@@ -180,6 +194,19 @@ k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorM
   const int cl_id = (int)blockIdx.x / CL, n_cl = (int)gridDim.x / CL;
   const int total_tiles = p.cls[p.ncls - 1].tile0 + p.cls[p.ncls - 1].m_groups * n_tiles;
   constexpr uint16_t kMask = (uint16_t)((1u << CL) - 1u);
+  // the w-th work item of this CTA.  WS: one fixed N tile, M tiles ws_m0, ws_m0 + ws_dm, ... (CTAs with neighbouring ids
+  // take the same M tile for the n_tiles different N tiles at about the same time: the activation tile comes from HBM once)
+  const int ws_nt = WS ? (int)blockIdx.x % n_tiles : 0;
+  const int ws_m0 = WS ? (int)blockIdx.x / n_tiles : 0, ws_dm = WS ? (int)gridDim.x / n_tiles : 1;
+  const int my_items = WS ? (p.cls[0].m_groups > ws_m0 ? (p.cls[0].m_groups - ws_m0 + ws_dm - 1) / ws_dm : 0)
+                          : (total_tiles > cl_id ? (total_tiles - cl_id + n_cl - 1) / n_cl : 0);
+  auto get_tile = [&](int w, int& ci, int& m_g, int& n_t) {
+    ci = 0;
+    if (WS) { m_g = ws_m0 + w * ws_dm; n_t = ws_nt; return; }
+    const int tile = cl_id + w * n_cl;
+    if (MULTI) decode_tile(p, tile, n_tiles, ci, m_g, n_t);
+    else { m_g = tile / n_tiles; n_t = tile - m_g * n_tiles; }   // m-major: CTAs running together share A tiles, weights stay in L2
+  };
 
   if (warp == 0 && lane == 0) {
     for (int j = 0; j < p.ncls; ++j) prefetch_tmap(&tmA.m[j]);
@@ -187,8 +214,9 @@ k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorM
     // full / tempty are only used in the leader CTA of a pair: full gets ONE arrive (the leader's expect_tx for both
     // CTAs' bytes), tempty gets one arrive per epilogue warp of both CTAs; empty / tfull exist in both CTAs and get
     // one (multicast) commit arrival from the leader's MMA thread
-    for (int i = 0; i < kStages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+    for (int i = 0; i < n_stages; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
     for (int i = 0; i < kAccStages; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 8 * CL); }
+    mbar_init(bres_bar, 1);
     fence_mbar_init();
   }
   if (warp == 1) {
@@ -205,10 +233,16 @@ k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorM
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       const uint32_t* const km = live_kmask(p.kmask, p.kmask_words, p.N);
-      for (int tile = cl_id; tile < total_tiles; tile += n_cl) {
-        int ci = 0, m_g, n_t;
-        if (MULTI) decode_tile(p, tile, n_tiles, ci, m_g, n_t);
-        else { m_g = tile / n_tiles; n_t = tile - m_g * n_tiles; }   // m-major: CTAs running together share A tiles, weights stay in L2
+      if (WS && my_items > 0) {
+        // every K block of this CTA's output-channel tile, once
+        const ClsEntry& c0 = p.cls[0];
+        mbar_arrive_expect_tx(bres_bar, (uint32_t)(c0.ntaps * p.cchunks * kBBytes));
+        for (int tap = 0; tap < c0.ntaps; ++tap)
+          for (int cc = 0; cc < p.cchunks; ++cc)
+            tma_load_2d(smem + (tap * p.cchunks + cc) * kBBytes, &tmB, bres_bar, p.taps[tap].kofs + cc * kBlockK, ws_nt * BLOCK_N);
+      }
+      for (int w = 0; w < my_items; ++w) {
+        int ci, m_g, n_t; get_tile(w, ci, m_g, n_t);
         const ClsEntry& ce = p.cls[MULTI ? ci : 0];
         const CUtensorMap* const mapA = &tmA.m[MULTI ? ci : 0];
         const int m_t = m_g * CL + cta_rank;
@@ -218,15 +252,15 @@ k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorM
         const int cw = ce.base_w + cq * p.step_w, ch = ce.base_h + cp * p.step_h;
         auto load_block = [&](const TapEntry& te, int cc) {
           mbar_wait(&empty_bar[stage], phase ^ 1, 1);
-          uint8_t* sA = smem + stage * kStageBytes;
+          uint8_t* sA = a_base + stage * a_stride;
           uint8_t* sB = sA + kABytes;
           if (CL == 1) {
-            mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+            mbar_arrive_expect_tx(&full_bar[stage], WS ? kABytes : kStageBytes);
             if (p.a_mode == 1)
               tma_load_im2col_4d(sA, mapA, &full_bar[stage], cc * kBlockK, cw, ch, cn, te.off_w, te.off_h);
             else
               tma_load_2d(sA, mapA, &full_bar[stage], te.kofs + cc * kBlockK, m0);
-            tma_load_2d(sB, &tmB, &full_bar[stage], te.kofs + cc * kBlockK, n_t * BLOCK_N);
+            if (!WS) tma_load_2d(sB, &tmB, &full_bar[stage], te.kofs + cc * kBlockK, n_t * BLOCK_N);
           } else {
             // pair: my A tile and my half of the weight tile land in MY shared memory, the bytes are credited to the
             // LEADER's full barrier (which expects both CTAs' stage bytes)
@@ -238,7 +272,7 @@ k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorM
               tma_load_2d_pair(sA, mapA, lead_full, te.kofs + cc * kBlockK, m0);
             tma_load_2d_pair(sB, &tmB, lead_full, te.kofs + cc * kBlockK, n_t * BLOCK_N + cta_rank * kBRows);
           }
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         };
         const int tap_base = MULTI ? ce.tap0 : 0;     // single class: a static table offset (no dependent parameter load)
         if (!km) {
@@ -271,7 +305,9 @@ k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorM
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       const uint32_t* const km = live_kmask(p.kmask, p.kmask_words, p.N);
-      for (int tile = cl_id; tile < total_tiles; tile += n_cl) {
+      if (WS && my_items > 0) { mbar_wait(bres_bar, 0, 5); tc_fence_after(); }
+      for (int w = 0; w < my_items; ++w) {
+        const int tile = cl_id + w * n_cl;      // (not used by the weight-stationary walk)
         if (MULTI) {      // a class no tap reaches has no accumulator: its tiles belong to the epilogue warps alone
           int ci0, mg0, nt0; decode_tile(p, tile, n_tiles, ci0, mg0, nt0);
           if (p.cls[ci0].ntaps == 0) continue;
@@ -279,11 +315,11 @@ k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorM
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BLOCK_N);
-        auto mma_block = [&](uint32_t accumulate) {
+        auto mma_block = [&](uint32_t accumulate, int kb) {
           mbar_wait(&full_bar[stage], phase, 3);
           tc_fence_after();
-          const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
-          const uint32_t b_addr = a_addr + kABytes;
+          const uint32_t a_addr = smem_u32(a_base + stage * a_stride);
+          const uint32_t b_addr = WS ? smem_u32(smem + kb * kBBytes) : a_addr + kABytes;   // WS: K block kb of the resident tile
           const uint64_t adesc = make_smem_desc(a_addr, 16, 1024, kLayoutSW128);
           const uint64_t bdesc = make_smem_desc(b_addr, 16, 1024, kLayoutSW128);
 #pragma unroll
@@ -294,19 +330,19 @@ k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorM
           }
           // frees this smem stage (in both CTAs of a pair) when the MMAs have read it
           if (CL == 1) umma_commit(&empty_bar[stage]); else umma_commit_pair(&empty_bar[stage], kMask);
-          if (++stage == kStages) { stage = 0; phase ^= 1; }
+          if (++stage == n_stages) { stage = 0; phase ^= 1; }
         };
         if (!MULTI && !km) {
           // dense single-class walk: no tile arithmetic at all on this thread (it paces the tensor pipe)
           const int kiters = p.cls[0].ntaps * p.cchunks;
-          for (int it = 0; it < kiters; ++it) mma_block((uint32_t)it);
+          for (int it = 0; it < kiters; ++it) mma_block((uint32_t)it, it);
         } else {
           int ci = 0, m_g = 0, n_t = 0;
-          if (MULTI) decode_tile(p, tile, n_tiles, ci, m_g, n_t); else n_t = tile % n_tiles;
+          if (MULTI) decode_tile(p, tile, n_tiles, ci, m_g, n_t); else n_t = WS ? ws_nt : tile % n_tiles;
           const ClsEntry& ce = p.cls[MULTI ? ci : 0];       // a class without taps issues nothing: its epilogue writes the addend (or zero) alone
           if (!km) {
             const int kiters = ce.ntaps * p.cchunks;
-            for (int it = 0; it < kiters; ++it) mma_block((uint32_t)it);
+            for (int it = 0; it < kiters; ++it) mma_block((uint32_t)it, it);
           } else {
             KSkip ks; uint32_t any = 0;
             ks.begin(km, p.kmask_words, n_t * BLOCK_N, BLOCK_N, p.N);
@@ -315,7 +351,7 @@ k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorM
               for (int cc = 0; cc < p.cchunks; ++cc) {
                 const bool last = tap == ce.ntaps - 1 && cc == p.cchunks - 1;
                 if (!ks.on(kb0 + cc) && !(last && !any)) continue;               // same decision as the producer
-                mma_block(any);
+                mma_block(any, tap * p.cchunks + cc);
                 any = 1;
               }
             }
@@ -333,10 +369,8 @@ k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorM
     const int quarter = warp & 3;             // TMEM lane quarter this warp may access
     const int half = (warp - 2) >> 2;         // which half of the 64-column chunks this warp drains
     int acc = 0; uint32_t acc_phase = 0;
-    for (int tile = cl_id; tile < total_tiles; tile += n_cl) {
-      int ci = 0, m_g, n_t;
-      if (MULTI) decode_tile(p, tile, n_tiles, ci, m_g, n_t);
-      else { m_g = tile / n_tiles; n_t = tile - m_g * n_tiles; }
+    for (int w = 0; w < my_items; ++w) {
+      int ci, m_g, n_t; get_tile(w, ci, m_g, n_t);
       const ClsEntry& ce = p.cls[MULTI ? ci : 0];
       const bool has_acc = MULTI ? ce.ntaps > 0 : true;   // a class no tap reaches: the accumulator was never written, its value is zero
       const int m_t = m_g * CL + cta_rank;
@@ -906,17 +940,28 @@ static int pick_block_n(long long m_tiles, int n) {
   return best;
 }
 
-template <int BN, int CL, bool MULTI>
+constexpr int kSmemMax = 232448;                 // 227 KB: the per-CTA opt-in limit of sm_100
+constexpr int kWsMaxBBytes = 144 * 1024;         // resident weight blocks of the weight-stationary walk
+
+template <int BN, int CL, bool MULTI, bool WS>
 static int launch_fwd(const AMaps& a, const CUtensorMap& b, FwdParams& p, cudaStream_t st) {
   constexpr int kStages = fwd_stages(BN, CL);
-  constexpr int smem = kStages * (kBlockM * kBlockK * 2 + (BN / CL) * kBlockK * 2) + 8 * 32 * 128 + 1024 + 256;
+  constexpr int kTail = 8 * 32 * 128 + 1024 + 512;    // epilogue staging, alignment slack, barriers
+  int smem = kStages * (kBlockM * kBlockK * 2 + (BN / CL) * kBlockK * 2) + kTail;
+  const int n_tiles = (p.N + BN - 1) / BN;
+  if (WS) {
+    p.ws_b_bytes = p.cls[0].ntaps * p.cchunks * BN * kBlockK * 2;
+    p.ws_stages = (kSmemMax - kTail - p.ws_b_bytes) / (kBlockM * kBlockK * 2);
+    if (p.ws_stages > 16) p.ws_stages = 16;
+    if (p.ws_stages < 3) return TP_ERR_UNSUPPORTED;
+    smem = p.ws_b_bytes + p.ws_stages * kBlockM * kBlockK * 2 + kTail;
+  }
   static bool attr_set = false;
   if (!attr_set) {
-    TP_CUDA_CHECK(cudaFuncSetAttribute(k_igemm_fwd<BN, CL, MULTI>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    TP_CUDA_CHECK(cudaFuncSetAttribute(k_igemm_fwd<BN, CL, MULTI, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS ? kSmemMax : smem));
     attr_set = true;
   }
   // work items: per class, (groups of CL M tiles) x (N tiles), classes back to back
-  const int n_tiles = (p.N + BN - 1) / BN;
   long long ctiles = 0;
   for (int c = 0; c < p.ncls; ++c) {
     const long long m_tiles = (p.cls[c].M + kBlockM - 1) / kBlockM;
@@ -927,14 +972,15 @@ static int launch_fwd(const AMaps& a, const CUtensorMap& b, FwdParams& p, cudaSt
   }
   if (ctiles > 0x7fffffffll || ctiles <= 0) return TP_ERR_UNSUPPORTED;
   const long long max_cl = sm_count() / CL;
-  const int grid = (int)(ctiles < max_cl ? ctiles : max_cl) * CL;
+  int grid = (int)(ctiles < max_cl ? ctiles : max_cl) * CL;
+  if (WS) grid = (sm_count() / n_tiles) * n_tiles;           // every CTA owns one N tile: a whole number of CTAs per N tile
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kFwdThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  TP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_igemm_fwd<BN, CL, MULTI>, a, b, p));
+  TP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_igemm_fwd<BN, CL, MULTI, WS>, a, b, p));
   TP_LAUNCH_CHECK();
   return TP_OK;
 }
@@ -952,22 +998,38 @@ static int run_fwd(const AMaps& a, const CUtensorMap& b, FwdParams& p, int bn, c
   const bool multi = !p.linear;
   if (multi) {
     if (p.cluster == 2) {
-      if (bn == 256) return launch_fwd<256, 2, true>(a, b, p, st);
-      if (bn == 128) return launch_fwd<128, 2, true>(a, b, p, st);
-      return launch_fwd<64, 2, true>(a, b, p, st);
+      if (bn == 256) return launch_fwd<256, 2, true, false>(a, b, p, st);
+      if (bn == 128) return launch_fwd<128, 2, true, false>(a, b, p, st);
+      return launch_fwd<64, 2, true, false>(a, b, p, st);
     }
-    if (bn == 256) return launch_fwd<256, 1, true>(a, b, p, st);
-    if (bn == 128) return launch_fwd<128, 1, true>(a, b, p, st);
-    return launch_fwd<64, 1, true>(a, b, p, st);
+    if (bn == 256) return launch_fwd<256, 1, true, false>(a, b, p, st);
+    if (bn == 128) return launch_fwd<128, 1, true, false>(a, b, p, st);
+    return launch_fwd<64, 1, true, false>(a, b, p, st);
   }
   if (p.cluster == 2) {
-    if (bn == 256) return launch_fwd<256, 2, false>(a, b, p, st);
-    if (bn == 128) return launch_fwd<128, 2, false>(a, b, p, st);
-    return launch_fwd<64, 2, false>(a, b, p, st);
+    if (bn == 256) return launch_fwd<256, 2, false, false>(a, b, p, st);
+    if (bn == 128) return launch_fwd<128, 2, false, false>(a, b, p, st);
+    return launch_fwd<64, 2, false, false>(a, b, p, st);
   }
-  if (bn == 256) return launch_fwd<256, 1, false>(a, b, p, st);
-  if (bn == 128) return launch_fwd<128, 1, false>(a, b, p, st);
-  return launch_fwd<64, 1, false>(a, b, p, st);
+  // weight-stationary walk: the tile's weight blocks fit next to >= 3 activation stages, there is a whole number of CTAs
+  // per N tile and enough M tiles for every CTA to amortise the one-time weight load
+  const int n_tiles = (p.N + bn - 1) / bn;
+  const long long m_tiles = (p.cls[0].M + kBlockM - 1) / kBlockM;
+  const long long b_bytes = (long long)p.cls[0].ntaps * p.cchunks * bn * kBlockK * 2;
+  // Measured on B200 (profiles/r02_notes.md, conv_bench at B = 512): bit-identical, but only 0-5 % faster on the layer3
+  // 1x1s and 5-8 % SLOWER on layer1's (fewer bytes in flight per SM with 16 KB stages) — like the cta_group::2 pair kernel
+  // of round 1 this says the weight bytes crossing L2 -> SM are not what paces these layers.  Opt-in (TP_IGEMM_WS=1),
+  // parity-tested.
+  const char* e = getenv("TP_IGEMM_WS");
+  const bool ws = e && atoi(e) != 0 && b_bytes <= kWsMaxBBytes && n_tiles <= sm_count() / 2 && m_tiles >= 4ll * (sm_count() / n_tiles);
+  if (ws) {
+    if (bn == 256) return launch_fwd<256, 1, false, true>(a, b, p, st);
+    if (bn == 128) return launch_fwd<128, 1, false, true>(a, b, p, st);
+    return launch_fwd<64, 1, false, true>(a, b, p, st);
+  }
+  if (bn == 256) return launch_fwd<256, 1, false, false>(a, b, p, st);
+  if (bn == 128) return launch_fwd<128, 1, false, false>(a, b, p, st);
+  return launch_fwd<64, 1, false, false>(a, b, p, st);
 }
 
 // Cluster size for a problem: pairs of M tiles share the weight tile (multicast) whenever there are enough tiles.

@@ -244,6 +244,7 @@ class P2PGradReducer:
     def reduce(self):
         """Average gradients across ranks; afterwards every ``param.grad`` views its bucket slot.  Buckets whose
         kernel already went out during the backward pass are only joined."""
+        ops.join_wgrad(self.device)
         armed, self._armed = self._armed, False
         cur = torch.cuda.current_stream(self.device)
         joined = False

@@ -111,6 +111,7 @@ class BaseHarness:
     def _step_body(self, inputs, targets):
         """zero_grad -> autocast forward -> CE -> backward (+ P2P gradient mean under it) -> SGD -> accuracy.
         Everything here is device work on the current stream (capturable: no host sync, no pointer changes)."""
+        from .. import ops
         store = self._grad_store()
         store.zero()                       # one memset of the persistent gradient storage (param.grad views its slot)
         if self.distributed:
@@ -119,7 +120,13 @@ class BaseHarness:
         with autocast(device_type="cuda", dtype=self.precision, enabled=self.use_amp):
             outputs = self.model(inputs)
             loss = self.criterion(outputs, targets)
-        loss.backward()
+        side_wgrad = bool(getattr(self.cfg.experiment_params, "wgrad_side_stream", True))
+        ops.set_wgrad_side_stream(side_wgrad)     # weight gradients run on a side stream beside the dgrad chain ...
+        try:
+            loss.backward()
+        finally:
+            ops.set_wgrad_side_stream(False)
+            ops.join_wgrad(self.device)           # ... and are joined before anything reads param.grad
         if self.distributed:
             self.reducer.reduce()          # joins the side stream; leftover buckets go out here
         self.optimizer.step()

@@ -84,6 +84,42 @@ def grad_ready(*slots):
                 _grad_ready_hook(s.data_ptr())
 
 
+# ---- weight gradients on a side stream -------------------------------------------------------------------------------
+# dW of a layer is needed by nobody before the gradient exchange / the optimizer, while dX is the critical path of the
+# backward pass.  With WGRAD_SIDE_STREAM the wgrad GEMM + finalize of every masked layer go to one side stream behind an
+# event of the compute stream; at small per-GPU batches (the 8-GPU operating point: 64 images) the kernels are one or two
+# waves each and the two chains fill each other's gaps.  The operands are kept alive until ``join_wgrad`` (the caching
+# allocator would otherwise hand their blocks to the next main-stream allocation while the side stream still reads them).
+# Off unless a caller that also joins turns it on (BaseHarness._step_body does, around its backward pass).
+WGRAD_SIDE_STREAM = False
+_wgrad_streams = {}
+_wgrad_keepalive = []
+
+
+def set_wgrad_side_stream(on: bool):
+    global WGRAD_SIDE_STREAM
+    WGRAD_SIDE_STREAM = bool(on)
+
+
+def _wgrad_stream(device):
+    st = _wgrad_streams.get(device.index)
+    if st is None:
+        st = _wgrad_streams[device.index] = torch.cuda.Stream(device)
+    return st
+
+
+def join_wgrad(device=None):
+    """Make the current stream wait for every weight gradient launched on the side stream since the last join, and let go
+    of the operands kept alive for them.  Call after ``loss.backward()``, before anything consumes ``param.grad``."""
+    if not _wgrad_keepalive:
+        return
+    devs = {t[0].device for t in _wgrad_keepalive}
+    for d in devs:
+        if device is None or d == device:
+            torch.cuda.current_stream(d).wait_stream(_wgrad_stream(d))
+    _wgrad_keepalive.clear()
+
+
 def _require_cuda(*tensors):
     for t in tensors:
         if t is not None and not t.is_cuda:
@@ -702,13 +738,25 @@ class MaskedConv2dFn(torch.autograd.Function):
                     ws_, bs_ = ctx.grad_slots if ctx.grad_slots is not None else (None, None)
                     direct_w = ws_ is not None and ws_.is_contiguous() and ws_.numel() == m32.numel()
                     direct_b = need_db and bs_ is not None
-                    dw, db = conv_wgrad(desc, xn, dyn, m32, cin, need_db, dw_out=ws_ if direct_w else None,
-                                        db_out=bs_ if direct_b else None)
-                    if direct_w:
-                        dw = None
-                    if direct_b:
-                        db = None
-                    grad_ready(ws_ if direct_w else None, bs_ if direct_b else None)
+                    if WGRAD_SIDE_STREAM and direct_w and (direct_b or not need_db):
+                        # nothing of this result flows back through autograd: run it beside the dgrad chain
+                        dev = xn.device
+                        cur, side = torch.cuda.current_stream(dev), _wgrad_stream(dev)
+                        ev = torch.cuda.Event(); ev.record(cur)
+                        side.wait_event(ev)
+                        with torch.cuda.stream(side):
+                            conv_wgrad(desc, xn, dyn, m32, cin, need_db, dw_out=ws_, db_out=bs_ if direct_b else None)
+                            grad_ready(ws_, bs_ if direct_b else None)
+                        _wgrad_keepalive.append((xn, dyn, m32))
+                        dw = db = None
+                    else:
+                        dw, db = conv_wgrad(desc, xn, dyn, m32, cin, need_db, dw_out=ws_ if direct_w else None,
+                                            db_out=bs_ if direct_b else None)
+                        if direct_w:
+                            dw = None
+                        if direct_b:
+                            db = None
+                        grad_ready(ws_ if direct_w else None, bs_ if direct_b else None)
         if need_db and db is None:
             db = dy.float().sum(dim=(0, 2, 3))
         if dskip is not None and dx is None and need_dx is False:
