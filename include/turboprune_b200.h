@@ -150,6 +150,23 @@ int tp_im2col_stem(const void* src, int src_dtype, int64_t sn, int64_t sc, int64
                    int n, int c, int h, int w, int r, int s, int cg, int stride_h, int stride_w, int pad_h, int pad_w,
                    int p, int q, void* xcol, int kp, void* stream);
 
+/* ---- data path either side of the model --------------------------
+ * tp_cifar_augment: random translate (batch_crop of the reflect-padded images, utils/dataset.py:43-69), per-image
+ * left-right flip (:38-40) and cutout (:72-98) of CifarLoader.__iter__ (:192-226) as ONE gather pass:
+ *   out[n][c][y][x] = inside_cut(n,y,x) ? 0 : src[n][c][y + r + shifts[n][0]][xf + r + shifts[n][1]],  xf = flip[n] ? w-1-x : x
+ * src fp32 [n][c][h+2r][w+2r] contiguous, out fp32 [n][c][h][w]; shifts int64 [n][2] in [-r, r] (NULL: no translate, then
+ * r must describe the padding actually present, usually 0), flip uint8 [n] (NULL: none), cut_y / cut_x int64 [n] top-left
+ * corners of a cut_size square (both NULL: none).  The draws are the caller's (torch RNG, reference order). */
+int tp_cifar_augment(const void* src, void* out, const int64_t* shifts, const uint8_t* flip,
+                     const int64_t* cut_y, const int64_t* cut_x, int cut_size,
+                     int n, int c, int h, int w, int r, void* stream);
+/* Synthetic batches (stand-in for the FFCV / CIFAR loaders, which need data sets): Philox4x32-10, counter
+ * (counter_offset + i/4, 0, 0, 0), key = seed; element i takes word i%4.  tp_synth_normal writes N(0,1) fp32 (Box-Muller
+ * on 24-bit uniforms; raw_words != 0: the 32-bit words themselves, for bit-exact pinning of the stream);
+ * tp_synth_labels writes int64 labels floor(word * num_classes / 2^32). */
+int tp_synth_normal(void* out, int64_t numel, uint64_t seed, uint64_t counter_offset, int raw_words, void* stream);
+int tp_synth_labels(void* out, int64_t numel, int num_classes, uint64_t seed, uint64_t counter_offset, void* stream);
+
 /* ---- masked implicit-GEMM convolution / linear on tcgen05 tensor cores -----------------
  * Replaces F.conv2d / F.linear / F.conv1d(k=1) on the masked weight
  * (utils/mask_layers.py:26-34, :70, :110-118) and their autograd backward.

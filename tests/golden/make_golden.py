@@ -269,7 +269,33 @@ def gen_sgd():
     np.savez_compressed(os.path.join(HERE, "sgd_small.npz"), **out)
 
 
+def gen_aug():
+    """aug_small.npz: the reference's batch_crop / batch_flip_lr / batch_cutout (utils/dataset.py:38-98) run on CPU; the
+    draws each call made are re-drawn from the same seed and stored next to its output."""
+    ds = refshim.load_reference_dataset()
+    g = torch.Generator().manual_seed(11)
+    imgs = torch.randn(7, 3, 12, 12, generator=g)
+    padded = torch.nn.functional.pad(imgs, (2,) * 4, "reflect")                  # translate = 2 -> 16 x 16, r <= 2 branch
+    padded4 = torch.nn.functional.pad(imgs, (4,) * 4, "reflect")                 # translate = 4 -> the two-pass branch
+    out = {"imgs": imgs.numpy(), "padded": padded.numpy(), "padded4": padded4.numpy()}
+    for tag, src, r in (("crop2", padded, 2), ("crop4", padded4, 4)):
+        torch.manual_seed(21); out[f"{tag}.out"] = ds.batch_crop(src, 12).numpy()
+        torch.manual_seed(21); out[f"{tag}.shifts"] = torch.randint(-r, r + 1, size=(7, 2)).numpy()
+    torch.manual_seed(22); out["flip.out"] = ds.batch_flip_lr(imgs).numpy()
+    torch.manual_seed(22); out["flip.mask"] = (torch.rand(7) < 0.5).numpy()
+    torch.manual_seed(23); out["cut.out"] = ds.batch_cutout(imgs, 5).numpy()
+    torch.manual_seed(23); out["cut.y"] = torch.randint(0, 12 - 5 + 1, size=(7,)).numpy(); out["cut.x"] = torch.randint(0, 12 - 5 + 1, size=(7,)).numpy()
+    # the epoch pipeline of CifarLoader.__iter__ (:204-221): translate -> flip -> cutout
+    torch.manual_seed(24)
+    x = ds.batch_crop(padded4, 12); x = ds.batch_flip_lr(x); x = ds.batch_cutout(x, 3)
+    out["epoch.out"] = x.numpy()
+    torch.manual_seed(24)
+    out["epoch.shifts"] = torch.randint(-4, 5, size=(7, 2)).numpy(); out["epoch.mask"] = (torch.rand(7) < 0.5).numpy()
+    out["epoch.y"] = torch.randint(0, 12 - 3 + 1, size=(7,)).numpy(); out["epoch.x"] = torch.randint(0, 12 - 3 + 1, size=(7,)).numpy()
+    np.savez_compressed(os.path.join(HERE, "aug_small.npz"), **out)
+
+
 if __name__ == "__main__":
-    gen_ops(); gen_prune(); gen_probs_and_hashes(); gen_densities(); gen_sgd()
+    gen_ops(); gen_prune(); gen_probs_and_hashes(); gen_densities(); gen_sgd(); gen_aug()
     for f in sorted(os.listdir(HERE)):
         print(f, os.path.getsize(os.path.join(HERE, f)))

@@ -79,6 +79,29 @@ def load_reference():
     return ml, pu, cm
 
 
+def load_reference_dataset():
+    """The reference's utils/dataset.py (airbench-style GPU augmentation helpers) — needs a webdataset stand-in."""
+    if "dataset" in _loaded:
+        return _loaded["dataset"]
+    if not reference_available():
+        raise FileNotFoundError(REFERENCE_ROOT)
+    _install_stubs()
+    if "webdataset" not in sys.modules:
+        _stub("webdataset")
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "utils" or k.startswith("utils.")}
+    sys.path.insert(0, REFERENCE_ROOT)
+    try:
+        ds = importlib.import_module("utils.dataset")
+    finally:
+        sys.path.remove(REFERENCE_ROOT)
+        for k in list(sys.modules):
+            if k == "utils" or k.startswith("utils."):
+                sys.modules.pop(k)
+        sys.modules.update(saved)
+    _loaded["dataset"] = ds
+    return ds
+
+
 class Cfg(dict):
     """dict with attribute access — enough of a DictConfig for the reference."""
 

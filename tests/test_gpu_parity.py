@@ -908,3 +908,65 @@ def test_weight_stationary_walk_bit_identical(dev, case, monkeypatch):
         y.backward(dy)
         outs[ws] = (y.detach().clone(), xx.grad.detach().clone())
     assert torch.equal(outs["0"][0], outs["1"][0]) and torch.equal(outs["0"][1], outs["1"][1])
+
+
+# ---------------------------------------------------------------- data path --------------------
+def test_cifar_augmentation_kernel_matches_reference_fixture(dev):
+    """tp_cifar_augment with the draws the reference made (fixture written by running utils/dataset.py:38-98): every op
+    alone and the fused translate -> flip -> cutout epoch pass are bit-exact; the public batch_* wrappers (same names,
+    draws made with torch's generator in the reference's order) equal the oracle fed with the re-drawn values."""
+    from oracle import data as D
+    from turboprune_b200.utils import dataset as ds
+    z = np.load(os.path.join(G, "aug_small.npz"))
+    T = lambda k: torch.from_numpy(z[k]).to(dev)
+    imgs, pad2, pad4 = T("imgs"), T("padded"), T("padded4")
+    assert np.array_equal(ds._augment(pad2, (12, 12), 2, shifts=T("crop2.shifts")).cpu().numpy(), z["crop2.out"])
+    assert np.array_equal(ds._augment(pad4, (12, 12), 4, shifts=T("crop4.shifts")).cpu().numpy(), z["crop4.out"])
+    assert np.array_equal(ds._augment(imgs, (12, 12), 0, flip=T("flip.mask")).cpu().numpy(), z["flip.out"])
+    assert np.array_equal(ds._augment(imgs, (12, 12), 0, corner_y=T("cut.y"), corner_x=T("cut.x"), cut_size=5).cpu().numpy(), z["cut.out"])
+    fused = ds._augment(pad4, (12, 12), 4, shifts=T("epoch.shifts"), flip=T("epoch.mask"), corner_y=T("epoch.y"), corner_x=T("epoch.x"), cut_size=3)
+    assert np.array_equal(fused.cpu().numpy(), z["epoch.out"])
+    # public wrappers: same draw order as the reference on the images' device
+    g = torch.Generator().manual_seed(4)
+    big = torch.randn(33, 3, 32, 32, generator=g).to(dev)
+    padb = torch.nn.functional.pad(big, (4,) * 4, "reflect")
+    torch.manual_seed(31); a = ds.batch_crop(padb, 32)
+    torch.manual_seed(31); sh = torch.randint(-4, 5, size=(33, 2), device=dev)
+    assert np.array_equal(a.cpu().numpy(), D.batch_crop(padb.cpu().numpy(), 32, sh.cpu().numpy()))
+    torch.manual_seed(32); b = ds.batch_flip_lr(big)
+    torch.manual_seed(32); fm = torch.rand(33, device=dev) < 0.5
+    assert np.array_equal(b.cpu().numpy(), D.batch_flip_lr(big.cpu().numpy(), fm.cpu().numpy()))
+    torch.manual_seed(33); c = ds.batch_cutout(big, 8)
+    torch.manual_seed(33); cy = torch.randint(0, 25, size=(33,), device=dev); cx = torch.randint(0, 25, size=(33,), device=dev)
+    assert np.array_equal(c.cpu().numpy(), D.batch_cutout(big.cpu().numpy(), 8, cy.cpu().numpy(), cx.cpu().numpy()))
+    torch.manual_seed(34); e = ds.augment_epoch(padb, 32, flip=True, cutout=6)
+    torch.manual_seed(34)
+    sh = torch.randint(-4, 5, size=(33, 2), device=dev); fm = torch.rand(33, device=dev) < 0.5
+    cy = torch.randint(0, 27, size=(33,), device=dev); cx = torch.randint(0, 27, size=(33,), device=dev)
+    ref = D.augment(padb.cpu().numpy(), 32, sh.cpu().numpy(), fm.cpu().numpy(), 6, cy.cpu().numpy(), cx.cpu().numpy())
+    assert np.array_equal(e.cpu().numpy(), ref)
+
+
+def test_synthetic_generator_matches_oracle(dev):
+    """Philox4x32-10 words bit-exact against the oracle (pinned by Random123's known-answer vector), Box-Muller normals to
+    float rounding, labels exact; the loader draws a fresh, reproducible batch every step."""
+    from oracle import data as D
+    from turboprune_b200.utils import dataset as ds
+    n = 100_003
+    raw = torch.empty(n, dtype=torch.float32, device=dev)
+    ds.synth_normal_(raw, seed=12345678901, counter_offset=77, raw_words=True)
+    assert np.array_equal(raw.cpu().numpy().view(np.uint32), D.synth_words(n, 12345678901, 77))
+    x = torch.empty(n, dtype=torch.float32, device=dev)
+    ds.synth_normal_(x, seed=9, counter_offset=5)
+    ref = D.synth_normal(n, 9, 5)
+    assert float(np.abs(x.cpu().numpy() - ref).max()) < 2e-5
+    t = torch.empty(4099, dtype=torch.int64, device=dev)
+    ds.synth_labels_(t, 1000, seed=9, counter_offset=3)
+    assert np.array_equal(t.cpu().numpy(), D.synth_labels(4099, 1000, 9, 3))
+    a = ds.SyntheticLoader(8, 3, (3, 32, 32), 10, dev, seed=5, fresh=True)
+    b = ds.SyntheticLoader(8, 3, (3, 32, 32), 10, dev, seed=5, fresh=True)
+    xa = [x.clone() for x, _ in a]; xb = [x.clone() for x, _ in b]
+    assert all(torch.equal(p, q) for p, q in zip(xa, xb)) and not torch.equal(xa[0], xa[1])
+    cl = ds.SyntheticLoader(4, 1, (3, 16, 16), 10, dev, seed=1, channels_last=True, fresh=True)
+    xc, tc = next(iter(cl))
+    assert xc.shape == (4, 3, 16, 16) and xc.is_contiguous(memory_format=torch.channels_last) and tc.dtype == torch.int64

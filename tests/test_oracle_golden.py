@@ -175,3 +175,38 @@ def test_oracle_matches_live_reference_when_present():
         hh.update(np.ascontiguousarray(a).tobytes())
     assert hh.hexdigest() == h["levels"][0]["masks_sha256"]
     assert int(np.float32(thr).view(np.uint32)) == h["levels"][0]["thr_bits"]
+
+
+# ---------------------------------------------------------------- data path --------------------
+def test_augmentation_oracle_matches_reference_fixture_and_live():
+    """oracle.data.batch_crop / batch_flip_lr / batch_cutout / augment against outputs of the reference's own functions
+    (utils/dataset.py:38-98, fixture written by make_golden.py) and, when /root/reference is mounted, against a live run."""
+    from oracle import data as D
+    z = np.load(os.path.join(G, "aug_small.npz"))
+    assert np.array_equal(D.batch_crop(z["padded"], 12, z["crop2.shifts"]), z["crop2.out"])
+    assert np.array_equal(D.batch_crop(z["padded4"], 12, z["crop4.shifts"]), z["crop4.out"])
+    assert np.array_equal(D.batch_flip_lr(z["imgs"], z["flip.mask"]), z["flip.out"])
+    assert np.array_equal(D.batch_cutout(z["imgs"], 5, z["cut.y"], z["cut.x"]), z["cut.out"])
+    assert np.array_equal(D.augment(z["padded4"], 12, z["epoch.shifts"], z["epoch.mask"], 3, z["epoch.y"], z["epoch.x"]), z["epoch.out"])
+    import refshim
+    if refshim.reference_available():
+        ds = refshim.load_reference_dataset()
+        g = torch.Generator().manual_seed(3)
+        imgs = torch.randn(5, 3, 10, 10, generator=g)
+        pad = torch.nn.functional.pad(imgs, (3,) * 4, "reflect")
+        torch.manual_seed(8); ref = ds.batch_crop(pad, 10)
+        torch.manual_seed(8); sh = torch.randint(-3, 4, size=(5, 2))
+        assert np.array_equal(D.batch_crop(pad.numpy(), 10, sh.numpy()), ref.numpy())
+
+
+def test_philox_known_answer_and_generator_statistics():
+    """Philox4x32-10 pinned by Random123's known-answer vector (counter 0, key 0); the derived normals / labels behave."""
+    from oracle import data as D
+    w = D.philox4x32_10(np.array([0], dtype=np.uint64), 0)[0]
+    assert [int(x) for x in w] == [0x6627E8D5, 0xE169C58D, 0xBC57AC4C, 0x9B00DBD8]
+    x = D.synth_normal(200_000, seed=7)
+    assert abs(float(x.mean())) < 0.01 and abs(float(x.std()) - 1.0) < 0.01 and np.isfinite(x).all()
+    t = D.synth_labels(100_000, 10, seed=7)
+    assert t.min() == 0 and t.max() == 9 and abs(np.bincount(t, minlength=10) / 1e5 - 0.1).max() < 0.01
+    assert not np.array_equal(D.synth_words(64, 7, 0), D.synth_words(64, 7, 16))       # counter offset moves the stream
+    assert np.array_equal(D.synth_words(64, 7, 16)[:32], D.synth_words(128, 7, 0)[64:96])
