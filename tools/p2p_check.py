@@ -3,7 +3,7 @@
 
 1. tp_p2p_allreduce_mask (one-shot, two-shot) and tp_p2p_allreduce_nvls (when the symmetric allocation has a multicast
    address) with a mask: against the oracle's fixed rank-order mean (bit-exact; NVLS: bit-exact for W = 2, within
-   2 ulp of the result's magnitude for W > 2 because the switch fixes the summation order) and replica bit-identity.
+   4 eps of the mean summand magnitude for W > 2 because the switch fixes the summation order) and replica bit-identity.
 2. The overlapped reducer inside a real backward pass (ResNet-18, per-rank data): gradients bit-identical to the
    non-overlapped launch order; rank-0 mask broadcast after a rank-dependent pruning step.
 3. Timing of a ResNet-50-sized bucket (102 MB) per algorithm against NCCL all_reduce (skipped with --no-timing).
@@ -43,7 +43,9 @@ def check_kernels(rank, world, dev):
                                               masks[id(p)].cpu().numpy() if id(p) in masks else None)
                     got = p.grad.cpu().numpy()
                     if algo == "nvls" and world > 2:
-                        good = bool(np.all(np.abs(got - ref) <= 2 * np.spacing(np.abs(ref).astype(np.float32)) * world))
+                        # the switch fixes the order of the W-term sum: rounding differs by a few ulp of the partial sums
+                        mag = sum(np.abs(all_g[r][i].numpy()) for r in range(world)) / world
+                        good = bool(np.all(np.abs(got - ref) <= 4 * np.finfo(np.float32).eps * mag + 1e-30))
                     else:
                         good = np.array_equal(got, ref)
                     if not good:
