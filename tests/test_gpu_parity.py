@@ -970,3 +970,30 @@ def test_synthetic_generator_matches_oracle(dev):
     cl = ds.SyntheticLoader(4, 1, (3, 16, 16), 10, dev, seed=1, channels_last=True, fresh=True)
     xc, tc = next(iter(cl))
     assert xc.shape == (4, 3, 16, 16) and xc.is_contiguous(memory_format=torch.channels_last) and tc.dtype == torch.int64
+
+
+@pytest.mark.parametrize("case", [(3, 3, 224, 224, 7, 2, 3, torch.float32, True), (5, 3, 32, 32, 3, 1, 1, torch.float32, False),
+                                  (2, 1, 37, 29, 5, 2, 2, torch.float32, False), (2, 4, 20, 300, 3, 1, 1, torch.bfloat16, True),
+                                  (1, 8, 9, 9, 3, 2, 0, torch.float32, False)])
+def test_stem_im2col_strip_kernel_equals_cell_kernel(dev, case, monkeypatch):
+    """The strip kernel (input rows staged once in shared memory, division-free gathers) writes the same bf16 matrix as the
+    per-cell kernel, bit for bit: RGB 7x7/2 ImageNet stem, CIFAR stem, odd sizes, output rows wider than one strip, bf16 and
+    channels_last / NCHW-strided inputs."""
+    from turboprune_b200 import ops
+    n, c, h, w, k, s_, p_, dt, cl = case
+    g = torch.Generator(device=dev).manual_seed(sum(case[:7]))
+    x = torch.randn(n, c, h, w, device=dev, generator=g).to(dt)
+    if cl:
+        x = x.contiguous(memory_format=torch.channels_last)
+    desc = ops.make_desc(n, h, w, c, 16, k, k, (s_, s_), (p_, p_))
+    cg, kp = ops.stem_geometry(c, k, k)
+    outs = []
+    for mode in ("cell", "rows"):
+        monkeypatch.setenv("TP_STEM_IM2COL", mode)
+        outs.append(ops.im2col_stem(x, desc, kp, cg))
+    assert torch.equal(outs[0].view(torch.int16), outs[1].view(torch.int16))
+    # and against a direct unfold of the bf16-rounded input (column = tap * cg + channel)
+    cols = torch.nn.functional.unfold(x.float().to(torch.bfloat16).float().contiguous(), k, padding=p_, stride=s_)   # [n, c*k*k, L]
+    cols = cols.view(n, c, k * k, -1).permute(0, 3, 2, 1).reshape(n * desc.p * desc.q, k * k * c)
+    assert torch.equal(outs[1][:, :k * k * c].float(), cols)
+    assert float(outs[1][:, k * k * c:].abs().max()) == 0.0 if kp > k * k * c else True
