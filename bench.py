@@ -374,10 +374,13 @@ def main():
     timer = ops.KernelTimer()
     KT = min(K, 5)
     cfg.experiment_params["cuda_graph"] = False
+    side_wgrad = cfg.experiment_params.get("wgrad_side_stream", True)
+    cfg.experiment_params["wgrad_side_stream"] = False      # per-kernel durations: every GEMM alone on the device, on ONE stream
     ops.set_timer(timer)
     ms_eager = timed(KT, lambda i: step(next(batches)))
     ops.set_timer(None)
     cfg.experiment_params["cuda_graph"] = use_graph
+    cfg.experiment_params["wgrad_side_stream"] = side_wgrad
     tot = timer.totals()
     gemm_ms = sum(v[0] for v in tot.values()) * (K / KT)
     pk = peaks()
