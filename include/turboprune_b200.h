@@ -198,6 +198,15 @@ int tp_conv_fprop_stats(const tp_conv_desc* d, const void* x, const void* wf, co
  * epilogue instead of by a separate elementwise add (autograd's grad accumulation at a ResNet block input). */
 int tp_conv_dgrad(const tp_conv_desc* d, const void* dy, const void* wd, const void* kmask_d, const void* addend,
                   void* dx, void* ws, size_t ws_bytes, void* stream);
+/* The same dgrad when dx is the gradient of a BatchNorm+ReLU output z = relu(bn(y)) without residual (the bn1 / bn2 of a
+ * torchvision block feeding conv2 / conv3, custom_models.py:184): the epilogue writes g = dx * [z > 0] (gate recomputed
+ * from y with the forward's own expression) and, per group of 32 pixels and channel, sum(g) and sum(g * xhat) —
+ * partial holds tp_conv_dgrad_partial_rows(d) rows of [2][cin] fp32.  tp_bn_backward_ext then needs no reduction pass over
+ * the activation.  Stride-1 convolutions only; bn_weight / bn_bias may be NULL (affine = False). */
+size_t tp_conv_dgrad_partial_rows(const tp_conv_desc* d);
+int tp_conv_dgrad_bnrelu(const tp_conv_desc* d, const void* dy, const void* wd, const void* kmask_d,
+                         const void* bn_y, const void* bn_weight, const void* bn_bias, const void* bn_mean, const void* bn_invstd,
+                         void* g, void* partial, void* stream);
 /* dw[cout][cin_real][r][s] (fp32, OIHW) = mask * conv_wgrad(x, dy); db[cout] = sum dy (optional) */
 int tp_conv_wgrad(const tp_conv_desc* d, const void* x, const void* dy, const void* mask,
                   int cin_real, void* dw, void* db, void* ws, size_t ws_bytes, void* stream);
@@ -236,6 +245,11 @@ int tp_bn_backward(const void* dz, const void* z, const void* y, int64_t m, int 
 /* Max pooling on NHWC bf16 (square window k, stride, symmetric padding with -inf, NaN propagates like
  * torch): forward writes y [n,p,q,c] and the uint8 arg-max window index idx [n,p,q,c]; backward gathers
  * dx [n,h,w,c] from dy through idx (deterministic, no atomics).  c % 8 == 0. */
+/* tp_bn_backward for a gradient that already is g = dz * [z > 0] with its partial sums (tp_conv_dgrad_bnrelu):
+ * fold, coefficients, apply pass dy = k0 g + k1 y + k2; dweight / dbias as in tp_bn_backward. */
+int tp_bn_backward_ext(const void* g, const void* y, int64_t M, int C, const void* weight, const void* bias,
+                       const void* save_mean, const void* save_invstd, const void* partial_rows, int64_t n_rows,
+                       void* dy, void* dweight, void* dbias, void* ws, size_t ws_bytes, void* stream);
 int tp_maxpool_forward(const void* x, void* y, void* idx, int n, int h, int w, int c, int k, int stride, int pad,
                        int p, int q, void* stream);
 int tp_maxpool_backward(const void* dy, const void* idx, void* dx, int n, int h, int w, int c, int k, int stride, int pad,

@@ -997,3 +997,58 @@ def test_stem_im2col_strip_kernel_equals_cell_kernel(dev, case, monkeypatch):
     cols = cols.view(n, c, k * k, -1).permute(0, 3, 2, 1).reshape(n * desc.p * desc.q, k * k * c)
     assert torch.equal(outs[1][:, :k * k * c].float(), cols)
     assert float(outs[1][:, k * k * c:].abs().max()) == 0.0 if kp > k * k * c else True
+
+
+@pytest.mark.parametrize("case", [(6, 64, 128, 3, 18), (4, 128, 256, 1, 14), (3, 64, 64, 3, 23)])
+def test_bn_backward_reduction_in_dgrad_epilogue(dev, case):
+    """conv_a -> BatchNorm+ReLU -> conv_b: with the fusion conv_b's dgrad writes g = dz * [z > 0] and the partial sums
+    (sum g, sum g*xhat) so that the BatchNorm backward runs no reduction pass; against the unfused path: identical gate
+    (exactly the same zeros), dgamma / dbeta to fp32 summation-order accuracy, input and weight gradients to bf16 accuracy;
+    a BatchNorm whose output has two consumers falls back transparently."""
+    import copy
+    from turboprune_b200 import fused_norm as fn, ops
+    from turboprune_b200.utils import mask_layers as ml
+    b, c1, c2, k, hw = case
+    g = torch.Generator(device=dev).manual_seed(sum(case))
+    conv_a = ml.ConvMask(in_channels=64, out_channels=c1, kernel_size=3, padding=1, bias=False).to(dev)
+    bn = fn.BatchNorm2dB200(c1).to(dev).train()
+    conv_b = ml.ConvMask(in_channels=c1, out_channels=c2, kernel_size=k, padding=k // 2, bias=False).to(dev)
+    with torch.no_grad():
+        conv_a.mask.copy_((torch.rand(conv_a.weight.shape, device=dev, generator=g) < 0.5).float())
+        conv_b.mask.copy_((torch.rand(conv_b.weight.shape, device=dev, generator=g) < 0.5).float())
+        bn.weight.copy_(torch.rand(c1, device=dev, generator=g) + 0.5); bn.bias.copy_(torch.randn(c1, device=dev, generator=g) * 0.3)
+    x = torch.randn(b, 64, hw, hw, device=dev, generator=g).to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    res = []
+    for fused in (False, True):
+        ops.set_bn_bwd_fusion(fused)
+        try:
+            ca, bb, cb = copy.deepcopy(conv_a), copy.deepcopy(bn), copy.deepcopy(conv_b)
+            xx = x.clone().requires_grad_(True)
+            z, _ = fn._conv_bn(ca, bb, xx, relu=True)
+            assert (getattr(z, "_tp_bn_src", None) is not None) == fused
+            out = cb(z)
+            gz = torch.Generator(device=dev).manual_seed(5)
+            out.backward(torch.randn(out.shape, device=dev, generator=gz).to(out.dtype).contiguous(memory_format=torch.channels_last))
+            assert not fn._PARTIALS                                   # the offer was consumed by the BatchNorm's backward
+            res.append((xx.grad.float(), ca.weight.grad.clone(), bb.weight.grad.clone(), bb.bias.grad.clone(), cb.weight.grad.clone()))
+        finally:
+            ops.set_bn_bwd_fusion(True)
+    u, f = res
+    assert _rel(f[2], u[2]) < 1e-4 and _rel(f[3], u[3]) < 1e-4        # dgamma, dbeta: same terms, different summation order
+    assert _rel(f[4], u[4]) == 0.0                                     # conv_b's wgrad does not depend on the fusion
+    assert _rel(f[0], u[0]) < 2e-2 and _rel(f[1], u[1]) < 2e-2         # through bf16 dy: a last-bit flip of the coefficients at most
+    # two consumers of the BatchNorm output: autograd sums the gradients, the hint cannot match, results stay right
+    ca, bb, cb = copy.deepcopy(conv_a), copy.deepcopy(bn), copy.deepcopy(conv_b)
+    xx = x.clone().requires_grad_(True)
+    z, _ = fn._conv_bn(ca, bb, xx, relu=True)
+    (cb(z).float().sum() + (z.float() * 0.5).sum()).backward()
+    fn.drop_partials()
+    ops.set_bn_bwd_fusion(False)
+    try:
+        ca2, bb2, cb2 = copy.deepcopy(conv_a), copy.deepcopy(bn), copy.deepcopy(conv_b)
+        x2 = x.clone().requires_grad_(True)
+        z2, _ = fn._conv_bn(ca2, bb2, x2, relu=True)
+        (cb2(z2).float().sum() + (z2.float() * 0.5).sum()).backward()
+    finally:
+        ops.set_bn_bwd_fusion(True)
+    assert _rel(bb.weight.grad, bb2.weight.grad) < 1e-4 and _rel(xx.grad, x2.grad) < 2e-2

@@ -538,4 +538,34 @@ int tp_bn_backward(const void* dz, const void* z, const void* y, int64_t M, int 
   return TP_OK;
 }
 
+// BatchNorm(+ReLU) backward whose reduction was already done by the dgrad that produced its incoming gradient
+// (tp_conv_dgrad_bnrelu): g = dz * [z > 0] is given together with per-32-row partial sums (sum g, sum g * xhat); what is
+// left is the fold of the partials, the coefficients and the apply pass dy = k0 g + k1 y + k2.
+int tp_bn_backward_ext(const void* g, const void* y, int64_t M, int C, const void* weight, const void* bias,
+                       const void* save_mean, const void* save_invstd, const void* partial_rows, int64_t n_rows,
+                       void* dy, void* dweight, void* dbias, void* ws, size_t ws_bytes, void* stream) {
+  if (!g || !y || !dy || !save_mean || !save_invstd || !partial_rows || n_rows <= 0 || M <= 0 || C <= 0 || C % 8 != 0 || !ws) return TP_ERR_INVALID;
+  if (ws_bytes < tp_bn_workspace_bytes(M, C)) return TP_ERR_WORKSPACE;
+  int rc = bind_device_of(y); if (rc) return rc;
+  cudaStream_t st = (cudaStream_t)stream;
+  BnGeom gm = bn_geom(M, C);
+  float* partial = (float*)ws;
+  float* coef = partial + (size_t)gm.grid_x * 2 * C;
+  const float* fold_src = (const float*)partial_rows;
+  long long fold_rows = n_rows;
+  const long long groups = (n_rows + 1023) / 1024;
+  if (groups > 1) {
+    if (groups > gm.grid_x) return TP_ERR_WORKSPACE;
+    k_bn_fold_ext<<<dim3((C + kFinC - 1) / kFinC, (unsigned)groups), dim3(kFinC, kFinP), 0, st>>>((const float*)partial_rows, n_rows, C, partial);
+    fold_src = partial; fold_rows = groups;
+  }
+  k_bn_finalize_bwd<<<(C + kFinC - 1) / kFinC, dim3(kFinC, kFinP), 0, st>>>(fold_src, (int)fold_rows, M, C, (const float*)weight, (const float*)bias,
+                                                                          (const float*)save_mean, (const float*)save_invstd,
+                                                                          (float*)dweight, (float*)dbias, coef);
+  dim3 block(gm.tx, gm.ty), grid(gm.grid_x, gm.ctiles);
+  k_bn_bwd_apply<0, false><<<grid, block, 0, st>>>((const __nv_bfloat16*)g, nullptr, (const __nv_bfloat16*)y, M, C, coef, (__nv_bfloat16*)dy, nullptr);
+  TP_LAUNCH_CHECK();
+  return TP_OK;
+}
+
 }  // extern "C"

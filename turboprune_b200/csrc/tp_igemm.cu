@@ -75,6 +75,10 @@ struct FwdParams {
   float* stats;                  // optional (linear output only): per-channel sum / sum of squares of the bf16 outputs
                                  // of every 32-row group, [ceil(M/128)*4][2][N] fp32 — BatchNorm statistics without
                                  // another pass over the activation
+  // BNB instantiation (dgrad whose output is the gradient of a BatchNorm+ReLU output, no residual): the epilogue turns dz into
+  // g = dz * [y*scale + shift > 0] (the forward's own ReLU decision) and accumulates the BatchNorm backward sums of g
+  const __nv_bfloat16* bn_y;     // the BatchNorm INPUT y (same layout as out)
+  const float* bn_weight; const float* bn_bias; const float* bn_mean; const float* bn_invstd;   // per channel (weight / bias may be NULL)
   const uint32_t* kmask;         // optional K-block occupancy of the weight operand: [ceil(N/64)][kmask_words] bitmasks over
   int kmask_words;               // 64-column K blocks (tp_stage_weights); empty blocks are neither loaded nor multiplied
   TapEntry taps[kMaxTaps];
@@ -158,11 +162,18 @@ __device__ __forceinline__ void decode_tile(const FwdParams& p, int tile, int n_
 // activation tiles.  The dense walk re-loaded BLOCK_N x 64 weights with every K block of every tile: for the 1x1 layers
 // that was 2/3 of the L2 -> SM operand traffic (128 of 192 KB per 128 x 256 x 256 tile) and it — not HBM, not the tensor
 // pipe — paced them (profiles/r01_notes.md: layer3 1x1 at 3.35 us per tile against 1.1 us of MMA and 1.9 us of HBM time).
-template <int BLOCK_N, int CL, bool MULTI, bool WS>
+//
+// BNB = true (single class, linear output): the BatchNorm backward reduction of the layer that FEEDS this convolution is
+// done here, in the dgrad epilogue, instead of by k_bn_bwd_reduce (one read of dz and one of y per such layer less, one
+// launch less): after the bf16 gradient sub-tile has been staged, each lane re-reads it row-coalesced together with the
+// matching y values, applies the ReLU gate, stores g and adds sum(g), sum(g * xhat) of its 8 channels x 8 rows; rows are
+// then combined by the same fixed-order xor tree as the forward statistics.  Output: g, and [32-row group][2][N] partials.
+template <int BLOCK_N, int CL, bool MULTI, bool WS, bool BNB>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorMap tmB,
             const __grid_constant__ FwdParams p) {
   static_assert(!WS || (CL == 1 && !MULTI), "weight-stationary walk: single CTA, single class");
+  static_assert(!BNB || (CL == 1 && !MULTI && !WS), "BatchNorm-backward epilogue: single CTA, single class, default walk");
   constexpr int kABytes = kBlockM * kBlockK * 2;           // 16 KB
   constexpr int kBRows = BLOCK_N / CL;                     // weight rows THIS CTA loads
   constexpr int kBBytes = kBRows * kBlockK * 2;
@@ -517,6 +528,69 @@ k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorM
           uint4 o[8];
 #pragma unroll
           for (int i = 0; i < 8; ++i) o[i] = lds128(((i & 1) ? rd_odd : rd_even) + (uint32_t)((i >> 1) * 1024));
+          if (BNB) {
+            // gate + BatchNorm backward sums on the row-coalesced view: this lane owns channels n0 + c16*8 .. +8 of rows r_in + 4i
+            uint4 yv[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              yv[i] = make_uint4(0u, 0u, 0u, 0u);
+              if (i * 4 + r_in < rows_left && col_ok) yv[i] = *reinterpret_cast<const uint4*>(p.bn_y + row_off(i) + n0);
+            }
+            float sc[8], sf[8], is_[8], nm[8], s1[8], s2[8];
+            if (col_ok) {
+              const int cb = n0 + c16 * 8;
+#pragma unroll
+              for (int q = 0; q < 8; q += 4) {
+                const float4 one4 = make_float4(1.f, 1.f, 1.f, 1.f), zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 a4 = p.bn_weight ? *reinterpret_cast<const float4*>(p.bn_weight + cb + q) : one4;
+                const float4 b4 = p.bn_bias ? *reinterpret_cast<const float4*>(p.bn_bias + cb + q) : zero4;
+                const float4 m4 = *reinterpret_cast<const float4*>(p.bn_mean + cb + q), i4 = *reinterpret_cast<const float4*>(p.bn_invstd + cb + q);
+                is_[q] = i4.x; is_[q + 1] = i4.y; is_[q + 2] = i4.z; is_[q + 3] = i4.w;
+                nm[q] = m4.x; nm[q + 1] = m4.y; nm[q + 2] = m4.z; nm[q + 3] = m4.w;
+                // scale / shift exactly as k_bn_finalize_stats computed them for the forward apply pass
+                sc[q] = a4.x * i4.x; sc[q + 1] = a4.y * i4.y; sc[q + 2] = a4.z * i4.z; sc[q + 3] = a4.w * i4.w;
+                sf[q] = fmaf(-m4.x, sc[q], b4.x); sf[q + 1] = fmaf(-m4.y, sc[q + 1], b4.y);
+                sf[q + 2] = fmaf(-m4.z, sc[q + 2], b4.z); sf[q + 3] = fmaf(-m4.w, sc[q + 3], b4.w);
+              }
+            } else {
+#pragma unroll
+              for (int q = 0; q < 8; ++q) { sc[q] = 0.f; sf[q] = 0.f; is_[q] = 0.f; nm[q] = 0.f; }
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { s1[q] = 0.f; s2[q] = 0.f; }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              if (i * 4 + r_in < rows_left) {
+                __nv_bfloat162* gh = reinterpret_cast<__nv_bfloat162*>(&o[i]);
+                const __nv_bfloat162* yh = reinterpret_cast<const __nv_bfloat162*>(&yv[i]);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  float2 d2 = __bfloat1622float2(gh[q]);
+                  const float2 y2 = __bfloat1622float2(yh[q]);
+                  // the forward wrote z = max(fma(y, scale, shift), 0): same expression, same operands -> same decision
+                  if (!(fmaf(y2.x, sc[2 * q], sf[2 * q]) > 0.f)) d2.x = 0.f;
+                  if (!(fmaf(y2.y, sc[2 * q + 1], sf[2 * q + 1]) > 0.f)) d2.y = 0.f;
+                  gh[q] = __floats2bfloat162_rn(d2.x, d2.y);                    // exact: d2 is a bf16 value or zero
+                  s1[2 * q] += d2.x;     s2[2 * q] = fmaf(d2.x, (y2.x - nm[2 * q]) * is_[2 * q], s2[2 * q]);
+                  s1[2 * q + 1] += d2.y; s2[2 * q + 1] = fmaf(d2.y, (y2.y - nm[2 * q + 1]) * is_[2 * q + 1], s2[2 * q + 1]);
+                }
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              if (i * 4 + r_in < rows_left && col_ok) *reinterpret_cast<uint4*>(gout + row_off(i) + n0) = o[i];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], 8);  s2[q] += __shfl_xor_sync(0xffffffffu, s2[q], 8);
+              s1[q] += __shfl_xor_sync(0xffffffffu, s1[q], 16); s2[q] += __shfl_xor_sync(0xffffffffu, s2[q], 16);
+            }
+            if (r_in == 0 && col_ok) {
+              float4* d1 = reinterpret_cast<float4*>(stats + n0);
+              float4* d2 = reinterpret_cast<float4*>(stats + N + n0);
+              d1[0] = make_float4(s1[0], s1[1], s1[2], s1[3]); d1[1] = make_float4(s1[4], s1[5], s1[6], s1[7]);
+              d2[0] = make_float4(s2[0], s2[1], s2[2], s2[3]); d2[1] = make_float4(s2[4], s2[5], s2[6], s2[7]);
+            }
+          } else {
 #pragma unroll
           for (int i = 0; i < 8; ++i)
             if (i * 4 + r_in < rows_left && col_ok) *reinterpret_cast<uint4*>(gout + row_off(i) + n0) = o[i];
@@ -550,6 +624,7 @@ k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorM
               d2[0] = make_float4(s2[0], s2[1], s2[2], s2[3]); d2[1] = make_float4(s2[4], s2[5], s2[6], s2[7]);
             }
           }
+          }   // !BNB
           __syncwarp();
         }
         }   // has_acc
@@ -943,7 +1018,7 @@ static int pick_block_n(long long m_tiles, int n) {
 constexpr int kSmemMax = 232448;                 // 227 KB: the per-CTA opt-in limit of sm_100
 constexpr int kWsMaxBBytes = 144 * 1024;         // resident weight blocks of the weight-stationary walk
 
-template <int BN, int CL, bool MULTI, bool WS>
+template <int BN, int CL, bool MULTI, bool WS, bool BNB = false>
 static int launch_fwd(const AMaps& a, const CUtensorMap& b, FwdParams& p, cudaStream_t st) {
   constexpr int kStages = fwd_stages(BN, CL);
   constexpr int kTail = 8 * 32 * 128 + 1024 + 512;    // epilogue staging, alignment slack, barriers
@@ -958,7 +1033,7 @@ static int launch_fwd(const AMaps& a, const CUtensorMap& b, FwdParams& p, cudaSt
   }
   static bool attr_set = false;
   if (!attr_set) {
-    TP_CUDA_CHECK(cudaFuncSetAttribute(k_igemm_fwd<BN, CL, MULTI, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS ? kSmemMax : smem));
+    TP_CUDA_CHECK(cudaFuncSetAttribute(k_igemm_fwd<BN, CL, MULTI, WS, BNB>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS ? kSmemMax : smem));
     attr_set = true;
   }
   // work items: per class, (groups of CL M tiles) x (N tiles), classes back to back
@@ -980,7 +1055,7 @@ static int launch_fwd(const AMaps& a, const CUtensorMap& b, FwdParams& p, cudaSt
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
-  TP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_igemm_fwd<BN, CL, MULTI, WS>, a, b, p));
+  TP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_igemm_fwd<BN, CL, MULTI, WS, BNB>, a, b, p));
   TP_LAUNCH_CHECK();
   return TP_OK;
 }
@@ -1010,6 +1085,12 @@ static int run_fwd(const AMaps& a, const CUtensorMap& b, FwdParams& p, int bn, c
     if (bn == 256) return launch_fwd<256, 2, false, false>(a, b, p, st);
     if (bn == 128) return launch_fwd<128, 2, false, false>(a, b, p, st);
     return launch_fwd<64, 2, false, false>(a, b, p, st);
+  }
+  if (p.bn_y) {      // BatchNorm-backward epilogue (needs the linear staged path; the caller checked the shapes)
+    if (!p.tma_store || !p.stats) return TP_ERR_UNSUPPORTED;
+    if (bn == 256) return launch_fwd<256, 1, false, false, true>(a, b, p, st);
+    if (bn == 128) return launch_fwd<128, 1, false, false, true>(a, b, p, st);
+    return launch_fwd<64, 1, false, false, true>(a, b, p, st);
   }
   // weight-stationary walk: the tile's weight blocks fit next to >= 3 activation stages, there is a whole number of CTAs
   // per N tile and enough M tiles for every CTA to amortise the one-time weight load
@@ -1124,9 +1205,36 @@ int tp_conv_fprop_stats(const tp_conv_desc* d, const void* x, const void* wf, co
   return run_fwd(ta, tb, p, bn, st);
 }
 
+struct BnGate { const void* y; const float* weight; const float* bias; const float* mean; const float* invstd; float* partial; };
+
+static int conv_dgrad_impl(const tp_conv_desc* d, const void* dy, const void* wd, const void* kmask_d, const void* addend,
+                           void* dx, const BnGate* gate, void* stream);
+
 int tp_conv_dgrad(const tp_conv_desc* d, const void* dy, const void* wd, const void* kmask_d, const void* addend,
                   void* dx, void* ws, size_t ws_bytes, void* stream) {
   (void)ws; (void)ws_bytes;
+  return conv_dgrad_impl(d, dy, wd, kmask_d, addend, dx, nullptr, stream);
+}
+
+int tp_conv_dgrad_bnrelu(const tp_conv_desc* d, const void* dy, const void* wd, const void* kmask_d,
+                         const void* bn_y, const void* bn_weight, const void* bn_bias, const void* bn_mean, const void* bn_invstd,
+                         void* g, void* partial, void* stream) {
+  if (!d || !bn_y || !bn_mean || !bn_invstd || !partial) return TP_ERR_INVALID;
+  if (d->stride_h != 1 || d->stride_w != 1 || d->cin % 8 != 0) return TP_ERR_UNSUPPORTED;
+  if ((((uintptr_t)bn_y) | ((uintptr_t)bn_weight) | ((uintptr_t)bn_bias) | ((uintptr_t)bn_mean) | ((uintptr_t)bn_invstd) | ((uintptr_t)partial)) & 15)
+    return TP_ERR_UNSUPPORTED;
+  BnGate bn = {bn_y, (const float*)bn_weight, (const float*)bn_bias, (const float*)bn_mean, (const float*)bn_invstd, (float*)partial};
+  return conv_dgrad_impl(d, dy, wd, kmask_d, nullptr, g, &bn, stream);
+}
+
+size_t tp_conv_dgrad_partial_rows(const tp_conv_desc* d) {
+  if (!d) return 0;
+  const long long M = (long long)d->n * d->h * d->w;
+  return (size_t)((M + kBlockM - 1) / kBlockM) * 4;
+}
+
+static int conv_dgrad_impl(const tp_conv_desc* d, const void* dy, const void* wd, const void* kmask_d, const void* addend,
+                           void* dx, const BnGate* gate, void* stream) {
   if (!d || !dy || !wd || !dx) return TP_ERR_INVALID;
   // here the contraction runs over (r', s', cout): channel count of dY must be TMA friendly
   const int cop = d->cout;                       // caller passes dY with cout % 8 == 0 (padded if needed)
@@ -1145,6 +1253,10 @@ int tp_conv_dgrad(const tp_conv_desc* d, const void* dy, const void* wd, const v
   p.ldc = d->cin; p.out = (__nv_bfloat16*)dx; p.bias = nullptr; p.addend = (const __nv_bfloat16*)addend;
   p.kmask = (const uint32_t*)kmask_d; p.kmask_words = (int)tp_kblock_mask_words(ktot);
   p.step_w = 1; p.step_h = 1;
+  if (gate) {
+    p.bn_y = (const __nv_bfloat16*)gate->y; p.bn_weight = gate->weight; p.bn_bias = gate->bias; p.bn_mean = gate->mean; p.bn_invstd = gate->invstd;
+    p.stats = gate->partial;
+  }
   AMaps ta; CUtensorMap tb;
   if (sh == 1 && sw == 1) {
     // dX = conv(dY, rot180(W)^T) with padding (R-1-pad): wd is stored already rotated

@@ -20,20 +20,35 @@ def _ptr(t):
     return c_void_p(t.data_ptr()) if t is not None else None
 
 
+# Partial sums offered by a dgrad that already did a BatchNorm's backward reduction (ops.conv_dgrad_bnrelu): keyed by the
+# storage pointer of the gated gradient, validated by the token of the BatchNorm forward call they belong to.
+_PARTIALS = {}
+
+
+def offer_partials(g, partial, token):
+    _PARTIALS[g.data_ptr()] = (partial, token)
+
+
+def drop_partials():
+    _PARTIALS.clear()
+
+
 class _BNFn(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, residual, weight, bias, running_mean, running_var, nbt, momentum, eps, training, relu, grad_slots=None, ext_stats=None):
+    def forward(ctx, x, residual, weight, bias, running_mean, running_var, nbt, momentum, eps, training, relu, grad_slots=None, ext_stats=None,
+                saved=None):
         lib = _cabi.load()
         ctx.set_materialize_grads(False)
         ctx.grad_slots = grad_slots
+        ctx.token = saved[3] if saved is not None else None
         n, c, h, w = x.shape
-        xn = ops.to_nhwc_bf16(x, c)
+        xn = saved[0] if saved is not None else ops.to_nhwc_bf16(x, c)
         rn = ops.to_nhwc_bf16(residual, c) if residual is not None else None
         m = n * h * w
         dev = x.device
         z = ops.empty_cl(n, c, h, w, dev)
-        save_mean = torch.empty(c, dtype=torch.float32, device=dev) if training else None
-        save_invstd = torch.empty(c, dtype=torch.float32, device=dev) if training else None
+        save_mean = (saved[1] if saved is not None else torch.empty(c, dtype=torch.float32, device=dev)) if training else None
+        save_invstd = (saved[2] if saved is not None else torch.empty(c, dtype=torch.float32, device=dev)) if training else None
         wsb = ops._workspace(lib.tp_bn_workspace_bytes(m, c), dev, "bn")
         with torch.cuda.device(dev):
             use_ext = ext_stats is not None and training
@@ -67,10 +82,19 @@ class _BNFn(torch.autograd.Function):
         dweight = ws_ if direct else torch.empty(c, dtype=torch.float32, device=dev)
         dbias = bs_ if direct else torch.empty(c, dtype=torch.float32, device=dev)
         wsb = ops._workspace(lib.tp_bn_workspace_bytes(m, c), dev, "bn")
+        hint = _PARTIALS.pop(dzn.data_ptr(), None) if _PARTIALS else None
+        if hint is not None and (hint[1] is not ctx.token or ctx.relu != 2 or ctx.has_res):
+            hint = None          # not ours (a recycled address): the gradient is then treated as the raw dz, which is always right
         with torch.cuda.device(dev):
-            rc = lib.tp_bn_backward(_ptr(dzn), _ptr(z), _ptr(xn), m, c, _ptr(weight), _ptr(bias), _ptr(save_mean), _ptr(save_invstd),
-                                    int(ctx.relu), _ptr(dy), _ptr(dres), _ptr(dweight), _ptr(dbias), _ptr(wsb), wsb.numel(),
-                                    _cabi.stream_ptr(dev))
+            if hint is not None:
+                # the dgrad that produced dz already gated it and summed it: fold, coefficients, apply
+                rc = lib.tp_bn_backward_ext(_ptr(dzn), _ptr(xn), m, c, _ptr(weight), _ptr(bias), _ptr(save_mean), _ptr(save_invstd),
+                                            _ptr(hint[0]), hint[0].shape[0], _ptr(dy), _ptr(dweight), _ptr(dbias), _ptr(wsb),
+                                            wsb.numel(), _cabi.stream_ptr(dev))
+            else:
+                rc = lib.tp_bn_backward(_ptr(dzn), _ptr(z), _ptr(xn), m, c, _ptr(weight), _ptr(bias), _ptr(save_mean), _ptr(save_invstd),
+                                        int(ctx.relu), _ptr(dy), _ptr(dres), _ptr(dweight), _ptr(dbias), _ptr(wsb), wsb.numel(),
+                                        _cabi.stream_ptr(dev))
         _cabi.check(rc, "tp_bn_backward")
         ops._count(3)
         gx = dy.permute(0, 3, 1, 2)
@@ -82,7 +106,7 @@ class _BNFn(torch.autograd.Function):
         if direct:
             dweight = dbias = None
             ops.grad_ready(ws_, bs_)
-        return gx, gr, dweight, dbias, None, None, None, None, None, None, None, None, None
+        return gx, gr, dweight, dbias, None, None, None, None, None, None, None, None, None, None
 
 
 class BatchNorm2dB200(nn.BatchNorm2d):
@@ -101,9 +125,21 @@ class BatchNorm2dB200(nn.BatchNorm2d):
             return torch.relu(y) if relu else y
         momentum = 0.0 if self.momentum is None else self.momentum
         slots = grad_slots(self.weight, self.bias)
-        return _BNFn.apply(x, residual, self.weight, self.bias, self.running_mean, self.running_var,
-                           self.num_batches_tracked if (training and self.track_running_stats) else None,
-                           momentum, self.eps, training, relu, slots, ext_stats)
+        saved = None
+        if training and relu and residual is None and ops.BN_BWD_FUSION and torch.is_grad_enabled():
+            # BatchNorm+ReLU whose output feeds a masked convolution: that convolution's dgrad can do this layer's backward
+            # reduction in its epilogue — it needs y, the batch statistics and the affine parameters
+            c = x.shape[1]
+            with torch.no_grad():
+                xn = ops.to_nhwc_bf16(x.detach(), c)
+            saved = (xn, torch.empty(c, dtype=torch.float32, device=x.device),
+                     torch.empty(c, dtype=torch.float32, device=x.device), object())
+        z = _BNFn.apply(x, residual, self.weight, self.bias, self.running_mean, self.running_var,
+                        self.num_batches_tracked if (training and self.track_running_stats) else None,
+                        momentum, self.eps, training, relu, slots, ext_stats, saved)
+        if saved is not None:
+            z._tp_bn_src = (saved[0], self.weight, self.bias, saved[1], saved[2], saved[3])
+        return z
 
 
 class _MaxPoolFn(torch.autograd.Function):

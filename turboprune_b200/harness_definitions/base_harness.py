@@ -127,6 +127,8 @@ class BaseHarness:
         finally:
             ops.set_wgrad_side_stream(False)
             ops.join_wgrad(self.device)           # ... and are joined before anything reads param.grad
+            from .. import fused_norm
+            fused_norm.drop_partials()
         if self.distributed:
             self.reducer.reduce()          # joins the side stream; leftover buckets go out here
         self.optimizer.step()

@@ -586,6 +586,35 @@ def conv_dgrad(desc, dy_nhwc, wd, addend=None, kmask=None):
     return dx
 
 
+BN_BWD_FUSION = True     # dgrad epilogue does the BatchNorm backward reduction of the layer that feeds the convolution
+
+
+def set_bn_bwd_fusion(on: bool):
+    global BN_BWD_FUSION
+    BN_BWD_FUSION = bool(on)
+
+
+def conv_dgrad_bnrelu(desc, dy_nhwc, wd, bn_src, kmask=None):
+    """dgrad whose result is the gradient of a BatchNorm+ReLU output: returns (g, partial) with g = dx * [z > 0] and the
+    per-32-pixel partial sums (sum g, sum g * xhat) the BatchNorm backward needs; None when the shape has no staged path."""
+    lib = _cabi.load()
+    dev = dy_nhwc.device
+    y, weight, bias, mean, invstd = bn_src[:5]
+    g = torch.empty(desc.n, desc.h, desc.w, desc.cin, dtype=torch.bfloat16, device=dev)
+    rows = int(lib.tp_conv_dgrad_partial_rows(ctypes.byref(desc)))
+    partial = torch.empty(rows, 2, desc.cin, dtype=torch.float32, device=dev)
+    km = (kmask if kmask is not None else getattr(wd, "kmask", None)) if KBLOCK_SKIP else None
+    P = lambda t: c_void_p(t.data_ptr()) if t is not None else None
+    with torch.cuda.device(dev), _Timed("dgrad", desc):
+        rc = lib.tp_conv_dgrad_bnrelu(ctypes.byref(desc), P(dy_nhwc), P(wd), P(km), P(y), P(weight), P(bias), P(mean), P(invstd),
+                                      P(g), P(partial), _cabi.stream_ptr(dev))
+    if rc == -5:          # TP_ERR_UNSUPPORTED: no 16-byte aligned linear output for this shape
+        return None
+    _cabi.check(rc, "tp_conv_dgrad_bnrelu")
+    _count()
+    return g, partial
+
+
 def conv_wgrad(desc, x_nhwc, dy_nhwc, mask4d, cin_real, want_db=False, dw_out=None, db_out=None):
     """``dw_out`` / ``db_out``: write the gradients straight into these (contiguous fp32) buffers — used with the
     persistent gradient arena so no separate accumulate kernel runs."""
@@ -615,9 +644,11 @@ class MaskedConv2dFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, x, weight, mask, bias, stride, padding, want_skip=False, grad_slots=None, staged=None, want_stats=False):
+    def forward(ctx, x, weight, mask, bias, stride, padding, want_skip=False, grad_slots=None, staged=None, want_stats=False,
+                bn_src=None):
         _require_cuda(x, weight, mask)
         ctx.set_materialize_grads(False)
+        ctx.bn_src = None
         ctx.want_skip = want_skip
         ctx.want_stats = want_stats
         stats = None
@@ -667,6 +698,11 @@ class MaskedConv2dFn(torch.autograd.Function):
                 conv_fprop(desc, xn, wf, bias, out=y)
             ctx.mode = "conv"
             ctx.save_for_backward(xn, m32, wd)
+            # x is the output of a fused BatchNorm+ReLU (no residual): this layer's dgrad can do that BatchNorm's backward
+            # reduction in its epilogue (stride 1, no channel padding, the NHWC buffers line up)
+            if (bn_src is not None and BN_BWD_FUSION and need_dx and not want_skip and stride == (1, 1) and cin_p == cin
+                    and bn_src[0].shape == xn.shape):
+                ctx.bn_src = bn_src
             ctx.wd_kmask = getattr(wd, "kmask", None) if wd is not None else None     # attributes do not survive save_for_backward
         ctx.desc = desc
         ctx.cin = cin
@@ -692,7 +728,7 @@ class MaskedConv2dFn(torch.autograd.Function):
         dskip = rest[0] if ctx.want_skip and rest else None
         desc = ctx.desc
         if dy is None:          # only the skip output was used downstream
-            return dskip, None, None, None, None, None, None, None, None, None
+            return dskip, None, None, None, None, None, None, None, None, None, None
         cout = desc.cout
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         need_db = ctx.has_bias and ctx.needs_input_grad[3]
@@ -724,7 +760,16 @@ class MaskedConv2dFn(torch.autograd.Function):
                 xdesc = ddesc if cin == desc.cin else _cabi.ConvDesc(desc.n, desc.h, desc.w, cin, ctx.cout_p, desc.r, desc.s,
                                                                       desc.stride_h, desc.stride_w, desc.pad_h, desc.pad_w,
                                                                       desc.p, desc.q)
-                dx = conv_dgrad(xdesc, dyn, wd, addend, kmask=ctx.wd_kmask).permute(0, 3, 1, 2)
+                fused = None
+                if ctx.bn_src is not None and addend is None:
+                    fused = conv_dgrad_bnrelu(xdesc, dyn, wd, ctx.bn_src, kmask=ctx.wd_kmask)
+                if fused is not None:
+                    g, partial = fused
+                    from . import fused_norm
+                    fused_norm.offer_partials(g, partial, ctx.bn_src[5])          # picked up by that BatchNorm's backward
+                    dx = g.permute(0, 3, 1, 2)
+                else:
+                    dx = conv_dgrad(xdesc, dyn, wd, addend, kmask=ctx.wd_kmask).permute(0, 3, 1, 2)
                 if dx.dtype != ctx.x_dtype:
                     dx = dx.to(ctx.x_dtype)
             if need_dw:
@@ -761,13 +806,15 @@ class MaskedConv2dFn(torch.autograd.Function):
             db = dy.float().sum(dim=(0, 2, 3))
         if dskip is not None and dx is None and need_dx is False:
             dx = None
-        return dx, dw, None, db, None, None, None, None, None, None
+        return dx, dw, None, db, None, None, None, None, None, None, None
 
 
 def masked_conv2d(x, weight, mask, bias=None, stride=(1, 1), padding=(0, 0), want_skip=False, grad_slots=None, staged=None,
-                  want_stats=False):
-    """Returns y, or (y, x_skip) with ``want_skip``, with the BatchNorm statistics tensor appended for ``want_stats``."""
-    return MaskedConv2dFn.apply(x, weight, mask, bias, tuple(stride), tuple(padding), want_skip, grad_slots, staged, want_stats)
+                  want_stats=False, bn_src=None):
+    """Returns y, or (y, x_skip) with ``want_skip``, with the BatchNorm statistics tensor appended for ``want_stats``.
+    ``bn_src``: what ``BatchNorm2dB200`` attaches to its BatchNorm+ReLU output (``x._tp_bn_src``)."""
+    return MaskedConv2dFn.apply(x, weight, mask, bias, tuple(stride), tuple(padding), want_skip, grad_slots, staged, want_stats,
+                                bn_src)
 
 
 def masked_linear(x, weight2d, mask2d, bias=None, grad_slots=None, staged=None):

@@ -84,7 +84,8 @@ class ConvMask(_MaskMixin, nn.Conv2d):
         self._check_plain()
         if isinstance(self.padding, str):
             raise NotImplementedError("string padding modes")
-        return ops.masked_conv2d(x, self.weight, self.mask, self.bias, _pair(self.stride), _pair(self.padding), want_skip, _slots(self), ops.take_staged(self), want_stats)
+        return ops.masked_conv2d(x, self.weight, self.mask, self.bias, _pair(self.stride), _pair(self.padding), want_skip, _slots(self),
+                                 ops.take_staged(self), want_stats, getattr(x, "_tp_bn_src", None))
 
 
 class LinearMask(_MaskMixin, nn.Linear):
