@@ -98,26 +98,42 @@ def config4():
 
 
 def config5():
+    """1 process: per-GPU batch 64 on one GPU.  Under torchrun: data parallel over all ranks (BASELINE.json: 8 x B200), SNIP
+    scored on every rank's first batch, rank 0's masks imposed, gradient exchange over NVLink under the backward pass."""
     import refshim
     from turboprune_b200.utils import custom_models as cm, pruning_utils as pu
     from turboprune_b200.utils.dataset import SyntheticLoader
+    world = int(os.environ.get("WORLD_SIZE", "1")); rank = int(os.environ.get("RANK", "0"))
     dev = torch.device("cuda", torch.cuda.current_device())
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=dev)
     cfg = refshim.make_cfg("local_deit_small_patch16_224", "imagenet", mask_layer_type="LinearMask", precision="bfloat16", prune_method="snip")
     cfg["optimizer_params"].update(lr=0.01)
+    cfg["experiment_params"]["distributed"] = world > 1
     torch.manual_seed(0)
     model = cm.CustomModel(cfg).to(dev).train()
-    loader = SyntheticLoader(64, 1, (3, 224, 224), 1000, dev, seed=1)
+    loader = SyntheticLoader(64, 1, (3, 224, 224), 1000, dev, seed=1 + rank)
     torch.cuda.synchronize(); t0 = time.perf_counter()
     pu.prune_snip(cfg, model, loader, 0.5)
+    pu.sync_masks_from_rank0(model)
     torch.cuda.synchronize(); t_prune = time.perf_counter() - t0
     model.zero_grad(set_to_none=True)
-    res = {"config": "5: DeiT-small, SNIP 50 % sparsity, per-GPU batch 64, bf16 (masked Linear path)", "sparsity_percent": model.get_overall_sparsity(),
-           "prune_snip_s": t_prune}
-    h = _harness(cfg, model, 64)
-    res.update(_throughput(h, 64))
+    res = {"config": f"5: DeiT-small, SNIP 50 % sparsity, per-GPU batch 64, bf16 (masked Linear path), {world} GPU(s)",
+           "sparsity_percent": model.get_overall_sparsity(), "prune_snip_s": t_prune}
+    h = _harness(cfg, model, 64 * world)
+    if world > 1:
+        dist.barrier()
+    r = _throughput(h, 64)
+    if world > 1:
+        ms = torch.tensor([r["ms_per_step"]], device=dev); dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        r["ms_per_step"] = float(ms.item()); r["images_per_s"] = 64 * world / r["ms_per_step"] * 1e3
+        h.reducer.check_status()
+    res.update(r)
     flops = 3 * 2 * 4.183e9                     # SURVEY.md §8(d): masked linears fwd 4.183 GMAC/img, x3 for fwd + dgrad + wgrad
     res["masked_linear_tflops"] = res["images_per_s"] * flops / 1e12
-    return res
+    if world > 1:
+        dist.barrier()
+    return res if rank == 0 else None
 
 
 def rn50tail():
@@ -178,7 +194,7 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     for w in which:
         fn = {"3": config3, "4": config4, "5": config5, "rn50tail": rn50tail}[w]
-        if w != "3" and rank != 0:
+        if w not in ("3", "5") and rank != 0:
             continue
         res = fn()
         if res is not None:
