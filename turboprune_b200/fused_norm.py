@@ -26,7 +26,9 @@ _PARTIALS = {}
 
 
 def offer_partials(g, partial, token):
-    _PARTIALS[g.data_ptr()] = (partial, token)
+    # g is kept alive (its address cannot be recycled) and its version counter remembered: when the BatchNorm output has a
+    # second consumer, autograd may ACCUMULATE the other gradient in place into g — same address, different content
+    _PARTIALS[g.data_ptr()] = (partial, token, g, g._version)
 
 
 def drop_partials():
@@ -83,8 +85,9 @@ class _BNFn(torch.autograd.Function):
         dbias = bs_ if direct else torch.empty(c, dtype=torch.float32, device=dev)
         wsb = ops._workspace(lib.tp_bn_workspace_bytes(m, c), dev, "bn")
         hint = _PARTIALS.pop(dzn.data_ptr(), None) if _PARTIALS else None
-        if hint is not None and (hint[1] is not ctx.token or ctx.relu != 2 or ctx.has_res):
-            hint = None          # not ours (a recycled address): the gradient is then treated as the raw dz, which is always right
+        if hint is not None and (hint[1] is not ctx.token or hint[2]._version != hint[3] or ctx.relu != 2 or ctx.has_res):
+            hint = None          # not ours, or summed with another consumer's gradient in place: treat it as the raw dz (always right:
+                                 # gating an already gated gradient changes nothing)
         with torch.cuda.device(dev):
             if hint is not None:
                 # the dgrad that produced dz already gated it and summed it: fold, coefficients, apply
