@@ -510,6 +510,15 @@ def main():
                "sample": f"6 steps of batch 16 of the same workload after 2 warm-up steps (oracle port, torch CPU bf16 autocast, {s_per_step:.2f} s/step), "
                          f"torch.set_num_threads({threads}), os.cpu_count()={os.cpu_count()}"}
 
+    # data-parallel invariant: after all these steps every rank holds bit-identical weights (same seed, bit-identical
+    # gradient mean, deterministic kernels) — one checksum per rank, compared
+    replicas_identical = None
+    if world > 1:
+        with torch.no_grad():
+            mine = torch.stack([p.detach().double().sum() for p in model.parameters()]).sum().reshape(1)
+        allv = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allv, mine)
+        replicas_identical = all(torch.equal(allv[0], v) for v in allv)
     if rank == 0:
         line = {
             "metric": METRIC, "value": img_s, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
@@ -525,6 +534,7 @@ def main():
                         + ("" if not args.no_overlap else " [overlap disabled]"))},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
             "topk": topk, "reference_gpu_eager": gpu_eager, "loss_mean": float(loss_acc.item()) / K,
+            "replicas_identical": replicas_identical,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -136,6 +136,7 @@ class P2PGradReducer:
         self.overlap = bool(overlap)
         self._side = torch.cuda.Stream(dev)
         self._pending = [set() for _ in self._bk]
+        self._streams = [dict() for _ in self._bk]
         self._launched = [False] * len(self._bk)
         self._armed = False
         self._hooks = []
@@ -212,11 +213,16 @@ class P2PGradReducer:
             return
         seen = self._pending[bi]
         seen.add(slot_ptr)                           # a set, not a counter: a gradient reported twice counts once
+        # gradients of one bucket are written on DIFFERENT streams (BatchNorm / bias gradients on the compute stream, weight
+        # gradients on the wgrad side stream): the exchange has to wait for every stream that contributed, not only for the
+        # one that happened to report last (found by the per-level replica checksum on 4 GPUs: ranks diverged)
+        cur = torch.cuda.current_stream(self.device)
+        self._streams[bi][cur.cuda_stream] = cur
         if len(seen) == len(self._bk[bi]["params"]) and not self._launched[bi]:
-            cur = torch.cuda.current_stream(self.device)
-            ev = torch.cuda.Event()
-            ev.record(cur)
-            self._side.wait_event(ev)
+            for st in self._streams[bi].values():
+                ev = torch.cuda.Event()
+                ev.record(st)
+                self._side.wait_event(ev)
             with torch.cuda.device(self.device):
                 self._launch_bucket(bi, self._side)
 
@@ -228,6 +234,7 @@ class P2PGradReducer:
             for p in self.params:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._post_acc))
         self._pending = [set() for _ in self._bk]
+        self._streams = [dict() for _ in self._bk]
         self._launched = [False] * len(self._bk)
         self._armed = True
         ops.set_grad_ready_hook(self.notify)
