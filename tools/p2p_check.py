@@ -79,12 +79,18 @@ def check_overlap_and_mask_sync(rank, world, dev):
     red.set_model_masks(model.model)
     stager = ops.WeightStager([m for _, m in model._masked()])
     res = []
-    for overlap in (False, True, True):
+    # (overlap, weight gradients on the side stream): the last two are the harness's configuration — a bucket then holds
+    # gradients written on two streams, and its kernel has to wait for both
+    for overlap, side in ((False, False), (True, False), (True, False), (True, True), (True, True), (True, True)):
         red.overlap = overlap
         red.zero(); red.arm() if overlap else None
         stager.stage()
-        with torch.autocast("cuda", dtype=torch.bfloat16):
-            torch.nn.functional.cross_entropy(model(x), t).backward()
+        ops.set_wgrad_side_stream(side)
+        try:
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                torch.nn.functional.cross_entropy(model(x), t).backward()
+        finally:
+            ops.set_wgrad_side_stream(False)
         launched = sum(red._launched) if overlap else 0
         red.reduce()
         torch.cuda.synchronize(); red.check_status()
@@ -93,7 +99,7 @@ def check_overlap_and_mask_sync(rank, world, dev):
             print(f"overlap: {launched} of {len(red._bk)} buckets were launched during the backward pass", flush=True)
         if overlap and launched == 0:
             ok = False
-    ok &= torch.equal(res[0], res[1]) and torch.equal(res[1], res[2])
+    ok &= all(torch.equal(res[0], r) for r in res[1:])
     gathered = [torch.empty_like(res[1]) for _ in range(world)]
     dist.all_gather(gathered, res[1])
     ok &= all(torch.equal(gathered[0], q) for q in gathered)
