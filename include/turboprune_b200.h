@@ -36,6 +36,9 @@ const char* tp_strerror(int code);
 const char* tp_last_cuda_error(void);      /* text of the last CUDA error seen by this thread */
 int         tp_abi_version(void);          /* bumps when a signature changes */
 int         tp_device_sm_count(void);      /* cached multiprocessor count of the current device */
+/* Programmatic dependent launch for the train-step kernels (default off; TP_PDL=1 in the environment turns it on).
+ * Returns the previous setting.  A debugging / A-B switch: results are bit-identical either way. */
+int         tp_set_pdl(int on);
 
 /* ---- score kinds (utils/pruning_utils.py) ------------------------------------------- */
 #define TP_SCORE_MAG      0   /* |m*w|      prune_mag :75, prune_random_* :109-116 (w := randn draw) */

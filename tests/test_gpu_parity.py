@@ -604,8 +604,10 @@ def test_batched_weight_staging_matches_per_layer(dev):
     assert all(torch.equal(a, b) for a, b in zip(*res))
 
 
-def test_arena_direct_gradient_writes_equal_autograd_accumulation(dev):
-    """With a GradArena attached, wgrad / BN backward write dW, db, dgamma, dbeta straight into the slots (no
+@pytest.mark.parametrize("arch", ["resnet18", "vgg16"])
+def test_arena_direct_gradient_writes_equal_autograd_accumulation(dev, arch):
+    """(vgg16: convolutions WITH a bias — its gradient goes to the slot too, once.)
+    With a GradArena attached, wgrad / BN backward write dW, db, dgamma, dbeta straight into the slots (no
     AccumulateGrad kernel); the values must be the ones autograd would have accumulated into a fresh .grad, and a
     model whose grads were detached (zero_grad(set_to_none=True)) must fall back to the ordinary path."""
     import copy
@@ -613,13 +615,14 @@ def test_arena_direct_gradient_writes_equal_autograd_accumulation(dev):
     from turboprune_b200.grad_exchange import GradArena
     from turboprune_b200.utils import custom_models as cm, pruning_utils as pu
     torch.manual_seed(0)
-    base = cm.TorchVisionModel(refshim.make_cfg("resnet18", "cifar10"))
+    base = cm.TorchVisionModel(refshim.make_cfg(arch, "cifar10"))
     torch.manual_seed(1)
     pu.prune_er_erk(base, 0.3)
     g = torch.Generator().manual_seed(3)
     x = torch.randn(32, 3, 32, 32, generator=g).to(dev); t = torch.randint(0, 10, (32,), generator=g).to(dev)
 
     def run(m):
+        torch.manual_seed(7)                   # vgg16's classifier has dropout: the same draw for every run
         with torch.autocast("cuda", dtype=torch.bfloat16):
             torch.nn.functional.cross_entropy(m(x), t).backward()
 

@@ -33,6 +33,7 @@ SIGNATURES = {
     "tp_last_cuda_error": (c_char_p, []),
     "tp_abi_version": (c_int, []),
     "tp_device_sm_count": (c_int, []),
+    "tp_set_pdl": (c_int, [c_int]),
     "tp_topk_workspace_bytes": (c_size_t, [c_int, c_int64]),
     "tp_topk_threshold_mask": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
                                        POINTER(c_int64), c_int, c_int64, c_int, c_void_p, c_void_p, c_size_t,

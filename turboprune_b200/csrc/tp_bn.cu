@@ -67,6 +67,7 @@ __device__ __forceinline__ void stg16(void* p, const uint4& v) {
 // partial[blockIdx.x][0][c] = sum (x - shift_c), partial[blockIdx.x][1][c] = sum (x - shift_c)^2
 __global__ void __launch_bounds__(kBnThreads) k_bn_stats(const __nv_bfloat16* __restrict__ y, long long M, int C,
                                                          float* __restrict__ partial) {
+  pdl_enter();
   __shared__ float s_acc[kBnThreads][17];
   const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
   const int cvec = blockIdx.y * TX + tx;              // channel-vector index
@@ -144,6 +145,7 @@ __global__ void __launch_bounds__(kFinC * kFinP) k_bn_finalize_stats(const float
                                     float* running_mean, float* running_var, long long* nbt, float momentum, float eps,
                                     float* __restrict__ save_mean, float* __restrict__ save_invstd,
                                     float* __restrict__ scale, float* __restrict__ shift) {
+  pdl_enter();
   __shared__ float sm[2][kFinP][kFinC];
   const int c = blockIdx.x * kFinC + threadIdx.x;
   float s1, s2;
@@ -180,6 +182,7 @@ __global__ void __launch_bounds__(kFinC * kFinP) k_bn_finalize_stats(const float
 // partial[g][2][C], 1024 rows per CTA in a fixed order; k_bn_finalize_stats then folds the (few) g rows.
 __global__ void __launch_bounds__(kFinC * kFinP) k_bn_fold_ext(const float* __restrict__ ext, long long rows, int C,
                                                                float* __restrict__ partial) {
+  pdl_enter();
   __shared__ float sm[2][kFinP][kFinC];
   const int tx = threadIdx.x, ty = threadIdx.y;
   const int c = blockIdx.x * kFinC + tx;
@@ -210,6 +213,7 @@ __global__ void __launch_bounds__(kFinC * kFinP) k_bn_fold_ext(const float* __re
 __global__ void k_bn_eval_coeffs(int C, const float* __restrict__ weight, const float* __restrict__ bias,
                                  const float* __restrict__ running_mean, const float* __restrict__ running_var, float eps,
                                  float* __restrict__ scale, float* __restrict__ shift) {
+  pdl_enter();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const float invstd = rsqrtf(running_var[c] + eps);
@@ -222,6 +226,7 @@ template <bool RELU, bool RES>
 __global__ void __launch_bounds__(kBnThreads) k_bn_apply(const __nv_bfloat16* __restrict__ y, const __nv_bfloat16* __restrict__ res,
                                                          __nv_bfloat16* __restrict__ z, long long M, int C,
                                                          const float* __restrict__ scale, const float* __restrict__ shift) {
+  pdl_enter();
   const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
   const int cvec = blockIdx.y * TX + tx;
   if (cvec * 8 >= C) return;
@@ -277,6 +282,7 @@ __global__ void __launch_bounds__(kBnThreads) k_bn_bwd_reduce(const __nv_bfloat1
                                                               const float* __restrict__ mean, const float* __restrict__ invstd,
                                                               const float* __restrict__ weight, const float* __restrict__ bias,
                                                               float* __restrict__ partial, __nv_bfloat16* __restrict__ gout) {
+  pdl_enter();
   __shared__ float s_acc[kBnThreads][17];
   const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
   const int cvec = blockIdx.y * TX + tx;
@@ -358,6 +364,7 @@ __global__ void __launch_bounds__(kFinC * kFinP) k_bn_finalize_bwd(const float* 
                                   const float* __restrict__ weight, const float* __restrict__ bias,
                                   const float* __restrict__ mean, const float* __restrict__ invstd,
                                   float* __restrict__ dweight, float* __restrict__ dbias, float* __restrict__ coef) {
+  pdl_enter();
   __shared__ float sm[2][kFinP][kFinC];
   const int c = blockIdx.x * kFinC + threadIdx.x;
   float s1, s2;
@@ -380,6 +387,7 @@ __global__ void __launch_bounds__(kBnThreads) k_bn_bwd_apply(const __nv_bfloat16
                                                              const __nv_bfloat16* __restrict__ y, long long M, int C,
                                                              const float* __restrict__ coef, __nv_bfloat16* __restrict__ dy,
                                                              __nv_bfloat16* __restrict__ dres) {
+  pdl_enter();
   const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
   const int cvec = blockIdx.y * TX + tx;
   if (cvec * 8 >= C) return;
@@ -476,29 +484,29 @@ int tp_bn_forward_ext(const void* y, const void* residual, void* z, int64_t M, i
     const float* fold_src = (const float*)ext_stats;       // <= 1024 rows: the finalize kernel folds them directly
     long long fold_rows = ext_rows;
     if (groups > 1) {
-      k_bn_fold_ext<<<dim3((C + kFinC - 1) / kFinC, (unsigned)groups), dim3(kFinC, kFinP), 0, st>>>((const float*)ext_stats, ext_rows, C, partial);
+      launch(k_bn_fold_ext, dim3((C + kFinC - 1) / kFinC, (unsigned)groups), dim3(kFinC, kFinP), 0, st, (const float*)ext_stats, ext_rows, C, partial);
       fold_src = partial; fold_rows = groups;
     }
-    k_bn_finalize_stats<<<(C + kFinC - 1) / kFinC, dim3(kFinC, kFinP), 0, st>>>(fold_src, (int)fold_rows, nullptr, M, C,
+    launch(k_bn_finalize_stats, (C + kFinC - 1) / kFinC, dim3(kFinC, kFinP), 0, st, fold_src, (int)fold_rows, nullptr, M, C,
                                                           (const float*)weight, (const float*)bias, (float*)running_mean,
                                                           (float*)running_var, (long long*)num_batches_tracked, momentum, eps,
                                                           (float*)save_mean, (float*)save_invstd, scale, shift);
   } else if (training) {
-    k_bn_stats<<<grid, block, 0, st>>>((const __nv_bfloat16*)y, M, C, partial);
-    k_bn_finalize_stats<<<(C + kFinC - 1) / kFinC, dim3(kFinC, kFinP), 0, st>>>(partial, g.grid_x, (const __nv_bfloat16*)y, M, C,
+    launch(k_bn_stats, grid, block, 0, st, (const __nv_bfloat16*)y, M, C, partial);
+    launch(k_bn_finalize_stats, (C + kFinC - 1) / kFinC, dim3(kFinC, kFinP), 0, st, partial, g.grid_x, (const __nv_bfloat16*)y, M, C,
                                                           (const float*)weight, (const float*)bias, (float*)running_mean,
                                                           (float*)running_var, (long long*)num_batches_tracked, momentum, eps,
                                                           (float*)save_mean, (float*)save_invstd, scale, shift);
   } else {
-    k_bn_eval_coeffs<<<(C + 255) / 256, 256, 0, st>>>(C, (const float*)weight, (const float*)bias, (const float*)running_mean,
+    launch(k_bn_eval_coeffs, (C + 255) / 256, 256, 0, st, C, (const float*)weight, (const float*)bias, (const float*)running_mean,
                                                        (const float*)running_var, eps, scale, shift);
   }
   const __nv_bfloat16* yy = (const __nv_bfloat16*)y; const __nv_bfloat16* rr = (const __nv_bfloat16*)residual;
   __nv_bfloat16* zz = (__nv_bfloat16*)z;
-  if (relu && rr) k_bn_apply<true, true><<<grid, block, 0, st>>>(yy, rr, zz, M, C, scale, shift);
-  else if (relu) k_bn_apply<true, false><<<grid, block, 0, st>>>(yy, rr, zz, M, C, scale, shift);
-  else if (rr) k_bn_apply<false, true><<<grid, block, 0, st>>>(yy, rr, zz, M, C, scale, shift);
-  else k_bn_apply<false, false><<<grid, block, 0, st>>>(yy, rr, zz, M, C, scale, shift);
+  if (relu && rr) launch(k_bn_apply<true, true>, grid, block, 0, st, yy, rr, zz, M, C, scale, shift);
+  else if (relu) launch(k_bn_apply<true, false>, grid, block, 0, st, yy, rr, zz, M, C, scale, shift);
+  else if (rr) launch(k_bn_apply<false, true>, grid, block, 0, st, yy, rr, zz, M, C, scale, shift);
+  else launch(k_bn_apply<false, false>, grid, block, 0, st, yy, rr, zz, M, C, scale, shift);
   TP_LAUNCH_CHECK();
   return TP_OK;
 }
@@ -520,20 +528,20 @@ int tp_bn_backward(const void* dz, const void* z, const void* y, int64_t M, int 
   __nv_bfloat16* o = (__nv_bfloat16*)dy; __nv_bfloat16* r = (__nv_bfloat16*)dres;
   // with an activation AND a residual the gated gradient g is the residual's gradient: write it in the reduce pass
   const bool g_first = relu != 0 && r != nullptr;
-  if (relu == 1 && g_first) k_bn_bwd_reduce<1, true><<<grid, block, 0, st>>>(d, zz, yy, M, C, mu, is, wp, bp, partial, r);
-  else if (relu == 2 && g_first) k_bn_bwd_reduce<2, true><<<grid, block, 0, st>>>(d, zz, yy, M, C, mu, is, wp, bp, partial, r);
-  else if (relu == 1) k_bn_bwd_reduce<1, false><<<grid, block, 0, st>>>(d, zz, yy, M, C, mu, is, wp, bp, partial, nullptr);
-  else if (relu == 2) k_bn_bwd_reduce<2, false><<<grid, block, 0, st>>>(d, zz, yy, M, C, mu, is, wp, bp, partial, nullptr);
-  else k_bn_bwd_reduce<0, false><<<grid, block, 0, st>>>(d, zz, yy, M, C, mu, is, wp, bp, partial, nullptr);
-  k_bn_finalize_bwd<<<(C + kFinC - 1) / kFinC, dim3(kFinC, kFinP), 0, st>>>(partial, g.grid_x, M, C, wp, bp, mu, is,
+  if (relu == 1 && g_first) launch(k_bn_bwd_reduce<1, true>, grid, block, 0, st, d, zz, yy, M, C, mu, is, wp, bp, partial, r);
+  else if (relu == 2 && g_first) launch(k_bn_bwd_reduce<2, true>, grid, block, 0, st, d, zz, yy, M, C, mu, is, wp, bp, partial, r);
+  else if (relu == 1) launch(k_bn_bwd_reduce<1, false>, grid, block, 0, st, d, zz, yy, M, C, mu, is, wp, bp, partial, nullptr);
+  else if (relu == 2) launch(k_bn_bwd_reduce<2, false>, grid, block, 0, st, d, zz, yy, M, C, mu, is, wp, bp, partial, nullptr);
+  else launch(k_bn_bwd_reduce<0, false>, grid, block, 0, st, d, zz, yy, M, C, mu, is, wp, bp, partial, nullptr);
+  launch(k_bn_finalize_bwd, (C + kFinC - 1) / kFinC, dim3(kFinC, kFinP), 0, st, partial, g.grid_x, M, C, wp, bp, mu, is,
                                                                           (float*)dweight, (float*)dbias, coef);
-  if (g_first) k_bn_bwd_apply<0, false><<<grid, block, 0, st>>>(r, zz, yy, M, C, coef, o, nullptr);     // g is final: no gate, no second write
-  else if (relu == 1 && r) k_bn_bwd_apply<1, true><<<grid, block, 0, st>>>(d, zz, yy, M, C, coef, o, r);
-  else if (relu == 1) k_bn_bwd_apply<1, false><<<grid, block, 0, st>>>(d, zz, yy, M, C, coef, o, r);
-  else if (relu == 2 && r) k_bn_bwd_apply<2, true><<<grid, block, 0, st>>>(d, zz, yy, M, C, coef, o, r);
-  else if (relu == 2) k_bn_bwd_apply<2, false><<<grid, block, 0, st>>>(d, zz, yy, M, C, coef, o, r);
-  else if (r) k_bn_bwd_apply<0, true><<<grid, block, 0, st>>>(d, zz, yy, M, C, coef, o, r);
-  else k_bn_bwd_apply<0, false><<<grid, block, 0, st>>>(d, zz, yy, M, C, coef, o, r);
+  if (g_first) launch(k_bn_bwd_apply<0, false>, grid, block, 0, st, r, zz, yy, M, C, coef, o, nullptr);     // g is final: no gate, no second write
+  else if (relu == 1 && r) launch(k_bn_bwd_apply<1, true>, grid, block, 0, st, d, zz, yy, M, C, coef, o, r);
+  else if (relu == 1) launch(k_bn_bwd_apply<1, false>, grid, block, 0, st, d, zz, yy, M, C, coef, o, r);
+  else if (relu == 2 && r) launch(k_bn_bwd_apply<2, true>, grid, block, 0, st, d, zz, yy, M, C, coef, o, r);
+  else if (relu == 2) launch(k_bn_bwd_apply<2, false>, grid, block, 0, st, d, zz, yy, M, C, coef, o, r);
+  else if (r) launch(k_bn_bwd_apply<0, true>, grid, block, 0, st, d, zz, yy, M, C, coef, o, r);
+  else launch(k_bn_bwd_apply<0, false>, grid, block, 0, st, d, zz, yy, M, C, coef, o, r);
   TP_LAUNCH_CHECK();
   return TP_OK;
 }
@@ -556,14 +564,14 @@ int tp_bn_backward_ext(const void* g, const void* y, int64_t M, int C, const voi
   const long long groups = (n_rows + 1023) / 1024;
   if (groups > 1) {
     if (groups > gm.grid_x) return TP_ERR_WORKSPACE;
-    k_bn_fold_ext<<<dim3((C + kFinC - 1) / kFinC, (unsigned)groups), dim3(kFinC, kFinP), 0, st>>>((const float*)partial_rows, n_rows, C, partial);
+    launch(k_bn_fold_ext, dim3((C + kFinC - 1) / kFinC, (unsigned)groups), dim3(kFinC, kFinP), 0, st, (const float*)partial_rows, n_rows, C, partial);
     fold_src = partial; fold_rows = groups;
   }
-  k_bn_finalize_bwd<<<(C + kFinC - 1) / kFinC, dim3(kFinC, kFinP), 0, st>>>(fold_src, (int)fold_rows, M, C, (const float*)weight, (const float*)bias,
+  launch(k_bn_finalize_bwd, (C + kFinC - 1) / kFinC, dim3(kFinC, kFinP), 0, st, fold_src, (int)fold_rows, M, C, (const float*)weight, (const float*)bias,
                                                                           (const float*)save_mean, (const float*)save_invstd,
                                                                           (float*)dweight, (float*)dbias, coef);
   dim3 block(gm.tx, gm.ty), grid(gm.grid_x, gm.ctiles);
-  k_bn_bwd_apply<0, false><<<grid, block, 0, st>>>((const __nv_bfloat16*)g, nullptr, (const __nv_bfloat16*)y, M, C, coef, (__nv_bfloat16*)dy, nullptr);
+  launch(k_bn_bwd_apply<0, false>, grid, block, 0, st, (const __nv_bfloat16*)g, nullptr, (const __nv_bfloat16*)y, M, C, coef, (__nv_bfloat16*)dy, nullptr);
   TP_LAUNCH_CHECK();
   return TP_OK;
 }

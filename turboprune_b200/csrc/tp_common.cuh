@@ -28,6 +28,32 @@ int sm_count();                       // cached
 int bind_device_of(const void* p);
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
+// Programmatic dependent launch (PDL) for the kernels of the train step.  A step is ~540 dependent launches; without PDL
+// every one of them pays grid drain + launch + ramp-up in full.  With it the next grid's CTAs are scheduled while the
+// previous grid is still finishing (as soon as every CTA of the previous grid has STARTED and executed
+// `griddepcontrol.launch_dependents`), and block in `griddepcontrol.wait` until that grid has completed and its memory
+// is visible.  Rules kept here: (1) a kernel launched through launch() executes pdl_wait() before its first global
+// access (pdl_enter() at the top, or after a prologue that touches only parameters / shared memory / TMEM);
+// (2) the trigger comes first, so grids queue up behind each other only as deep as the SMs have room for.
+// Off by default (measured: a gain at small batches, a loss at batch 512 — see pdl_enabled()); TP_PDL=1 turns it on.
+bool pdl_enabled();
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_trigger(); pdl_wait(); }
+
+template <typename... KA, typename... A>
+inline cudaError_t launch(void (*kernel)(KA...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KA>(args)...);
+}
+#endif
+
 // A bump allocator over the caller's workspace.
 struct Arena {
   char* base; size_t cap; size_t off;

@@ -1,5 +1,6 @@
 // Error plumbing, device cache and the segment-table upload shared by all kernels.
 #include "tp_common.cuh"
+#include <stdlib.h>
 #include <string.h>
 #include <vector>
 
@@ -9,6 +10,14 @@ static thread_local char g_last_err[512] = "";
 
 void set_last_cuda_error(cudaError_t e, const char* where) {
   snprintf(g_last_err, sizeof(g_last_err), "%s: %s (%s)", where, cudaGetErrorName(e), cudaGetErrorString(e));
+}
+
+static int g_pdl = -1;
+bool pdl_enabled() {
+  // measured (profiles/r02_notes.md, experiment 9): per-GPU batch 64: 7.68 -> 7.58 ms per step; batch 512: 42.14 -> 42.74 ms.
+  // Opt-in (TP_PDL=1 or tp_set_pdl(1)) until the trigger placement is tuned per kernel.
+  if (g_pdl < 0) { const char* e = getenv("TP_PDL"); g_pdl = (e && e[0] == '1') ? 1 : 0; }
+  return g_pdl == 1;
 }
 
 int sm_count() {
@@ -97,6 +106,7 @@ const char* tp_strerror(int code) {
 const char* tp_last_cuda_error(void) { return tp::g_last_err; }
 int tp_abi_version(void) { return 7; }
 int tp_device_sm_count(void) { return tp::sm_count(); }
+int tp_set_pdl(int on) { const int prev = tp::pdl_enabled() ? 1 : 0; tp::g_pdl = on ? 1 : 0; return prev; }
 
 size_t tp_segtable_workspace_bytes(int n_seg) {
   return tp::align_up(sizeof(tp::Seg) * (size_t)(n_seg > 0 ? n_seg : 1), 256) + 256;

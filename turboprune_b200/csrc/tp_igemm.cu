@@ -184,6 +184,7 @@ k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorM
                                  (kAccStages * BLOCK_N <= 128) ? 128 : (kAccStages * BLOCK_N <= 256) ? 256 : 512;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  pdl_trigger();
   constexpr int kStgBytes = 32 * 128;                      // one epilogue warp's 32 rows x 64 bf16 columns
   constexpr int kMaxStages = 16;
   const int n_stages = WS ? p.ws_stages : kStages;         // WS: a stage is the 16 KB activation tile alone
@@ -238,6 +239,7 @@ k_igemm_fwd(const __grid_constant__ AMaps tmA, const __grid_constant__ CUtensorM
   if (CL > 1) cluster_sync_all(); else __syncthreads();      // peers' barriers are initialised before anyone signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();          // barriers, TMEM and descriptor prefetch above overlap the previous grid's tail; global memory from here on
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
@@ -693,6 +695,7 @@ k_igemm_wgrad(const __grid_constant__ CUtensorMap tmA /* dY [Kpix, Cout] */,
   constexpr int kStageBytes = kABytes + kMaxNb * kChunkBytes;   // 48 KB
   constexpr int kStages = 4;
   constexpr uint32_t kTmemCols = 512;                     // 2 accumulator stages x 256 columns
+  pdl_trigger();
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = (uint64_t*)(smem + kStages * kStageBytes);
@@ -716,6 +719,7 @@ k_igemm_wgrad(const __grid_constant__ CUtensorMap tmA /* dY [Kpix, Cout] */,
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     if (lane == 0) {
@@ -839,6 +843,7 @@ k_igemm_wgrad(const __grid_constant__ CUtensorMap tmA /* dY [Kpix, Cout] */,
 __global__ void __launch_bounds__(256) k_wgrad_finalize(const float* __restrict__ partial, const float* __restrict__ mask,
                                                         float* __restrict__ dw, int cout, int cin_real, int cin_p, int rs,
                                                         int nb, int m_tiles, int n_tiles, int splits, int sl) {
+  pdl_enter();
   __shared__ float s_lane[256];
   const int co = blockIdx.x;
   const int m_t = co / kBlockM, r = co % kBlockM;
@@ -878,6 +883,7 @@ __global__ void __launch_bounds__(256) k_wgrad_finalize(const float* __restrict_
 // db[c] = sum over pixels of dy[pix][c]  (bias gradient), dy bf16 [npix, ldc]
 __global__ void __launch_bounds__(256) k_colsum(const __nv_bfloat16* __restrict__ dy, long long npix, int c, int ldc,
                                                 float* __restrict__ db) {
+  pdl_enter();
   // one CTA per 32 channels; threads (32 x 8): 8 pixel lanes, fixed-order tree -> deterministic
   __shared__ float s[8][33];
   const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
@@ -1051,10 +1057,12 @@ static int launch_fwd(const AMaps& a, const CUtensorMap& b, FwdParams& p, cudaSt
   if (WS) grid = (sm_count() / n_tiles) * n_tiles;           // every CTA owns one N tile: a whole number of CTAs per N tile
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kFwdThreads); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = (CL == 1 && pdl_enabled()) ? 2 : 1;     // pairs stay fully serialised
   TP_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_igemm_fwd<BN, CL, MULTI, WS, BNB>, a, b, p));
   TP_LAUNCH_CHECK();
   return TP_OK;
@@ -1374,16 +1382,16 @@ int tp_conv_wgrad(const tp_conv_desc* d, const void* x, const void* dy, const vo
     attr_set = true;
   }
   const int items = p.m_tiles * p.n_tiles * splits;
-  k_igemm_wgrad<<<items < sms ? items : sms, kThreads, smem, st>>>(ta, tb, p);
+  launch(k_igemm_wgrad, items < sms ? items : sms, kThreads, smem, st, ta, tb, p);
   TP_LAUNCH_CHECK();
   // split lanes only pay when there are many splits (skinny layers); wide-K layers keep all 256 threads on K
   const int sl = splits >= 64 ? 8 : (splits >= 32 ? 4 : (splits >= 16 ? 2 : 1));
   const int fin_kt = 256 / sl;
-  k_wgrad_finalize<<<dim3(d->cout, (rs * d->cin + fin_kt - 1) / fin_kt), 256, 0, st>>>(
+  launch(k_wgrad_finalize, dim3(d->cout, (rs * d->cin + fin_kt - 1) / fin_kt), 256, 0, st, 
       p.partial, (const float*)mask, (float*)dw, d->cout, cin_real, d->cin, rs, p.nb, p.m_tiles, p.n_tiles, splits, sl);
   TP_LAUNCH_CHECK();
   if (db) {
-    k_colsum<<<(d->cout + 31) / 32, 256, 0, st>>>((const __nv_bfloat16*)dy, (long long)p.Kpix, d->cout, d->cout, (float*)db);
+    launch(k_colsum, (d->cout + 31) / 32, 256, 0, st, (const __nv_bfloat16*)dy, (long long)p.Kpix, d->cout, d->cout, (float*)db);
     TP_LAUNCH_CHECK();
   }
   return TP_OK;

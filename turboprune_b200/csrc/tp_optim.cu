@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(256) k_stage_weights(const float* __restrict__
                                                        __nv_bfloat16* __restrict__ wd, int cout_p, int wf_ld,
                                                        uint32_t* __restrict__ kmf, int kmf_words,
                                                        uint32_t* __restrict__ kmd, int kmd_words) {
+  pdl_enter();
   extern __shared__ float s_slab[];       // [kCoT][cin_chunk][rs] fp32, sized by the host
   // process channels in chunks of CC so the slab fits in smem
   const int CC = (cin + gridDim.y - 1) / gridDim.y;
@@ -129,6 +130,7 @@ struct StageItem {
 };
 
 __global__ void __launch_bounds__(256) k_stage_weights_batched(const StageItem* __restrict__ items, int n_items) {
+  pdl_enter();
   extern __shared__ float s_slab[];
   int lo = 0, hi = n_items - 1;
   const long long b = blockIdx.x;
@@ -166,6 +168,7 @@ __device__ __forceinline__ void kmask_count_empty(uint32_t* km, int rows, int wo
 }
 
 __global__ void __launch_bounds__(256) k_kmask_summary(const StageItem* __restrict__ items, int n_items) {
+  pdl_enter();
   const StageItem it = items[blockIdx.x];
   if (it.kmf) kmask_count_empty(it.kmf, (it.cout + 63) / 64, it.kmf_words, (it.wf_ld + 63) / 64);
   if (it.kmd && it.wd) kmask_count_empty(it.kmd, (it.cin + 63) / 64, it.kmd_words, (it.rs * it.cout_p + 63) / 64);
@@ -173,11 +176,13 @@ __global__ void __launch_bounds__(256) k_kmask_summary(const StageItem* __restri
 
 __global__ void __launch_bounds__(256) k_kmask_summary1(uint32_t* kmf, int rows_f, int words_f, int kb_f,
                                                          uint32_t* kmd, int rows_d, int words_d, int kb_d) {
+  pdl_enter();
   if (kmf) kmask_count_empty(kmf, rows_f, words_f, kb_f);
   if (kmd) kmask_count_empty(kmd, rows_d, words_d, kb_d);
 }
 
 __global__ void k_zero_bf16(__nv_bfloat16* p, long long n) {
+  pdl_enter();
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) p[i] = __float2bfloat16_rn(0.f);
@@ -187,6 +192,7 @@ __global__ void k_zero_bf16(__nv_bfloat16* p, long long n) {
 template <typename T>
 __global__ void __launch_bounds__(256) k_to_nhwc(const T* __restrict__ src, long long sn, long long sc, long long sh, long long sw,
                                                  int n, int c, int h, int w, __nv_bfloat16* __restrict__ dst, int c_pad) {
+  pdl_enter();
   long long total = (long long)n * h * w * c_pad;
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
@@ -210,6 +216,7 @@ __global__ void __launch_bounds__(256) k_to_nhwc(const T* __restrict__ src, long
 __global__ void __launch_bounds__(256) k_im2col_c8(const uint4* __restrict__ x, int n, int h, int w,
                                                    int R, int S, int stride_h, int stride_w, int pad_h, int pad_w,
                                                    int P, int Q, uint4* __restrict__ xcol, int kp8) {
+  pdl_enter();
   const long long total = (long long)n * P * Q * kp8;
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   const long long step = (long long)gridDim.x * blockDim.x;
@@ -235,6 +242,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_im2col_stem(const T* __restrict__ src, long long sn, long long sc, long long sh, long long sw,
                                                      int n, int c, int h, int w, int R, int S, int cg, int stride_h, int stride_w,
                                                      int pad_h, int pad_w, int P, int Q, uint4* __restrict__ xcol, int kp8) {
+  pdl_enter();
   // one thread = one 16-byte cell (8 consecutive columns) of the matrix; column e = tap * cg + channel.  The
   // (row offset, column offset, channel) of every column is decoded once per CTA into shared memory, so the inner
   // loop has no divisions.  cg = channels per tap: the RGB stem uses cg = 3 (K = 152 for 147 real columns) instead
@@ -283,6 +291,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) k_im2col_stem_rows(const T* __restrict__ src, long long sn, long long sc, long long sh, long long sw,
                                                           int n, int c, int h, int w, int R, int S, int cg, int stride_h, int stride_w,
                                                           int pad_h, int pad_w, int P, int Q, int QS, uint4* __restrict__ xcol, int kp8) {
+  pdl_enter();
   extern __shared__ __align__(16) unsigned short s_patch[];      // [R][pw * c] bf16 bits, then one zero slot
   const int pw = (QS - 1) * stride_w + S;                       // input columns under a strip
   const int pitch = pw * c;
@@ -342,6 +351,7 @@ __global__ void __launch_bounds__(256) k_im2col_stem_rows(const T* __restrict__ 
 // parameters.  20 B/elem: read w,g,buf; write w,buf.
 __global__ void __launch_bounds__(256) k_sgd(const Seg* __restrict__ segs, int n_seg, long long tiles,
                                              const float* __restrict__ lr_p, float mu, float wd, int first) {
+  pdl_enter();
   const float lr = *lr_p;
   const int t = threadIdx.x;
   for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
@@ -410,18 +420,18 @@ int tp_stage_weights(const void* w, const void* mask, int cout, int cin, int r, 
   if (wd) {
     long long nz = (long long)cin_p2 * rs * cout_p;
     if (cout_p > cout || cin_p2 > cin) {
-      k_zero_bf16<<<(unsigned)min((nz + 255) / 256, (long long)sm_count() * 16), 256, 0, st>>>((__nv_bfloat16*)wd, nz);
+      launch(k_zero_bf16, (unsigned)min((nz + 255) / 256, (long long)sm_count() * 16), 256, 0, st, (__nv_bfloat16*)wd, nz);
     }
   }
   const int kmf_words = (int)tp_kblock_mask_words(wf_ld), kmd_words = (int)tp_kblock_mask_words((int64_t)rs * cout_p);
   if (kmask_f) TP_CUDA_CHECK(cudaMemsetAsync(kmask_f, 0, ((size_t)((cout + 63) / 64) * kmf_words + 1) * 4, st));
   if (kmask_d && wd) TP_CUDA_CHECK(cudaMemsetAsync(kmask_d, 0, ((size_t)((cin + 63) / 64) * kmd_words + 1) * 4, st));
   dim3 grid((cout + kCoT - 1) / kCoT, ysplit);
-  k_stage_weights<<<grid, 256, smem, st>>>((const float*)w, (const float*)mask, cout, cin, rs,
+  launch(k_stage_weights, grid, 256, smem, st, (const float*)w, (const float*)mask, cout, cin, rs,
                                            (__nv_bfloat16*)wf, cin_p, (__nv_bfloat16*)wd, cout_p, wf_ld,
                                            (uint32_t*)kmask_f, kmf_words, (uint32_t*)kmask_d, kmd_words);
   if (kmask_f || (kmask_d && wd))
-    k_kmask_summary1<<<1, 256, 0, st>>>((uint32_t*)kmask_f, (cout + 63) / 64, kmf_words, (wf_ld + 63) / 64,
+    launch(k_kmask_summary1, 1, 256, 0, st, (uint32_t*)kmask_f, (cout + 63) / 64, kmf_words, (wf_ld + 63) / 64,
                                          wd ? (uint32_t*)kmask_d : nullptr, (cin + 63) / 64, kmd_words, (rs * cout_p + 63) / 64);
   TP_LAUNCH_CHECK();
   return TP_OK;
@@ -464,8 +474,8 @@ int tp_stage_weights_batched(const tp_stage_item* items, int n_items, int table_
   if (!table_cached)   // pageable source: staged by the runtime before returning (not capturable: cache the table first)
     TP_CUDA_CHECK(cudaMemcpyAsync(d_items, h.data(), sizeof(StageItem) * n_items, cudaMemcpyHostToDevice, st));
   if (kmask_all && kmask_bytes) TP_CUDA_CHECK(cudaMemsetAsync(kmask_all, 0, kmask_bytes, st));   // all layers' occupancy masks: one memset node
-  k_stage_weights_batched<<<(unsigned)cta, 256, smem, st>>>(d_items, n_items);
-  if (kmask_all && kmask_bytes) k_kmask_summary<<<n_items, 256, 0, st>>>(d_items, n_items);
+  launch(k_stage_weights_batched, (unsigned)cta, 256, smem, st, d_items, n_items);
+  if (kmask_all && kmask_bytes) launch(k_kmask_summary, n_items, 256, 0, st, d_items, n_items);
   TP_LAUNCH_CHECK();
   return TP_OK;
 }
@@ -476,8 +486,8 @@ int tp_to_nhwc_bf16(const void* src, int src_dtype, int64_t sn, int64_t sc, int6
   cudaStream_t st = (cudaStream_t)stream;
   long long total = (long long)n * h * w * c_pad;
   unsigned grid = (unsigned)min((total + 255) / 256, (long long)sm_count() * 32);
-  if (src_dtype == 0) k_to_nhwc<float><<<grid, 256, 0, st>>>((const float*)src, sn, sc, sh, sw, n, c, h, w, (__nv_bfloat16*)dst, c_pad);
-  else if (src_dtype == 1) k_to_nhwc<__nv_bfloat16><<<grid, 256, 0, st>>>((const __nv_bfloat16*)src, sn, sc, sh, sw, n, c, h, w, (__nv_bfloat16*)dst, c_pad);
+  if (src_dtype == 0) launch(k_to_nhwc<float>, grid, 256, 0, st, (const float*)src, sn, sc, sh, sw, n, c, h, w, (__nv_bfloat16*)dst, c_pad);
+  else if (src_dtype == 1) launch(k_to_nhwc<__nv_bfloat16>, grid, 256, 0, st, (const __nv_bfloat16*)src, sn, sc, sh, sw, n, c, h, w, (__nv_bfloat16*)dst, c_pad);
   else return TP_ERR_INVALID;
   TP_LAUNCH_CHECK();
   return TP_OK;
@@ -489,7 +499,7 @@ int tp_im2col_c8(const void* x, int n, int h, int w, int r, int s, int stride_h,
   cudaStream_t st = (cudaStream_t)stream;
   const long long total = (long long)n * p * q * (kp / 8);
   unsigned grid = (unsigned)min((total + 255) / 256, (long long)sm_count() * 32);
-  k_im2col_c8<<<grid, 256, 0, st>>>((const uint4*)x, n, h, w, r, s, stride_h, stride_w, pad_h, pad_w, p, q, (uint4*)xcol, kp / 8);
+  launch(k_im2col_c8, grid, 256, 0, st, (const uint4*)x, n, h, w, r, s, stride_h, stride_w, pad_h, pad_w, p, q, (uint4*)xcol, kp / 8);
   TP_LAUNCH_CHECK();
   return TP_OK;
 }
@@ -510,9 +520,9 @@ int tp_im2col_stem(const void* src, int src_dtype, int64_t sn, int64_t sc, int64
       const long long strips = (long long)n * p * ((q + QS - 1) / QS);
       const unsigned g2 = (unsigned)min(strips, (long long)sm_count() * 8);
       if (src_dtype == 0)
-        k_im2col_stem_rows<float><<<g2, 256, patch, st>>>((const float*)src, sn, sc, sh, sw, n, c, h, w, r, s, cg, stride_h, stride_w, pad_h, pad_w, p, q, QS, (uint4*)xcol, kp / 8);
+        launch(k_im2col_stem_rows<float>, g2, 256, patch, st, (const float*)src, sn, sc, sh, sw, n, c, h, w, r, s, cg, stride_h, stride_w, pad_h, pad_w, p, q, QS, (uint4*)xcol, kp / 8);
       else if (src_dtype == 1)
-        k_im2col_stem_rows<__nv_bfloat16><<<g2, 256, patch, st>>>((const __nv_bfloat16*)src, sn, sc, sh, sw, n, c, h, w, r, s, cg, stride_h, stride_w, pad_h, pad_w, p, q, QS, (uint4*)xcol, kp / 8);
+        launch(k_im2col_stem_rows<__nv_bfloat16>, g2, 256, patch, st, (const __nv_bfloat16*)src, sn, sc, sh, sw, n, c, h, w, r, s, cg, stride_h, stride_w, pad_h, pad_w, p, q, QS, (uint4*)xcol, kp / 8);
       else return TP_ERR_INVALID;
       TP_LAUNCH_CHECK();
       return TP_OK;
@@ -522,9 +532,9 @@ int tp_im2col_stem(const void* src, int src_dtype, int64_t sn, int64_t sc, int64
   unsigned grid = (unsigned)min((total + 255) / 256, (long long)sm_count() * 32);
   const size_t smem = (size_t)kp * sizeof(uint32_t);
   if (src_dtype == 0)
-    k_im2col_stem<float><<<grid, 256, smem, st>>>((const float*)src, sn, sc, sh, sw, n, c, h, w, r, s, cg, stride_h, stride_w, pad_h, pad_w, p, q, (uint4*)xcol, kp / 8);
+    launch(k_im2col_stem<float>, grid, 256, smem, st, (const float*)src, sn, sc, sh, sw, n, c, h, w, r, s, cg, stride_h, stride_w, pad_h, pad_w, p, q, (uint4*)xcol, kp / 8);
   else if (src_dtype == 1)
-    k_im2col_stem<__nv_bfloat16><<<grid, 256, smem, st>>>((const __nv_bfloat16*)src, sn, sc, sh, sw, n, c, h, w, r, s, cg, stride_h, stride_w, pad_h, pad_w, p, q, (uint4*)xcol, kp / 8);
+    launch(k_im2col_stem<__nv_bfloat16>, grid, 256, smem, st, (const __nv_bfloat16*)src, sn, sc, sh, sw, n, c, h, w, r, s, cg, stride_h, stride_w, pad_h, pad_w, p, q, (uint4*)xcol, kp / 8);
   else return TP_ERR_INVALID;
   TP_LAUNCH_CHECK();
   return TP_OK;
@@ -550,7 +560,7 @@ int tp_sgd_momentum(void* const* w, const void* const* g, void* const* buf, cons
   }
   if (tiles == 0) return TP_OK;
   long long gmax = (long long)sm_count() * 8;
-  k_sgd<<<(unsigned)(tiles < gmax ? tiles : gmax), 256, 0, st>>>(d_segs, n_seg, tiles, lr_dev, momentum, weight_decay, first_step);
+  launch(k_sgd, (unsigned)(tiles < gmax ? tiles : gmax), 256, 0, st, d_segs, n_seg, tiles, lr_dev, momentum, weight_decay, first_step);
   TP_LAUNCH_CHECK();
   return TP_OK;
 }

@@ -19,6 +19,7 @@ __device__ __forceinline__ void unpack8p(const uint4& v, float (&f)[8]) {
 __global__ void __launch_bounds__(256) k_maxpool_fwd(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                      unsigned char* __restrict__ idx, int n, int h, int w, int c,
                                                      int k, int stride, int pad, int p, int q) {
+  pdl_enter();
   const int cv = c >> 3;
   const long long total = (long long)n * p * q * cv;
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -59,6 +60,7 @@ __global__ void __launch_bounds__(256) k_maxpool_fwd(const __nv_bfloat16* __rest
 __global__ void __launch_bounds__(256) k_maxpool_bwd(const __nv_bfloat16* __restrict__ dy, const unsigned char* __restrict__ idx,
                                                      __nv_bfloat16* __restrict__ dx, int n, int h, int w, int c,
                                                      int k, int stride, int pad, int p, int q) {
+  pdl_enter();
   const int cv = c >> 3;
   const long long total = (long long)n * h * w * cv;
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -101,6 +103,7 @@ __global__ void __launch_bounds__(256) k_maxpool_bwd(const __nv_bfloat16* __rest
 // forward per B = 512 step for 1.1 GB of traffic, i.e. 1.1 / 2.4 TB/s).  Same tap order, same arg-max rule, same rounding.
 __global__ void __launch_bounds__(256) k_maxpool_fwd_321(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y,
                                                          unsigned char* __restrict__ idx, int n, int h, int w, int c, int p, int q) {
+  pdl_enter();
   const int cv = c >> 3;
   const long long total = (long long)n * p * q * cv;
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -145,6 +148,7 @@ __global__ void __launch_bounds__(256) k_maxpool_fwd_321(const __nv_bfloat16* __
 
 __global__ void __launch_bounds__(256) k_maxpool_bwd_321(const __nv_bfloat16* __restrict__ dy, const unsigned char* __restrict__ idx,
                                                          __nv_bfloat16* __restrict__ dx, int n, int h, int w, int c, int p, int q) {
+  pdl_enter();
   const int cv = c >> 3;
   const long long total = (long long)n * h * w * cv;
   for (long long i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
@@ -204,10 +208,10 @@ int tp_maxpool_forward(const void* x, void* y, void* idx, int n, int h, int w, i
   const long long total = (long long)n * p * q * (c / 8);
   long long g = (total + 255) / 256, gm = (long long)sm_count() * 16;
   if (k == 3 && stride == 2 && pad == 1)
-    k_maxpool_fwd_321<<<(unsigned)(g < gm ? g : gm), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y,
+    launch(k_maxpool_fwd_321, (unsigned)(g < gm ? g : gm), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, (__nv_bfloat16*)y,
         (unsigned char*)idx, n, h, w, c, p, q);
   else
-    k_maxpool_fwd<<<(unsigned)(g < gm ? g : gm), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)y,
+    launch(k_maxpool_fwd, (unsigned)(g < gm ? g : gm), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)x, (__nv_bfloat16*)y,
         (unsigned char*)idx, n, h, w, c, k, stride, pad, p, q);
   TP_LAUNCH_CHECK();
   return TP_OK;
@@ -220,10 +224,10 @@ int tp_maxpool_backward(const void* dy, const void* idx, void* dx, int n, int h,
   const long long total = (long long)n * h * w * (c / 8);
   long long g = (total + 255) / 256, gm = (long long)sm_count() * 16;
   if (k == 3 && stride == 2 && pad == 1)
-    k_maxpool_bwd_321<<<(unsigned)(g < gm ? g : gm), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const unsigned char*)idx,
+    launch(k_maxpool_bwd_321, (unsigned)(g < gm ? g : gm), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)dy, (const unsigned char*)idx,
         (__nv_bfloat16*)dx, n, h, w, c, p, q);
   else
-    k_maxpool_bwd<<<(unsigned)(g < gm ? g : gm), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const unsigned char*)idx,
+    launch(k_maxpool_bwd, (unsigned)(g < gm ? g : gm), 256, 0, (cudaStream_t)stream, (const __nv_bfloat16*)dy, (const unsigned char*)idx,
         (__nv_bfloat16*)dx, n, h, w, c, k, stride, pad, p, q);
   TP_LAUNCH_CHECK();
   return TP_OK;

@@ -734,6 +734,7 @@ class MaskedConv2dFn(torch.autograd.Function):
         need_db = ctx.has_bias and ctx.needs_input_grad[3]
         dyn = to_nhwc_bf16(dy, ctx.cout_p)
         dx = dw = db = None
+        db_in_slot = False          # the bias gradient already sits in param.grad's arena slot: return None for it
         if ctx.mode == "stem":
             xg, m32 = ctx.saved_tensors
             if need_dw:
@@ -794,6 +795,7 @@ class MaskedConv2dFn(torch.autograd.Function):
                             grad_ready(ws_, bs_ if direct_b else None)
                         _wgrad_keepalive.append((xn, dyn, m32))
                         dw = db = None
+                        db_in_slot = direct_b
                     else:
                         dw, db = conv_wgrad(desc, xn, dyn, m32, cin, need_db, dw_out=ws_ if direct_w else None,
                                             db_out=bs_ if direct_b else None)
@@ -801,8 +803,9 @@ class MaskedConv2dFn(torch.autograd.Function):
                             dw = None
                         if direct_b:
                             db = None
+                            db_in_slot = True
                         grad_ready(ws_ if direct_w else None, bs_ if direct_b else None)
-        if need_db and db is None:
+        if need_db and db is None and not db_in_slot:
             db = dy.float().sum(dim=(0, 2, 3))
         if dskip is not None and dx is None and need_dx is False:
             dx = None
