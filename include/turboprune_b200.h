@@ -210,8 +210,11 @@ size_t tp_conv_dgrad_partial_rows(const tp_conv_desc* d);
 int tp_conv_dgrad_bnrelu(const tp_conv_desc* d, const void* dy, const void* wd, const void* kmask_d,
                          const void* bn_y, const void* bn_weight, const void* bn_bias, const void* bn_mean, const void* bn_invstd,
                          void* g, void* partial, void* stream);
-/* dw[cout][cin_real][r][s] (fp32, OIHW) = mask * conv_wgrad(x, dy); db[cout] = sum dy (optional) */
-int tp_conv_wgrad(const tp_conv_desc* d, const void* x, const void* dy, const void* mask,
+/* dw[cout][cin_real][r][s] (fp32, OIHW) = mask * conv_wgrad(x, dy); db[cout] = sum dy (optional).
+ * kmask_f (optional): the fprop occupancy mask tp_stage_weights produced for THIS mask (a block is marked occupied as soon
+ * as one mask entry under it is non-zero): 128-channel x 256-column output tiles whose blocks are all empty are neither
+ * computed nor read back, their gradient is written as zero — the result is the dense walk's, bit for bit. */
+int tp_conv_wgrad(const tp_conv_desc* d, const void* x, const void* dy, const void* mask, const void* kmask_f,
                   int cin_real, void* dw, void* db, void* ws, size_t ws_bytes, void* stream);
 
 /* tp_bn_forward with the batch statistics supplied by the producing convolution (tp_conv_fprop_stats):

@@ -6,6 +6,7 @@ bf16 (rel. error <= 2^-8 of the tensor's max), dW / db are fp32 (<= 1e-4); losse
 (BASELINE.json north_star)."""
 import hashlib
 import json
+import ctypes
 import os
 
 import numpy as np
@@ -790,6 +791,10 @@ def test_kblock_skipping_bit_identical_to_dense_walk(dev, case):
     m[:, :64, 0, 0] = 0                    # one dead tap for the first channel block
     if cout > 128:
         m[128:, :, k - 1, k - 1] = 0
+    if cout > 128:
+        m[128:192] = 0                     # a whole 128-channel wgrad tile row without a single kept weight
+    if k > 1:
+        m[:, :, 0, 0:2] = 0                # taps (0,0), (0,1) dead everywhere: whole 256-column wgrad tiles are empty
     # occupancy bits vs a direct computation
     cout_p = ops._round_up(cout, 64 if k > 1 else 8)
     wf, wd = ops.stage_weights(w, m, cin, True, cout_p)
@@ -821,6 +826,46 @@ def test_kblock_skipping_bit_identical_to_dense_walk(dev, case):
         assert torch.equal(a, b)
     if cout >= 128:
         assert float(outs[True][0][:, 64:128].abs().max()) == 0.0      # dead filters: exactly zero outputs
+
+
+@pytest.mark.parametrize("case", [(2, 14, 128, 256, 3), (4, 8, 256, 384, 1), (2, 10, 64, 128, 3)])
+def test_wgrad_skips_tiles_under_empty_mask_blocks(dev, case):
+    """tp_conv_wgrad with the occupancy mask: 128-channel x 256-column output tiles whose mask blocks are all zero are
+    neither computed nor read back.  The split-K workspace is poisoned with NaN first: a skipped tile that was read
+    anyway would show; the result equals the dense walk bit for bit and is exactly zero under the dead blocks.  A kept
+    weight that is exactly 0.0 keeps its block alive (the occupancy follows the MASK there, not mask * w)."""
+    from turboprune_b200 import ops
+    n, hw, cin, cout, k = case
+    g = torch.Generator(device=dev).manual_seed(sum(case))
+    x = torch.randn(n, hw, hw, cin, device=dev, generator=g).to(torch.bfloat16)
+    w = torch.randn(cout, cin, k, k, device=dev, generator=g) * 0.05
+    m = (torch.rand(cout, cin, k, k, device=dev, generator=g) < 0.3).float()
+    m[:128, :, 0, 0] = 0                                   # first tile row: tap (0,0) dead (a whole 256-column tile for cin >= 256 ...)
+    if k > 1:
+        m[:128, :, 0, 1] = 0                               # ... and tap (0,1) too: chunks 0..3 empty for cin = 128 as well
+    if cout > 128:
+        m[128:256] = 0                                     # second tile row completely dead
+    w[130:140] = 0.0                                       # zero weights under a zero mask: still empty
+    if cout > 128:
+        m[130, 3, k - 1, k - 1] = 1.0                      # ONE kept weight in the dead tile row, and its value is exactly 0.0:
+                                                           # mask * w is zero everywhere in that block, the block must stay occupied
+    desc = ops.make_desc(n, hw, hw, cin, cout, k, k, (1, 1), (k // 2, k // 2))
+    wf, _ = ops.stage_weights(w, m, cin, False, cout, want_kmask=True)
+    empty, total = ops.kblock_occupancy(wf.kmask, wf.shape[1])
+    assert empty > 0
+    y = ops.conv_fprop(desc, x, wf)
+    dy = torch.randn(y.shape, device=dev, generator=g).to(torch.bfloat16)
+    dense, _ = ops.conv_wgrad(desc, x, dy, m, cin)
+    dense = dense.clone()
+    nbytes = ops._cabi.load().tp_conv_workspace_bytes(ctypes.byref(desc), 2)
+    wsb = ops._workspace(nbytes, x.device, "wgrad")
+    wsb[: wsb.numel() // 4 * 4].view(torch.float32).fill_(float("nan"))
+    skip, _ = ops.conv_wgrad(desc, x, dy, m, cin, kmask=wf.kmask)
+    assert torch.isfinite(skip).all()
+    assert torch.equal(skip, dense)
+    assert float(skip[m == 0].abs().max()) == 0.0
+    if cout > 128:
+        assert float(dense[130, 3, k - 1, k - 1]) != 0.0    # the zero-valued kept weight has a gradient
 
 
 def test_skipped_block_report_on_structured_and_iid_masks(dev):

@@ -67,7 +67,7 @@ SIGNATURES = {
                                      c_void_p, c_void_p, c_void_p]),
     "tp_bn_backward_ext": (c_int, [c_void_p, c_void_p, c_int64, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64,
                                    c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
-    "tp_conv_wgrad": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
+    "tp_conv_wgrad": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p,
                               c_size_t, c_void_p]),
     "tp_sgd_momentum": (c_int, [POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p), POINTER(c_int64), c_int,
                                 c_void_p, c_float, c_float, c_int, c_int, c_void_p, c_size_t, c_void_p]),

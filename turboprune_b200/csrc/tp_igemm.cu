@@ -126,8 +126,21 @@ struct WgParams {
   int base_w, base_h, step_w, step_h;
   int m_tiles, n_tiles, splits, kb_per_split, kblocks;
   float* partial;           // [m_tiles*n_tiles*splits][128][nb*64]
+  const uint32_t* kmask;    // optional: the fprop occupancy mask of this layer's weights ([ceil(Cout/64)][kmask_words] bits over
+  int kmask_words;          // 64-column blocks of (tap, cin)): an output tile whose blocks are all masked out is not computed
   TapEntry taps[kMaxTaps];
 };
+
+// wgrad work item (128 output channels x nvalid 64-column chunks): true when every 64x64 block of it is empty in the
+// occupancy mask, i.e. every mask entry under it is zero (tp_stage_weights marks a block occupied as soon as one mask
+// entry is non-zero) — dW = mask * (...) is zero there whatever the activations are.
+__device__ __forceinline__ bool wg_item_empty(const uint32_t* __restrict__ km, int words, int row_groups, int m_t,
+                                              int chunk0, int nvalid) {
+  for (int r = 2 * m_t; r < 2 * m_t + 2 && r < row_groups; ++r)
+    for (int c = chunk0; c < chunk0 + nvalid; ++c)
+      if ((__ldg(km + (size_t)r * words + (c >> 5)) >> (c & 31)) & 1u) return false;
+  return true;
+}
 
 __device__ __forceinline__ void decompose_pixel(int m, int P, int Q, int& n, int& p, int& q) {
   q = m % Q; int t = m / Q; p = t % P; n = t / P;
@@ -707,6 +720,7 @@ k_igemm_wgrad(const __grid_constant__ CUtensorMap tmA /* dY [Kpix, Cout] */,
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int items = p.m_tiles * p.n_tiles * p.splits;
   const int ncols = p.nb * 64;
+  const int row_groups = (p.Mc + 63) >> 6;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmA); prefetch_tmap(&tmB);
@@ -720,6 +734,7 @@ k_igemm_wgrad(const __grid_constant__ CUtensorMap tmA /* dY [Kpix, Cout] */,
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();
+  const uint32_t* const km = live_kmask(p.kmask, p.kmask_words, p.Mc);     // null: no empty block anywhere (or no mask given)
 
   if (warp == 0) {
     if (lane == 0) {
@@ -735,6 +750,7 @@ k_igemm_wgrad(const __grid_constant__ CUtensorMap tmA /* dY [Kpix, Cout] */,
         const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
         const int chunk0 = n_t * p.nb;
         const int nvalid = min(p.nb, p.chunks - chunk0);
+        if (km && wg_item_empty(km, p.kmask_words, row_groups, m_t, chunk0, nvalid)) continue;   // all three roles skip the same items
         // Everything that needs an integer division is hoisted out of the K loop (one producer thread
         // feeds the whole SM): per-chunk (tap, channel) coordinates once per item, and the pixel
         // coordinate of a K block advanced incrementally by 64 = sn*P*Q + sp*Q + sq.
@@ -779,6 +795,10 @@ k_igemm_wgrad(const __grid_constant__ CUtensorMap tmA /* dY [Kpix, Cout] */,
       int acc = 0; uint32_t acc_phase = 0;
       for (int item = blockIdx.x; item < items; item += gridDim.x) {
         const int split = item / (p.m_tiles * p.n_tiles);
+        if (km) {
+          const int tile = item - split * (p.m_tiles * p.n_tiles), n_t = tile / p.m_tiles, m_t = tile - n_t * p.m_tiles;
+          if (wg_item_empty(km, p.kmask_words, row_groups, m_t, n_t * p.nb, min(p.nb, p.chunks - n_t * p.nb))) continue;
+        }
         const int kb0 = split * p.kb_per_split;
         const int kb1 = min(p.kblocks, kb0 + p.kb_per_split);
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1, 12);
@@ -811,6 +831,10 @@ k_igemm_wgrad(const __grid_constant__ CUtensorMap tmA /* dY [Kpix, Cout] */,
     for (int item = blockIdx.x; item < items; item += gridDim.x) {
       const int ntile = p.m_tiles * p.n_tiles;
       const int split = item / ntile, tile = item - split * ntile;
+      if (km) {
+        const int n_t = tile / p.m_tiles, m_t = tile - n_t * p.m_tiles;
+        if (wg_item_empty(km, p.kmask_words, row_groups, m_t, n_t * p.nb, min(p.nb, p.chunks - n_t * p.nb))) continue;
+      }
       float* prow = p.partial + (((long long)tile * p.splits + split) * kBlockM + quarter * 32 + lane) * ncols;
       mbar_wait(&tfull_bar[acc], acc_phase, 14);
       tc_fence_after();
@@ -842,9 +866,11 @@ k_igemm_wgrad(const __grid_constant__ CUtensorMap tmA /* dY [Kpix, Cout] */,
 // CTA per channel: 18 dependent rounds of L2/DRAM latency for a 3x3x64 layer — 50-80 us for 150 KB of output.)
 __global__ void __launch_bounds__(256) k_wgrad_finalize(const float* __restrict__ partial, const float* __restrict__ mask,
                                                         float* __restrict__ dw, int cout, int cin_real, int cin_p, int rs,
-                                                        int nb, int m_tiles, int n_tiles, int splits, int sl) {
+                                                        int nb, int m_tiles, int n_tiles, int splits, int sl,
+                                                        const uint32_t* __restrict__ kmask, int kmask_words) {
   pdl_enter();
   __shared__ float s_lane[256];
+  const uint32_t* const km = live_kmask(kmask, kmask_words, cout);
   const int co = blockIdx.x;
   const int m_t = co / kBlockM, r = co % kBlockM;
   const int ktot = rs * cin_p;
@@ -854,7 +880,11 @@ __global__ void __launch_bounds__(256) k_wgrad_finalize(const float* __restrict_
   const int kk = blockIdx.y * KT + kl;
   const long long sstride = (long long)kBlockM * ncols;          // floats between consecutive splits of a tile
   float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  if (kk < ktot) {
+  // a work item the GEMM skipped has no partials (the workspace holds whatever was there): its gradient is exactly zero
+  const int chunks = (ktot + 63) >> 6;
+  const bool skipped = km && kk < ktot &&
+                       wg_item_empty(km, kmask_words, (cout + 63) >> 6, m_t, ((kk >> 6) / nb) * nb, min(nb, chunks - ((kk >> 6) / nb) * nb));
+  if (kk < ktot && !skipped) {
     const int chunk = kk >> 6, n_t = chunk / nb, col = (chunk - n_t * nb) * 64 + (kk & 63);
     const float* base = partial + ((((long long)n_t * m_tiles + m_t) * splits) * kBlockM + r) * ncols + col;
     int sp = sj;
@@ -875,7 +905,7 @@ __global__ void __launch_bounds__(256) k_wgrad_finalize(const float* __restrict_
     const int tap = kk / cin_p, ci = kk - tap * cin_p;
     if (ci < cin_real) {
       const long long o = ((long long)co * cin_real + ci) * rs + tap;
-      dw[o] = mask[o] * acc;
+      dw[o] = skipped ? 0.f : mask[o] * acc;
     }
   }
 }
@@ -1332,7 +1362,7 @@ static int conv_dgrad_impl(const tp_conv_desc* d, const void* dy, const void* wd
   return run_fwd(ta, tb, p, bn, st);
 }
 
-int tp_conv_wgrad(const tp_conv_desc* d, const void* x, const void* dy, const void* mask,
+int tp_conv_wgrad(const tp_conv_desc* d, const void* x, const void* dy, const void* mask, const void* kmask_f,
                   int cin_real, void* dw, void* db, void* ws, size_t ws_bytes, void* stream) {
   if (!d || !x || !dy || !mask || !dw || !ws) return TP_ERR_INVALID;
   if (d->cin % 8 != 0 || d->cout % 8 != 0 || d->r * d->s > kMaxTaps || cin_real > d->cin) return TP_ERR_UNSUPPORTED;
@@ -1360,6 +1390,7 @@ int tp_conv_wgrad(const tp_conv_desc* d, const void* x, const void* dy, const vo
   const size_t need = (size_t)p.m_tiles * p.n_tiles * splits * kBlockM * p.nb * 64 * sizeof(float);
   if (ws_bytes < need) return TP_ERR_WORKSPACE;
   p.partial = (float*)ws;
+  p.kmask = (const uint32_t*)kmask_f; p.kmask_words = (int)tp_kblock_mask_words((int64_t)rs * d->cin);
   for (int r = 0; r < d->r; ++r) for (int s = 0; s < d->s; ++s) {
     TapEntry& t = p.taps[r * d->s + s];
     t.off_w = (uint16_t)s; t.off_h = (uint16_t)r; t.kofs = (r * d->s + s) * d->cin;
@@ -1388,7 +1419,8 @@ int tp_conv_wgrad(const tp_conv_desc* d, const void* x, const void* dy, const vo
   const int sl = splits >= 64 ? 8 : (splits >= 32 ? 4 : (splits >= 16 ? 2 : 1));
   const int fin_kt = 256 / sl;
   launch(k_wgrad_finalize, dim3(d->cout, (rs * d->cin + fin_kt - 1) / fin_kt), 256, 0, st, 
-      p.partial, (const float*)mask, (float*)dw, d->cout, cin_real, d->cin, rs, p.nb, p.m_tiles, p.n_tiles, splits, sl);
+      p.partial, (const float*)mask, (float*)dw, d->cout, cin_real, d->cin, rs, p.nb, p.m_tiles, p.n_tiles, splits, sl,
+      p.kmask, p.kmask_words);
   TP_LAUNCH_CHECK();
   if (db) {
     launch(k_colsum, (d->cout + 31) / 32, 256, 0, st, (const __nv_bfloat16*)dy, (long long)p.Kpix, d->cout, d->cout, (float*)db);

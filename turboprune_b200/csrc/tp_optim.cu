@@ -32,7 +32,14 @@ __device__ __forceinline__ void stage_slab(const float* __restrict__ w, const fl
   for (int i = t; i < nco * per_co; i += blockDim.x) {
     const int cl = i / per_co, j = i - cl * per_co;
     const long long gi = ((long long)(co0 + cl) * cin + c0) * rs + j;
-    s_slab[i] = mask[gi] * w[gi];            // utils/mask_layers.py:25 — fp32 product, then bf16 (autocast)
+    const float mk = mask[gi], prod = mk * w[gi];
+    s_slab[i] = prod;                        // utils/mask_layers.py:25 — fp32 product, then bf16 (autocast)
+    // The fprop occupancy mask doubles as the MASK's occupancy for wgrad tile skipping (dW = mask * ... is zero under an
+    // all-zero mask block): a kept weight that happens to be exactly zero must keep its block alive.  Never taken in practice.
+    if (kmf && prod == 0.f && mk != 0.f) {
+      const int c = j / rs, tap = j - c * rs, kb = (tap * cin_p + c0 + c) >> 6;
+      atomicOr(&kmf[(size_t)(co0 >> 6) * kmf_words + (kb >> 5)], 1u << (kb & 31));
+    }
   }
   __syncthreads();
   // wf: per output channel and tap, channels contiguous

@@ -615,9 +615,10 @@ def conv_dgrad_bnrelu(desc, dy_nhwc, wd, bn_src, kmask=None):
     return g, partial
 
 
-def conv_wgrad(desc, x_nhwc, dy_nhwc, mask4d, cin_real, want_db=False, dw_out=None, db_out=None):
+def conv_wgrad(desc, x_nhwc, dy_nhwc, mask4d, cin_real, want_db=False, dw_out=None, db_out=None, kmask=None):
     """``dw_out`` / ``db_out``: write the gradients straight into these (contiguous fp32) buffers — used with the
-    persistent gradient arena so no separate accumulate kernel runs."""
+    persistent gradient arena so no separate accumulate kernel runs.  ``kmask``: the fprop occupancy mask staged for
+    ``mask4d`` (``wf.kmask``): output tiles under all-zero mask blocks are skipped (their gradient is zero)."""
     lib = _cabi.load()
     dev = x_nhwc.device
     dw = dw_out if dw_out is not None else torch.empty(desc.cout, cin_real, desc.r, desc.s, dtype=torch.float32, device=dev)
@@ -625,8 +626,10 @@ def conv_wgrad(desc, x_nhwc, dy_nhwc, mask4d, cin_real, want_db=False, dw_out=No
     nbytes = lib.tp_conv_workspace_bytes(ctypes.byref(desc), 2)
     wsb = _workspace(nbytes, dev, "wgrad")
     with torch.cuda.device(dev), _Timed("wgrad", desc):
+        km = kmask if KBLOCK_SKIP else None
         rc = lib.tp_conv_wgrad(ctypes.byref(desc), c_void_p(x_nhwc.data_ptr()), c_void_p(dy_nhwc.data_ptr()),
-                               c_void_p(mask4d.data_ptr()), cin_real, c_void_p(dw.data_ptr()),
+                               c_void_p(mask4d.data_ptr()), c_void_p(km.data_ptr()) if km is not None else None,
+                               cin_real, c_void_p(dw.data_ptr()),
                                c_void_p(db.data_ptr()) if db is not None else None,
                                c_void_p(wsb.data_ptr()), wsb.numel(), _cabi.stream_ptr(dev))
     _cabi.check(rc, "tp_conv_wgrad")
@@ -704,6 +707,7 @@ class MaskedConv2dFn(torch.autograd.Function):
                     and bn_src[0].shape == xn.shape):
                 ctx.bn_src = bn_src
             ctx.wd_kmask = getattr(wd, "kmask", None) if wd is not None else None     # attributes do not survive save_for_backward
+            ctx.wf_kmask = getattr(wf, "kmask", None)                                  # wgrad skips tiles under all-zero mask blocks
         ctx.desc = desc
         ctx.cin = cin
         ctx.has_bias = bias is not None
@@ -791,14 +795,15 @@ class MaskedConv2dFn(torch.autograd.Function):
                         ev = torch.cuda.Event(); ev.record(cur)
                         side.wait_event(ev)
                         with torch.cuda.stream(side):
-                            conv_wgrad(desc, xn, dyn, m32, cin, need_db, dw_out=ws_, db_out=bs_ if direct_b else None)
+                            conv_wgrad(desc, xn, dyn, m32, cin, need_db, dw_out=ws_, db_out=bs_ if direct_b else None,
+                                       kmask=ctx.wf_kmask)
                             grad_ready(ws_, bs_ if direct_b else None)
                         _wgrad_keepalive.append((xn, dyn, m32))
                         dw = db = None
                         db_in_slot = direct_b
                     else:
                         dw, db = conv_wgrad(desc, xn, dyn, m32, cin, need_db, dw_out=ws_ if direct_w else None,
-                                            db_out=bs_ if direct_b else None)
+                                            db_out=bs_ if direct_b else None, kmask=ctx.wf_kmask)
                         if direct_w:
                             dw = None
                         if direct_b:
