@@ -46,7 +46,7 @@ struct SelState {
 
 constexpr int kSampleBits = 20;
 constexpr int kSweepThreads = 256;
-constexpr int kSmemCand = 1024;
+constexpr int kSmemCand = 2048;       // candidate staging per CTA (16 KB: the sample-key array, dead by then)
 
 template <int KIND>
 __device__ __forceinline__ unsigned int score_key(float w, float g, float m) {
@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(kSweepThreads) k_topk_fused(const TopkArgs a) 
   __shared__ __align__(16) Seg s_seg[kSmemSegs];        // the segment table (evicted from L2 by whatever ran before: every binary-search
                                                         // step of every thread was a DRAM round trip when it was read from global)
   uint2* const s_cand = reinterpret_cast<uint2*>(s_keys);             // kSmemCand * 8 B <= sizeof(s_keys); the sample keys are dead by P2
-  __shared__ unsigned int s_ncand;
+  __shared__ unsigned int s_ncand, s_flush[2];
   __shared__ unsigned long long s_base;
   __shared__ unsigned int s_red[2][kSweepThreads / 32];
   __shared__ unsigned int s_bin[2];
@@ -299,9 +299,26 @@ __global__ void __launch_bounds__(kSweepThreads) k_topk_fused(const TopkArgs a) 
   for (int i = t; i < kDigitBins; i += kSweepThreads) s_h[i] = 0;
   __syncthreads();
   constexpr int kVecIters = kTileElems / (kSweepThreads * 4);   // 4
-  for (long long tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
+  // Candidates collect in shared memory ACROSS tiles and go out once per CTA (a CTA sees a few hundred of them in total);
+  // the staging is emptied early only when it is half full.  The first version reserved the global slots after every tile:
+  // one global atomic round trip (~1 us) with the whole CTA waiting behind it, and three barriers, per 48 KB of data.
+  auto flush_cands = [&]() {                               // uniform over the CTA; caller has synchronised
+    const unsigned int nc = s_ncand < (unsigned)kSmemCand ? s_ncand : (unsigned)kSmemCand;   // slots past the staging went to global directly
+    if (nc) {
+      if (t == 0) s_base = atomicAdd(&st->n_cand, (unsigned long long)nc);
+      __syncthreads();
+      const unsigned long long b = s_base;
+      for (unsigned int i = t; i < nc; i += kSweepThreads)
+        if (b + i < a.cap) a.cand[b + i] = s_cand[i];
+    }
+    __syncthreads();
     if (t == 0) s_ncand = 0;
     __syncthreads();
+  };
+  if (t == 0) s_ncand = 0;
+  __syncthreads();
+  int sweep_it = 0;
+  for (long long tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
     const int si = find_seg(segs, a.n_seg, tile);
     const Seg sg = segs[si];
     const long long base = (tile - sg.tile0) * kTileElems;
@@ -342,17 +359,14 @@ __global__ void __launch_bounds__(kSweepThreads) k_topk_fused(const TopkArgs a) 
         if (WRITE) op[i] = o;
       }
     }
+    // the early-flush decision must be the same in every thread: thread 0 publishes its view BEFORE the barrier (slots of
+    // alternating parity: a slot is rewritten two barriers after it was read), late atomics of this tile only make it conservative
+    if (t == 0) s_flush[sweep_it & 1] = s_ncand >= (unsigned)(kSmemCand / 2) ? 1u : 0u;
     __syncthreads();
-    unsigned int nc = s_ncand < (unsigned)kSmemCand ? s_ncand : (unsigned)kSmemCand;
-    if (nc) {
-      if (t == 0) s_base = atomicAdd(&st->n_cand, (unsigned long long)nc);
-      __syncthreads();
-      unsigned long long b = s_base;
-      for (unsigned int i = t; i < nc; i += kSweepThreads)
-        if (b + i < a.cap) a.cand[b + i] = s_cand[i];
-    }
-    __syncthreads();
+    if (s_flush[sweep_it & 1]) flush_cands();
+    ++sweep_it;
   }
+  flush_cands();
   {  // block-reduce the two counters, one atomic pair per CTA
     unsigned int x = c.n_lt, y = c.n_eq;
     for (int o = 16; o; o >>= 1) { x += __shfl_xor_sync(0xffffffffu, x, o); y += __shfl_xor_sync(0xffffffffu, y, o); }
