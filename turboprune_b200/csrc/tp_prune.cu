@@ -252,6 +252,9 @@ __global__ void __launch_bounds__(kSweepThreads) k_topk_fused(const TopkArgs a) 
       *reinterpret_cast<uint4*>(&s_keys[((r * kSweepThreads + t) * kRun) + 4 * q]) = make_uint4(key[4 * q], key[4 * q + 1], key[4 * q + 2], key[4 * q + 3]);
   }
   __syncthreads();
+  // (Tried: asking the L2 for this CTA's first 2-8 sweep tiles here with cp.async.bulk.prefetch.L2 while the sample is being
+  // resolved.  The sweep got 2-8 us shorter, but this phase 4-21 us longer — the histogram atomics and the grid barrier
+  // queue behind the prefetch traffic.  profiles/r02_notes.md.)
   for (int i = t; i < kDigitBins; i += kSweepThreads) if (s_h[i]) atomicAdd(&hist_c[i], s_h[i]);
   grid.sync();
   stamp(st, 1);
