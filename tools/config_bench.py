@@ -39,6 +39,7 @@ def _harness(cfg, model, batch):
 
 
 def _throughput(h, batch, steps=20, warmup=6):
+    steps = int(os.environ.get("TP_CFG_STEPS", steps)); warmup = int(os.environ.get("TP_CFG_WARMUP", warmup))   # short runs under ncu
     it = iter(h.train_loader)
     b0 = next(it)
     for _ in range(warmup):

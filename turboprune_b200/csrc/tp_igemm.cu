@@ -910,23 +910,67 @@ __global__ void __launch_bounds__(256) k_wgrad_finalize(const float* __restrict_
   }
 }
 
-// db[c] = sum over pixels of dy[pix][c]  (bias gradient), dy bf16 [npix, ldc]
-__global__ void __launch_bounds__(256) k_colsum(const __nv_bfloat16* __restrict__ dy, long long npix, int c, int ldc,
-                                                float* __restrict__ db) {
+// db[c] = sum over pixels of dy[pix][c]  (bias gradient), dy bf16 [npix, ldc], c % 8 == 0.
+// Two stages, both in fixed order (deterministic): every CTA of a (pixel split x channel tile) grid sums its pixels — a thread
+// owns one 16-byte vector of 8 channels and walks the pixel axis, 4 rows in flight — into part[split][c]; a small kernel
+// folds the splits.  (The first version ran ONE CTA per 32 channels over all pixels with 2-byte loads: 200 us per layer —
+// 41 % of the DeiT-S step, profiles/r02_launches_deit_B64.md.)
+__global__ void __launch_bounds__(256) k_colsum_part(const __nv_bfloat16* __restrict__ dy, long long npix, int c, int ldc,
+                                                     float* __restrict__ part) {
   pdl_enter();
-  // one CTA per 32 channels; threads (32 x 8): 8 pixel lanes, fixed-order tree -> deterministic
-  __shared__ float s[8][33];
-  const int cx = threadIdx.x & 31, py = threadIdx.x >> 5;
-  const int ch = blockIdx.x * 32 + cx;
-  float acc = 0.f;
-  if (ch < c) for (long long i = py; i < npix; i += 8) acc += __bfloat162float(dy[i * ldc + ch]);
-  s[py][cx] = acc;
-  __syncthreads();
-  if (py == 0 && ch < c) {
-    float t = 0.f;
-    for (int j = 0; j < 8; ++j) t += s[j][cx];
-    db[ch] = t;
+  __shared__ float s_acc[256][9];
+  const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
+  const int cvec = blockIdx.y * TX + tx;
+  const bool act = cvec * 8 < c;
+  float a[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = 0.f;
+  auto add8 = [&](const uint4& v) {
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { const float2 f = __bfloat1622float2(h[i]); a[2 * i] += f.x; a[2 * i + 1] += f.y; }
+  };
+  if (act) {
+    const long long stride = (long long)gridDim.x * TY;
+    long long p = (long long)blockIdx.x * TY + ty;
+    const __nv_bfloat16* src = dy + (size_t)cvec * 8;
+    for (; p + 3 * stride < npix; p += 4 * stride) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) v[u] = *reinterpret_cast<const uint4*>(src + (size_t)(p + u * stride) * ldc);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) add8(v[u]);
+    }
+    for (; p < npix; p += stride) add8(*reinterpret_cast<const uint4*>(src + (size_t)p * ldc));
   }
+  const int tid = ty * TX + tx;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s_acc[tid][i] = a[i];
+  __syncthreads();
+  if (ty == 0 && act) {
+    float r[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) r[i] = 0.f;
+    for (int j = 0; j < TY; ++j)
+#pragma unroll
+      for (int i = 0; i < 8; ++i) r[i] += s_acc[j * TX + tx][i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) part[(size_t)blockIdx.x * c + cvec * 8 + i] = r[i];
+  }
+}
+
+__global__ void __launch_bounds__(256) k_colsum_fold(const float* __restrict__ part, int nparts, int c, float* __restrict__ db) {
+  pdl_enter();
+  const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+  if (ch >= c) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  int j = 0;
+  for (; j + 3 < nparts; j += 4) {                    // four independent chains, combined in a fixed order
+    s0 += part[(size_t)j * c + ch]; s1 += part[(size_t)(j + 1) * c + ch];
+    s2 += part[(size_t)(j + 2) * c + ch]; s3 += part[(size_t)(j + 3) * c + ch];
+  }
+  for (; j < nparts; ++j) s0 += part[(size_t)j * c + ch];
+  db[ch] = (s0 + s1) + (s2 + s3);
 }
 
 // ============================================================================================
@@ -1423,7 +1467,19 @@ int tp_conv_wgrad(const tp_conv_desc* d, const void* x, const void* dy, const vo
       p.kmask, p.kmask_words);
   TP_LAUNCH_CHECK();
   if (db) {
-    launch(k_colsum, (d->cout + 31) / 32, 256, 0, st, (const __nv_bfloat16*)dy, (long long)p.Kpix, d->cout, d->cout, (float*)db);
+    // the split-K partials are dead once the finalize above has run (same stream): the workspace holds the column partials now
+    const int c = d->cout, cv = c / 8;
+    int tx = 1;
+    while (tx < cv && tx < 256) tx <<= 1;
+    const int ty = 256 / tx, ctiles = (cv + tx - 1) / tx;
+    long long gx = ((long long)p.Kpix + (long long)ty * 4 - 1) / ((long long)ty * 4);          // >= 4 pixel rows per thread
+    const long long want = (long long)sms * 4 / ctiles, fit = (long long)(ws_bytes / ((size_t)c * sizeof(float)));
+    if (gx > want) gx = want;
+    if (gx > fit) gx = fit;
+    if (gx < 1) gx = 1;
+    if ((((uintptr_t)dy) & 15) != 0) return TP_ERR_INVALID;
+    launch(k_colsum_part, dim3((unsigned)gx, (unsigned)ctiles), dim3(tx, ty), 0, st, (const __nv_bfloat16*)dy, (long long)p.Kpix, c, c, (float*)ws);
+    launch(k_colsum_fold, (c + 255) / 256, 256, 0, st, (const float*)ws, (int)gx, c, (float*)db);
     TP_LAUNCH_CHECK();
   }
   return TP_OK;

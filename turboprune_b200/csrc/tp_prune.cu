@@ -137,7 +137,7 @@ __device__ __forceinline__ float classify(SweepCtx& c, unsigned int key, long lo
     unsigned long long gs = atomicAdd(&c.st->n_cand, 1ull);
     if (gs < c.cap) c.cand[gs] = make_uint2(key, (unsigned int)gidx);
   }
-  return 0.f;   // provisional; k_resolve patches it
+  return 0.f;   // provisional; the last phase of the kernel patches it
 }
 
 constexpr int kRun = 16;               // neighbouring elements per sample run
